@@ -1,0 +1,219 @@
+"""ctypes front end of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package
+``aboria_b200`` never does.  See the header of ``aboria_oracle.cpp``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+K_CONST_SUM, K_CONST_SUM_DIFF, K_INV_DIST, K_INV_DIST_AA = 0, 1, 2, 3
+K_WENDLAND_C2, K_LJ_FORCE, K_SPH_DENSITY, K_SPH_PRESSURE = 4, 5, 6, 7
+
+SORT_STD, SORT_STABLE = 0, 1
+
+
+def build():
+    """Compile liboracle with the committed Makefile (g++ only)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libaboria_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        vp, dp, u8p, ip, up = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int), C.POINTER(C.c_uint)
+        L.orc_create.restype = vp
+        L.orc_create.argtypes = [C.c_int]
+        L.orc_destroy.argtypes = [vp]
+        L.orc_collapse_index_vector.restype = C.c_int
+        L.orc_collapse_index_vector.argtypes = [C.c_int, up, ip]
+        L.orc_set_domain.argtypes = [vp, dp, dp, u8p, C.c_double]
+        L.orc_force_grid.argtypes = [vp, dp, dp, u8p, up]
+        L.orc_get_grid.argtypes = [vp, up, dp]
+        L.orc_point_to_bucket_index.restype = C.c_int
+        L.orc_point_to_bucket_index.argtypes = [vp, dp, ip]
+        L.orc_update_positions.restype = C.c_long
+        L.orc_update_positions.argtypes = [vp, dp, u8p, C.c_size_t, C.c_int]
+        L.orc_num_buckets.restype = C.c_size_t
+        L.orc_num_buckets.argtypes = [vp]
+        L.orc_get_build.argtypes = [vp, ip, up, up, up]
+        L.orc_gather.argtypes = [ip, C.c_size_t, vp, vp, C.c_size_t]
+        L.orc_update_iterators.argtypes = [vp, dp, C.c_size_t]
+        L.orc_buckets_near_point.restype = C.c_long
+        L.orc_buckets_near_point.argtypes = [vp, dp, C.c_double, ip, C.c_long]
+        L.orc_search_point.restype = C.c_long
+        L.orc_search_point.argtypes = [vp, dp, C.c_double, ip, ip, dp, C.c_long]
+        L.orc_pair_stats.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_sparse_matvec.restype = C.c_uint64
+        L.orc_sparse_matvec.argtypes = [vp, dp, C.c_size_t, C.c_int, dp, C.POINTER(dp), C.POINTER(dp), C.c_double, dp, C.c_int, C.c_int, dp, dp, C.c_int]
+        L.orc_brute_force_counts.argtypes = [C.c_int, dp, C.c_size_t, dp, dp, C.c_int, C.c_double, C.POINTER(C.c_uint32)]
+        L.orc_max_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def collapse_index_vector(size, v):
+    size = np.ascontiguousarray(size, dtype=np.uint32)
+    v = np.ascontiguousarray(v, dtype=np.int32)
+    return lib().orc_collapse_index_vector(len(size), size.ctypes.data_as(C.POINTER(C.c_uint)), v.ctypes.data_as(C.POINTER(C.c_int)))
+
+
+def brute_force_counts(pos, bmin, bmax, periodic, r):
+    pos = _f64(pos)
+    n, D = pos.shape
+    out = np.zeros(n, dtype=np.uint32)
+    bmin, bmax = _f64(bmin), _f64(bmax)
+    lib().orc_brute_force_counts(D, _dp(pos), n, _dp(bmin), _dp(bmax), int(bool(periodic)), float(r) * float(r), out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out
+
+
+class Oracle:
+    """Mirror of Particles<...,CellListOrdered> + create_sparse_operator for one
+    column particle set (positions only + caller-held variable columns)."""
+
+    def __init__(self, D):
+        self.D = D
+        self.h = lib().orc_create(D)
+        if not self.h:
+            raise ValueError("bad dimension")
+        self.pos = None  # sorted positions kept alive here
+        self.order = None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def _dom(self, bmin, bmax, periodic):
+        bmin = _f64(np.broadcast_to(bmin, (self.D,)))
+        bmax = _f64(np.broadcast_to(bmax, (self.D,)))
+        per = np.ascontiguousarray(np.broadcast_to(periodic, (self.D,)), dtype=np.uint8)
+        return bmin, bmax, per
+
+    def set_domain(self, bmin, bmax, periodic, n_leaf=10.0):
+        bmin, bmax, per = self._dom(bmin, bmax, periodic)
+        lib().orc_set_domain(self.h, _dp(bmin), _dp(bmax), per.ctypes.data_as(C.POINTER(C.c_uint8)), float(n_leaf))
+
+    def force_grid(self, bmin, bmax, periodic, size):
+        bmin, bmax, per = self._dom(bmin, bmax, periodic)
+        size = np.ascontiguousarray(np.broadcast_to(size, (self.D,)), dtype=np.uint32)
+        lib().orc_force_grid(self.h, _dp(bmin), _dp(bmax), per.ctypes.data_as(C.POINTER(C.c_uint8)), size.ctypes.data_as(C.POINTER(C.c_uint)))
+
+    def grid(self):
+        size = np.zeros(self.D, dtype=np.uint32)
+        side = np.zeros(self.D, dtype=np.float64)
+        lib().orc_get_grid(self.h, size.ctypes.data_as(C.POINTER(C.c_uint)), _dp(side))
+        return size, side
+
+    def point_to_bucket_index(self, r):
+        r = _f64(r)
+        v = np.zeros(self.D, dtype=np.int32)
+        idx = lib().orc_point_to_bucket_index(self.h, _dp(r), v.ctypes.data_as(C.POINTER(C.c_int)))
+        return idx, v
+
+    def update_positions(self, pos, alive=None, sort_mode=SORT_STABLE):
+        """pos (n,D) float64 is wrapped in place, alive (n,) uint8 updated in
+        place.  Returns dict(order, keys, bucket_begin, bucket_end, n_alive)."""
+        assert pos.dtype == np.float64 and pos.flags.c_contiguous and pos.shape[1] == self.D
+        n = pos.shape[0]
+        if alive is None:
+            alive = np.ones(n, dtype=np.uint8)
+        assert alive.dtype == np.uint8 and alive.flags.c_contiguous
+        na = lib().orc_update_positions(self.h, _dp(pos), alive.ctypes.data_as(C.POINTER(C.c_uint8)), n, sort_mode)
+        nb = lib().orc_num_buckets(self.h)
+        order = np.zeros(na, dtype=np.int32)
+        keys = np.zeros(na, dtype=np.uint32)
+        bb = np.zeros(nb, dtype=np.uint32)
+        be = np.zeros(nb, dtype=np.uint32)
+        ip, up = C.POINTER(C.c_int), C.POINTER(C.c_uint)
+        lib().orc_get_build(self.h, order.ctypes.data_as(ip), keys.ctypes.data_as(up), bb.ctypes.data_as(up), be.ctypes.data_as(up))
+        return dict(order=order, keys=keys, bucket_begin=bb, bucket_end=be, n_alive=int(na), alive=alive)
+
+    @staticmethod
+    def gather(order, col):
+        col = np.ascontiguousarray(col)
+        out = np.empty((len(order),) + col.shape[1:], dtype=col.dtype)
+        eb = col.dtype.itemsize * int(np.prod(col.shape[1:], dtype=np.int64))
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        lib().orc_gather(order.ctypes.data_as(C.POINTER(C.c_int)), len(order), col.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), eb)
+        return out
+
+    def init_neighbour_search(self, pos, bmin, bmax, periodic, n_leaf=10.0, alive=None, sort_mode=SORT_STABLE):
+        """src/Particles.h:445-455: set_domain, update_positions, reorder.
+        Returns the build dict plus 'pos' (reordered positions)."""
+        pos = np.array(pos, dtype=np.float64, order="C", copy=True)
+        self.set_domain(bmin, bmax, periodic, n_leaf)
+        out = self.update_positions(pos, alive, sort_mode)
+        self.pos = self.gather(out["order"], pos)
+        self.order = out["order"]
+        lib().orc_update_iterators(self.h, _dp(self.pos), self.pos.shape[0])
+        out["pos"] = self.pos
+        return out
+
+    def update_iterators(self, pos_sorted):
+        self.pos = _f64(pos_sorted)
+        lib().orc_update_iterators(self.h, _dp(self.pos), self.pos.shape[0])
+
+    def buckets_near_point(self, point, r, max_out=4096):
+        point = _f64(point)
+        out = np.zeros((max_out, self.D), dtype=np.int32)
+        c = lib().orc_buckets_near_point(self.h, _dp(point), float(r), out.ctypes.data_as(C.POINTER(C.c_int)), max_out)
+        return int(c), out[: min(c, max_out)]
+
+    def search_point(self, point, r, max_out=65536):
+        point = _f64(point)
+        j = np.zeros(max_out, dtype=np.int32)
+        im = np.zeros(max_out, dtype=np.int32)
+        dx = np.zeros((max_out, self.D), dtype=np.float64)
+        ip = C.POINTER(C.c_int)
+        c = lib().orc_search_point(self.h, _dp(point), float(r), j.ctypes.data_as(ip), im.ctypes.data_as(ip), _dp(dx), max_out)
+        m = min(c, max_out)
+        return int(c), j[:m], im[:m], dx[:m]
+
+    def pair_stats(self, row_pos, radius, radius_per_row=None):
+        row_pos = _f64(row_pos)
+        n = row_pos.shape[0]
+        cnt = np.zeros(n, dtype=np.uint32)
+        hs = np.zeros(n, dtype=np.uint64)
+        rpr = _f64(radius_per_row) if radius_per_row is not None else None
+        lib().orc_pair_stats(self.h, _dp(row_pos), n, float(radius), _dp(rpr), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), hs.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return cnt, hs
+
+    def sparse_matvec(self, row_pos, kernel_id, params, radius, b, BR=1, BC=1, row_vars=(), col_vars=(), radius_per_row=None, y=None, nthreads=0):
+        """y += K b (src/Kernels.h:720-751).  Returns (y, n_pairs)."""
+        row_pos = _f64(row_pos)
+        n_rows = row_pos.shape[0]
+        params = _f64(params if len(params) else [0.0])
+        b = _f64(b)
+        if y is None:
+            y = np.zeros(n_rows * BR, dtype=np.float64)
+        rv = [_f64(v) for v in row_vars]
+        cv = [_f64(v) for v in col_vars]
+        dpp = C.POINTER(C.c_double)
+        RV = (dpp * max(1, len(rv)))(*[_dp(v) for v in rv])
+        CV = (dpp * max(1, len(cv)))(*[_dp(v) for v in cv])
+        rpr = _f64(radius_per_row) if radius_per_row is not None else None
+        npairs = lib().orc_sparse_matvec(self.h, _dp(row_pos), n_rows, int(kernel_id), _dp(params), RV, CV, float(radius), _dp(rpr), BR, BC, _dp(b), _dp(y), int(nthreads))
+        return y, int(npairs)
+
+
+def max_threads():
+    return lib().orc_max_threads()

@@ -1,0 +1,184 @@
+"""Pins the CPU oracle against the reference's own known-answer tests
+(SURVEY.md §4 / §8c).  Each test cites the reference test it ports."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+def test_bucket_indicies():
+    # tests/utils.h:52-74
+    assert orc.collapse_index_vector([4, 7, 2], [1, 2, 1]) == 19
+    assert orc.collapse_index_vector([4, 7, 1, 6], [1, 2, 0, 4]) == 58
+
+
+def test_point_to_bucket_indicies():
+    # tests/utils.h:76-93
+    o = orc.Oracle(3)
+    o.force_grid(0.0, 1.0, False, 5)
+    idx, v = o.point_to_bucket_index([0.5, 0.5, 0.5])
+    assert list(v) == [2, 2, 2]
+    assert idx == 2 * 5 * 5 + 2 * 5 + 2
+
+
+def test_lattice_within_distance_1d():
+    # tests/iterators.h:49-116 (100 particles, n_leaf 10 -> 10 buckets)
+    rng = np.random.default_rng(0)
+    o = orc.Oracle(1)
+    o.init_neighbour_search(rng.random((100, 1)), 0.0, 1.0, False)
+    size, side = o.grid()
+    assert list(size) == [10]
+    for point, r, expect in [(0.5, 0.05, 2), (0.5, 0.15, 4), (0.1, 0.15, 3), (-0.1, 0.05, 0), (-0.1, 0.15, 1)]:
+        assert o.buckets_near_point([point], r)[0] == expect
+
+
+def test_lattice_within_distance_2d():
+    # tests/iterators.h:118-211 (1000 particles -> 10 x 10 buckets)
+    rng = np.random.default_rng(1)
+    o = orc.Oracle(2)
+    o.init_neighbour_search(rng.random((1000, 2)), 0.0, 1.0, False)
+    size, side = o.grid()
+    assert list(size) == [10, 10]
+    cases = [((0.5, 0.5), 0.05, 4), ((0.5, 0.5), 0.1001, 12), ((0.55, 0.55), 0.1001, 9), ((0.55, 0.55), 0.049999, 1),
+             ((-0.001, 0.001), 2.0, 100), ((-0.001, 0.001), 0.01, 1), ((1.001, 1.001), 0.01, 1)]
+    for point, r, expect in cases:
+        assert o.buckets_near_point(point, r)[0] == expect, (point, r)
+
+
+def test_single_particle():
+    # tests/neighbours.h:520-557
+    radius = 0.1
+    o = orc.Oracle(3)
+    o.init_neighbour_search([[0.0, 0.0, 0.0]], -1.0, 1.0, True)
+    assert o.search_point([radius / 2, radius / 2, 0], radius)[0] == 1
+    assert o.search_point([2 * radius, 0, 0], radius)[0] == 0
+
+
+def test_two_particles():
+    # tests/neighbours.h:559-605
+    radius = 0.1
+    o = orc.Oracle(3)
+    out = o.init_neighbour_search([[0.0, 0.0, 0.0], [radius / 2, 0, 0]], -1.0, 1.0, True)
+    c, j, im, dx = o.search_point([1.1 * radius, 0, 0], radius)
+    assert c == 1 and out["order"][j[0]] == 1  # found particle has id 1
+    assert o.search_point([0.9 * radius, 0, 0], radius)[0] == 2
+    assert o.search_point([1.6 * radius, 0, 0], radius)[0] == 0
+    assert o.search_point([0.25 * radius, 0.9 * radius, 0], radius)[0] == 2
+    assert o.search_point([0.25 * radius, 0.99 * radius, 0], radius)[0] == 0
+
+
+def _lattice(D, n):
+    # tests/neighbours.h:641-661: pos = index*dx + min + dx/2, first index fastest
+    idx = np.indices((n,) * D).reshape(D, -1).T[:, ::-1]
+    return idx.astype(np.float64) * 1.0 + 0.0 + 0.5
+
+
+@pytest.mark.parametrize("D,n,r,nn", [(1, 100, 1.5, 10), (2, 50, 1.0001, 10), (2, 50, 1.5, 10), (2, 20, 2.1, 10), (3, 10, 1.9, 10), (3, 10, 1.0001, 10)])
+def test_helper_d_regular(D, n, r, nn):
+    # tests/neighbours.h:627-686 with the case list :1252-1260 (L2 part: the
+    # Gauss circle count in 2-D; in other D compared with brute force)
+    pos = _lattice(D, n)
+    o = orc.Oracle(D)
+    out = o.init_neighbour_search(pos, 0.0, float(n), True, nn)
+    cnt, _ = o.pair_stats(out["pos"], r)
+    if D == 2:
+        n_expect = 0
+        for i in range(100):
+            n_expect += int(np.floor(r**2 / (4 * i + 1))) - int(np.floor(r**2 / (4 * i + 3)))
+        n_expect = 1 + 4 * n_expect
+        assert n_expect == {1.0001: 5, 1.5: 9, 2.1: 13}[r]
+        assert np.all(cnt == n_expect)
+    brute = orc.brute_force_counts(out["pos"], [0.0] * D, [float(n)] * D, True, r)
+    assert np.array_equal(cnt, brute)
+
+
+@pytest.mark.parametrize("D,N,r,nn,periodic", [
+    (1, 14, 0.1, 1, False), (1, 14, 0.1, 1, True), (1, 1000, 0.1, 10, True), (1, 1000, 0.1, 10, False),
+    (1, 1000, 0.1, 100, True), (1, 1000, 0.1, 100, False), (2, 1000, 0.5, 10, True), (2, 1000, 0.5, 10, False),
+    (2, 1000, 0.2, 1, True), (2, 1000, 0.2, 1, False), (3, 1000, 0.2, 100, True), (3, 1000, 0.2, 100, False),
+    (3, 1000, 0.2, 10, True), (3, 1000, 0.2, 10, False), (3, 1000, 0.2, 1, True), (3, 1000, 0.2, 1, False)])
+@pytest.mark.parametrize("sort_mode", [orc.SORT_STD, orc.SORT_STABLE])
+def test_helper_d_random(D, N, r, nn, periodic, sort_mode):
+    # tests/neighbours.h:968-1147 with cases :1273-1327 (IdentityTransform);
+    # positions are float32 values in [-1,1) as in the reference (:1000-1004)
+    rng = np.random.default_rng(1234 + D * 100 + N + int(periodic))
+    pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+    o = orc.Oracle(D)
+    out = o.init_neighbour_search(pos, -1.0, 1.0, periodic, nn, sort_mode=sort_mode)
+    assert out["n_alive"] == N
+    cnt, _ = o.pair_stats(out["pos"], r)
+    brute = orc.brute_force_counts(out["pos"], [-1.0] * D, [1.0] * D, periodic, r)
+    assert np.array_equal(cnt, brute)
+    # helper_data_structure (tests/data_structures.h:326-393): every particle lies
+    # in its bucket; bucket ranges partition the sorted array
+    bb, be, keys = out["bucket_begin"], out["bucket_end"], out["keys"]
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)
+    assert int((be.astype(np.int64) - bb).sum()) == N
+    for c in np.unique(keys):
+        assert np.all(keys[bb[c]:be[c]] == c)
+    # the two sort modes agree on everything but the within-cell order
+    assert sorted(out["order"].tolist()) == list(range(N))
+
+
+def test_sparse_operator_golden():
+    # tests/operators.h:810-933
+    diameter = 0.1
+    pos = np.array([[0, 0, 0], [diameter * 0.9, 0, 0], [diameter * 1.8, 0, 0]], dtype=np.float64)
+    o = orc.Oracle(3)
+    out = o.init_neighbour_search(pos, -1.0, 1.0, False)
+    order = out["order"]
+    s1 = np.full(3, 1.0)
+    s2 = np.full(3, 2.0)
+    v = np.array([1.0, 2.0, 3.0])
+    # Eigen vectors are indexed by post-reorder position
+    y, npairs = o.sparse_matvec(out["pos"], orc.K_CONST_SUM, [], diameter, v, row_vars=[s1], col_vars=[s2])
+    assert npairs == 7  # C_sparse.nonZeros() == 7
+    ids = order
+    expect = np.zeros(3)
+    for i in range(3):
+        for j in range(3):
+            if {int(ids[i]), int(ids[j])} == {0, 2}:
+                continue
+            expect[i] += 3.0 * v[j]
+    assert np.array_equal(y, expect)
+    if list(ids) == [0, 1, 2]:
+        assert list(y) == [9.0, 18.0, 15.0]
+    y2, npairs2 = o.sparse_matvec(out["pos"], orc.K_CONST_SUM_DIFF, [], diameter, v, BR=2, BC=1, row_vars=[s1], col_vars=[s2])
+    assert npairs2 == 7  # 14 scalar non-zeros
+    if list(ids) == [0, 1, 2]:
+        # the reference asserts only the first n=3 entries of its `check`
+        # vector {9,-3,18,-7,15,-5} (tests/operators.h:928-931); the 4th entry
+        # is a typo in the reference (-1-2-3 = -6) that is never compared.
+        assert list(y2[:3]) == [9.0, -3.0, 18.0]
+        assert list(y2) == [9.0, -3.0, 18.0, -6.0, 15.0, -5.0]
+
+
+def test_documentation_operator():
+    # tests/operators.h:121-311: N=100 uniform in the unit cube, eps=0.1,
+    # r=0.1, kernel a_i a_j/(|dx|+eps): K_s*b equals the assembled matrix * b
+    N, eps, r = 100, 0.1, 0.1
+    rng = np.random.default_rng(7)
+    pos = rng.random((N, 3))
+    a = rng.random(N)
+    o = orc.Oracle(3)
+    out = o.init_neighbour_search(pos, 0.0, 1.0, False)
+    ps, as_ = out["pos"], a[out["order"]]
+    b = np.linspace(0, 1.0, N)
+    y, _ = o.sparse_matvec(ps, orc.K_INV_DIST_AA, [eps], r, b, row_vars=[as_], col_vars=[as_])
+    dx = ps[None, :, :] - ps[:, None, :]
+    d2 = (dx[..., 0] * dx[..., 0] + dx[..., 1] * dx[..., 1]) + dx[..., 2] * dx[..., 2]
+    K = np.where(d2 <= r * r, (as_[:, None] * as_[None, :]) / (np.sqrt(d2) + eps), 0.0)
+    assert np.allclose(y, K @ b, rtol=1e-13, atol=0)
+
+
+def test_enforce_domain_and_dead():
+    # src/NeighbourSearchBase.h:185-238: periodic wrap, non-periodic kill, non-finite kill
+    pos = np.array([[1.25, 0.5], [-0.25, 0.5], [0.5, 1.5], [0.5, np.nan], [0.1, 0.2], [3.75, 0.999]], dtype=np.float64)
+    o = orc.Oracle(2)
+    o.set_domain([0.0, 0.0], [1.0, 1.0], [True, False], 1.0)
+    p = pos.copy()
+    out = o.update_positions(p)
+    assert list(out["alive"]) == [1, 1, 0, 0, 1, 1]
+    assert p[0, 0] == 0.25 and p[1, 0] == 0.75 and p[5, 0] == 0.75
+    assert sorted(out["order"].tolist()) == [0, 1, 4, 5]
+    assert out["n_alive"] == 4
