@@ -1,0 +1,317 @@
+// C-ABI entry points of libabr.so (declared in include/abr.h).
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "abr_internal.h"
+
+namespace abr {
+
+int set_error(Handle *h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  return code;
+}
+int check_cuda(Handle *h, cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return ABR_OK;
+  if (h) h->err = std::string(what) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();
+  return ABR_ERR_CUDA;
+}
+void host_set_domain_impl(Handle *h, size_t n);
+
+} // namespace abr
+
+using abr::Handle;
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+const char *abr_version(void) { return "aboria_b200 0.1 (sm_100a)"; }
+
+int abr_create(abr_handle *out, int device, void *stream) {
+  if (!out) return ABR_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("abr_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    cudaGetLastError();
+    return ABR_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "abr_create: bad device index";
+    return ABR_ERR_INVALID;
+  }
+  Handle *h = new (std::nothrow) Handle();
+  if (!h) return ABR_ERR_INVALID;
+  h->device = device;
+  h->stream = static_cast<cudaStream_t>(stream);
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaMalloc(&h->d_scalars, sizeof(abr::DevScalars))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_scalars, sizeof(abr::DevScalars))) != cudaSuccess) {
+    g_create_error = std::string("abr_create: ") + cudaGetErrorString(e);
+    delete h;
+    return ABR_ERR_CUDA;
+  }
+  cudaMemset(h->d_scalars, 0, sizeof(abr::DevScalars));
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
+  for (int d = 0; d < abr::MAXD; ++d) {
+    h->bmin[d] = 0;
+    h->bmax[d] = 1;
+    h->periodic[d] = false;
+    h->side[d] = 1;
+    h->inv_side[d] = 1;
+  }
+  *out = reinterpret_cast<abr_handle>(h);
+  return ABR_OK;
+}
+
+int abr_destroy(abr_handle hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < 2; ++i) {
+    h->keys[i].release();
+    h->idx[i].release();
+  }
+  h->tile_hist.release();
+  h->scan_tmp.release();
+  h->bucket_begin.release();
+  h->bucket_end.release();
+  h->danger_list.release();
+  if (h->d_scalars) cudaFree(h->d_scalars);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  delete h;
+  return ABR_OK;
+}
+
+int abr_set_stream(abr_handle hh, void *stream) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  h->stream = static_cast<cudaStream_t>(stream);
+  return ABR_OK;
+}
+
+int abr_synchronize(abr_handle hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ABR_OK;
+}
+
+const char *abr_last_error_string(abr_handle hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return g_create_error.c_str();
+  return h->err.c_str();
+}
+
+static int set_domain_common(Handle *h, int D, const double *bmin, const double *bmax, const uint8_t *periodic) {
+  if (D < 1 || D > abr::MAXD) return abr::set_error(h, ABR_ERR_UNSUPPORTED, "domain: D must be 1, 2 or 3");
+  if (!bmin || !bmax || !periodic) return abr::set_error(h, ABR_ERR_INVALID, "domain: null pointer");
+  for (int d = 0; d < D; ++d)
+    if (!(bmax[d] > bmin[d]) || !std::isfinite(bmin[d]) || !std::isfinite(bmax[d]))
+      return abr::set_error(h, ABR_ERR_INVALID, "domain: need finite bmin < bmax");
+  if (h->domain_set && h->D != D) { // a different particle type: start over
+    h->size_calculated_with_n = (size_t)-1;
+    h->n_alive_last = 0;
+  }
+  h->D = D;
+  for (int d = 0; d < D; ++d) {
+    h->bmin[d] = bmin[d];
+    h->bmax[d] = bmax[d];
+    h->periodic[d] = periodic[d] != 0;
+  }
+  h->domain_set = true;
+  h->built = false;
+  return ABR_OK;
+}
+
+int abr_domain_set(abr_handle hh, int D, const double *bmin, const double *bmax, const uint8_t *periodic, double n_leaf) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (!(n_leaf > 0)) return abr::set_error(h, ABR_ERR_INVALID, "domain: n_particles_in_leaf must be > 0");
+  int rc = set_domain_common(h, D, bmin, bmax, periodic);
+  if (rc) return rc;
+  h->n_leaf = n_leaf;
+  h->grid_forced = false;
+  // set_domain -> set_domain_impl with the current m_alive_indices.size()
+  // (src/NeighbourSearchBase.h:252-268, src/CellListOrdered.h:132-139)
+  abr::host_set_domain_impl(h, h->n_alive_last);
+  return ABR_OK;
+}
+
+int abr_domain_force_grid(abr_handle hh, int D, const double *bmin, const double *bmax, const uint8_t *periodic, const uint32_t *size) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (!size) return abr::set_error(h, ABR_ERR_INVALID, "force_grid: null size");
+  int rc = set_domain_common(h, D, bmin, bmax, periodic);
+  if (rc) return rc;
+  for (int d = 0; d < D; ++d) {
+    if (size[d] == 0) return abr::set_error(h, ABR_ERR_INVALID, "force_grid: zero size");
+    h->size[d] = size[d];
+    h->side[d] = (h->bmax[d] - h->bmin[d]) / h->size[d];
+    h->inv_side[d] = 1.0 / h->side[d];
+  }
+  h->grid_forced = true;
+  return ABR_OK;
+}
+
+int abr_domain_get(abr_handle hh, uint32_t *size, double *side, uint64_t *n_buckets) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (!h->domain_set) return abr::set_error(h, ABR_ERR_STATE, "domain_get: domain has not been set");
+  uint64_t prod = 1;
+  for (int d = 0; d < h->D; ++d) {
+    if (size) size[d] = h->size[d];
+    if (side) side[d] = h->side[d];
+    prod *= h->size[d];
+  }
+  if (n_buckets) *n_buckets = prod;
+  return ABR_OK;
+}
+
+int abr_celllist_build(abr_handle hh, double *pos, uint8_t *alive, size_t n, int32_t *order_out, size_t *n_alive_host) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (n > 0 && (!pos || !alive || !order_out)) return abr::set_error(h, ABR_ERR_INVALID, "build: null pointer");
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  return abr::build_celllist(h, pos, alive, n, order_out, n_alive_host);
+}
+
+int abr_celllist_get(abr_handle hh, const uint32_t **bucket_indices, const uint32_t **bucket_begin, const uint32_t **bucket_end, uint64_t *n_buckets) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (!h->built) return abr::set_error(h, ABR_ERR_STATE, "celllist_get: no build");
+  if (bucket_indices) *bucket_indices = h->sorted_keys;
+  if (bucket_begin) *bucket_begin = h->bucket_begin.as<uint32_t>();
+  if (bucket_end) *bucket_end = h->bucket_end.as<uint32_t>();
+  if (n_buckets) *n_buckets = h->ncells;
+  return ABR_OK;
+}
+
+int abr_gather_columns(abr_handle hh, int ncols, const void *const *src, void *const *dst, const size_t *elem_bytes, const int32_t *order, size_t n_out) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (ncols < 0 || (ncols > 0 && (!src || !dst || !elem_bytes))) return abr::set_error(h, ABR_ERR_INVALID, "gather: null pointer");
+  if (n_out > 0 && !order) return abr::set_error(h, ABR_ERR_INVALID, "gather: null order");
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  return abr::gather_columns(h, ncols, src, dst, elem_bytes, order, n_out);
+}
+
+int abr_query_set_particles(abr_handle hh, const double *pos_sorted, size_t n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (n > 0 && !pos_sorted) return abr::set_error(h, ABR_ERR_INVALID, "query: null positions");
+  if (n != h->n_alive_last) return abr::set_error(h, ABR_ERR_INVALID, "query: n differs from the alive count of the last build");
+  h->pos_sorted = pos_sorted;
+  h->n_sorted = n;
+  return ABR_OK;
+}
+
+int abr_sparse_matvec(abr_handle hh, const double *row_pos, size_t n_rows, int rows_are_cols, const abr_kernel_desc *k, double radius,
+                      const double *radius_per_row, const double *b, double *y, uint64_t *n_pairs_host) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::MatvecCall c{row_pos, n_rows, rows_are_cols, radius, radius_per_row, b, y, nullptr, nullptr, -1};
+  int rc = abr::run_builtin_matvec(h, c, k);
+  if (rc) return rc;
+  if (n_pairs_host) {
+    // diagnostic: counted by a separate stats pass (not part of the product path)
+    uint32_t *cnt = nullptr;
+    ABR_CUDA(h, cudaMalloc(&cnt, (n_rows + 1) * sizeof(uint32_t)));
+    abr::MatvecCall s{row_pos, n_rows, rows_are_cols, radius, radius_per_row, nullptr, nullptr, cnt, nullptr, -1};
+    rc = abr::run_pair_stats(h, s);
+    uint64_t total = 0;
+    if (!rc) {
+      std::string tmp;
+      uint32_t *hc = new uint32_t[n_rows];
+      cudaMemcpyAsync(hc, cnt, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream);
+      cudaStreamSynchronize(h->stream);
+      for (size_t i = 0; i < n_rows; ++i) total += hc[i];
+      delete[] hc;
+    }
+    cudaFree(cnt);
+    *n_pairs_host = total;
+    if (rc) return rc;
+  }
+  return ABR_OK;
+}
+
+int abr_pair_stats(abr_handle hh, const double *row_pos, size_t n_rows, int rows_are_cols, double radius, const double *radius_per_row,
+                   int path, uint32_t *count, uint64_t *hash) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (path != 0 && path != 1 && path != -1) return abr::set_error(h, ABR_ERR_INVALID, "pair_stats: path must be -1, 0 or 1");
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::MatvecCall c{row_pos, n_rows, rows_are_cols, radius, radius_per_row, nullptr, nullptr, count, hash, path};
+  return abr::run_pair_stats(h, c);
+}
+
+int abr_last_counters(abr_handle hh, uint64_t counters[4]) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !counters) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(abr::DevScalars), cudaMemcpyDeviceToHost, h->stream));
+  ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+  counters[0] = h->h_scalars->danger_count;
+  counters[1] = h->n_aliased;
+  counters[2] = h->counters[2];
+  counters[3] = 0;
+  return ABR_OK;
+}
+
+int abr_sparse_matvec_custom(abr_handle hh, const double *row_pos, size_t n_rows, int rows_are_cols, abr_launch_fn launch,
+                             const void *functor, int BR, int BC, double radius, const double *radius_per_row, const double *b,
+                             double *y, uint64_t *n_pairs_host) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::MatvecCall c{row_pos, n_rows, rows_are_cols, radius, radius_per_row, b, y, nullptr, nullptr, -1};
+  int rc = abr::run_custom_matvec(h, c, launch, functor, BR, BC);
+  if (rc) return rc;
+  if (n_pairs_host) *n_pairs_host = 0;
+  return ABR_OK;
+}
+
+int abr_malloc(abr_handle hh, void **ptr, size_t bytes) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !ptr) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  ABR_CUDA(h, cudaMalloc(ptr, bytes ? bytes : 1));
+  return ABR_OK;
+}
+int abr_free(abr_handle hh, void *ptr) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+  ABR_CUDA(h, cudaFree(ptr));
+  return ABR_OK;
+}
+int abr_memcpy_h2d(abr_handle hh, void *dst, const void *src, size_t bytes) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return ABR_OK;
+}
+int abr_memcpy_d2h(abr_handle hh, void *dst, const void *src, size_t bytes) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ABR_OK;
+}
+int abr_memset(abr_handle hh, void *dst, int value, size_t bytes) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaMemsetAsync(dst, value, bytes, h->stream));
+  return ABR_OK;
+}
+int abr_host_alloc_pinned(void **ptr, size_t bytes) {
+  if (!ptr) return ABR_ERR_INVALID;
+  return cudaMallocHost(ptr, bytes ? bytes : 1) == cudaSuccess ? ABR_OK : ABR_ERR_CUDA;
+}
+int abr_host_free_pinned(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? ABR_OK : ABR_ERR_CUDA; }
+
+} // extern "C"

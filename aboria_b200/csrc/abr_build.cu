@@ -1,0 +1,619 @@
+// Ordered cell-list build for sm_100a.
+//
+// Replaces the Thrust call chain of the reference
+//   neighbour_search_base::update_positions   (src/NeighbourSearchBase.h:350-495)
+//   CellListOrdered::update_positions_impl    (src/CellListOrdered.h:190-259)
+//   Particles::reorder                        (src/Particles.h:694-724)
+// with four hand-written stages:
+//   k1  enforce_domain + alive + bucket key, fused (one pass over positions)
+//   k2  LSD radix sort of (key, index), 8-bit digits, stable
+//   k3  bucket_begin / bucket_end from run boundaries of the sorted keys
+//       (+ a suffix-min fill for empty buckets, = lower/upper_bound semantics)
+//   k4  multi-column gather with coalesced 8-byte-word stores
+// Dead particles get the key `key_bound` (> every live key) so the stable sort
+// leaves exactly m_alive_indices-after-sort_by_key in front; no scan/scatter.
+//
+// Compiled with -fmad=false (see grid.cuh).
+#include <algorithm>
+#include <cmath>
+
+#include "abr_internal.h"
+
+namespace abr {
+
+// ---------------------------------------------------------------------------
+// k1: enforce_domain_lambda (src/NeighbourSearchBase.h:208-237) followed by
+// point_to_bucket_index (src/detail/SpatialUtil.h:118-131).  One thread per
+// particle; the position / alive flag are written back only when they changed
+// (same memory image as the reference's unconditional store, fewer bytes).
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+k_enforce_key(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t n, Grid g,
+              uint32_t *__restrict__ keys, DevScalars *sc) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double r[D], r0[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) r0[d] = r[d] = pos[(size_t)p * D + d];
+  const uint8_t a0 = alive[p];
+  uint8_t a = a0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    if (!isfinite(r[d])) {
+      a = 0;
+    } else if (g.periodic[d]) {
+      // The reference loops without bound (and never terminates once |r|/L
+      // exceeds 2^53).  A GPU kernel must not hang: after 2^20 steps the
+      // particle is killed like a non-finite one (documented deviation).
+      int guard = 0;
+      while (r[d] < g.bmin[d] && ++guard < (1 << 20)) r[d] += (g.bmax[d] - g.bmin[d]);
+      while (r[d] >= g.bmax[d] && ++guard < (1 << 20)) r[d] -= (g.bmax[d] - g.bmin[d]);
+      if (guard >= (1 << 20)) {
+        a = 0;
+        r[d] = r0[d];
+      }
+    } else {
+      if ((r[d] < g.bmin[d]) || (r[d] >= g.bmax[d])) a = 0;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+    if (__double_as_longlong(r[d]) != __double_as_longlong(r0[d])) pos[(size_t)p * D + d] = r[d];
+  if (a != a0) alive[p] = a;
+  uint32_t key = g.key_bound;
+  if (a) {
+    int v[D];
+    bool overflow = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      v[d] = (int)floor((r[d] - g.bmin[d]) * g.inv_side[d]);
+      overflow |= (v[d] >= g.size[d]) | (v[d] < 0);
+    }
+    key = (uint32_t)collapse_index<D>(g, v);
+    if (overflow) atomicAdd(&sc->n_aliased, 1u);
+    if (key >= g.key_bound) key = g.key_bound - 1; // cannot happen (v[d] <= size[d]); keeps the sort in range
+  }
+  keys[p] = key;
+}
+
+// ---------------------------------------------------------------------------
+// k2: radix sort.  Tile = 256 threads x 16 keys, warp-striped so that the
+// order (warp, slot, lane) equals the memory order -> stable ranks.
+// ---------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_IPT = 16;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RADIX = 256;
+
+// per-tile digit histogram, digit-major: hist[d * num_tiles + tile]
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t num_tiles,
+             uint32_t *__restrict__ hist) {
+  __shared__ uint32_t s_hist[RADIX];
+  const uint32_t tile = blockIdx.x;
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = tile * RS_TILE;
+#pragma unroll
+  for (int j = 0; j < RS_IPT; ++j) {
+    const uint32_t p = base + j * RS_THREADS + threadIdx.x;
+    if (p < n) atomicAdd(&s_hist[(keys[p] >> shift) & (RADIX - 1)], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * num_tiles + tile] = s_hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
+                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ idx_out,
+                const uint32_t *__restrict__ tile_offsets, int shift, uint32_t n,
+                uint32_t num_tiles) {
+  __shared__ uint32_t warp_hist[RS_WARPS][RADIX];
+  __shared__ uint32_t digit_start[RADIX];
+  __shared__ uint32_t glob_off[RADIX];
+  __shared__ uint32_t s_keys[RS_TILE];
+  __shared__ uint32_t s_idx[RS_TILE];
+  __shared__ uint32_t s_scan[RS_WARPS];
+
+  const uint32_t tile = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+  __syncthreads();
+
+  const uint32_t wbase = tile * RS_TILE + warp * (RS_IPT * 32);
+  uint32_t key[RS_IPT], val[RS_IPT];
+  uint16_t rank[RS_IPT];
+#pragma unroll
+  for (int j = 0; j < RS_IPT; ++j) {
+    const uint32_t p = wbase + j * 32 + lane;
+    const bool valid = p < n;
+    key[j] = valid ? keys_in[p] : 0xFFFFFFFFu;
+    val[j] = valid ? (idx_in ? idx_in[p] : p) : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < RS_IPT; ++j) {
+    const uint32_t p = wbase + j * 32 + lane;
+    const bool valid = p < n;
+    const uint32_t d = (key[j] >> shift) & (RADIX - 1);
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : (RADIX + lane));
+    const uint32_t prev = warp_hist[warp][d];
+    __syncwarp();
+    if (valid && (peers & lane_lt) == 0) warp_hist[warp][d] = prev + __popc(peers);
+    __syncwarp();
+    rank[j] = (uint16_t)(prev + __popc(peers & lane_lt));
+  }
+  __syncthreads();
+
+  // per digit: exclusive prefix over warps, block total
+  uint32_t total;
+  {
+    const int d = tid;
+    uint32_t running = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = warp_hist[w][d];
+      warp_hist[w][d] = running;
+      running += c;
+    }
+    total = running;
+    glob_off[d] = tile_offsets[(size_t)d * num_tiles + tile];
+  }
+  // exclusive scan of the 256 digit totals
+  uint32_t incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w)
+    if (w < warp) woff += s_scan[w];
+  digit_start[tid] = woff + incl - total;
+  __syncthreads();
+
+#pragma unroll
+  for (int j = 0; j < RS_IPT; ++j) {
+    const uint32_t p = wbase + j * 32 + lane;
+    if (p < n) {
+      const uint32_t d = (key[j] >> shift) & (RADIX - 1);
+      const uint32_t slot = digit_start[d] + warp_hist[warp][d] + rank[j];
+      s_keys[slot] = key[j];
+      s_idx[slot] = val[j];
+    }
+  }
+  __syncthreads();
+  const uint32_t tile_count = min((uint32_t)RS_TILE, n - tile * RS_TILE);
+  for (uint32_t s = tid; s < tile_count; s += RS_THREADS) {
+    const uint32_t k = s_keys[s];
+    const uint32_t d = (k >> shift) & (RADIX - 1);
+    const uint32_t out = glob_off[d] + (s - digit_start[d]);
+    keys_out[out] = k;
+    idx_out[out] = s_idx[s];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// device-wide scans (three-phase): exclusive prefix sum / inclusive suffix min
+// ---------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_IPT = 16;
+constexpr int SC_TILE = SC_THREADS * SC_IPT;
+
+struct OpSum {
+  __device__ static uint32_t identity() { return 0u; }
+  __device__ static uint32_t apply(uint32_t a, uint32_t b) { return a + b; }
+};
+struct OpMin {
+  __device__ static uint32_t identity() { return 0xFFFFFFFFu; }
+  __device__ static uint32_t apply(uint32_t a, uint32_t b) { return a < b ? a : b; }
+};
+
+template <class Op> __device__ inline uint32_t block_reduce(uint32_t v, uint32_t *s_tmp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = Op::apply(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  if (lane == 0) s_tmp[warp] = v;
+  __syncthreads();
+  uint32_t r = Op::identity();
+  for (int w = 0; w < SC_THREADS / 32; ++w) r = Op::apply(r, s_tmp[w]);
+  __syncthreads();
+  return r;
+}
+
+// REVERSE = false: element order is index order (prefix); true: reversed (suffix)
+template <class Op, bool REVERSE>
+__global__ void __launch_bounds__(SC_THREADS)
+k_scan_reduce(const uint32_t *__restrict__ in, uint64_t m, uint32_t *__restrict__ partial) {
+  __shared__ uint32_t s_tmp[SC_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * SC_TILE;
+  uint32_t v = Op::identity();
+  for (int j = 0; j < SC_IPT; ++j) {
+    const uint64_t e = base + (uint64_t)j * SC_THREADS + threadIdx.x;
+    if (e < m) v = Op::apply(v, in[REVERSE ? (m - 1 - e) : e]);
+  }
+  v = block_reduce<Op>(v, s_tmp);
+  if (threadIdx.x == 0) partial[blockIdx.x] = v;
+}
+
+// single block: exclusive scan of the partials in place
+template <class Op>
+__global__ void __launch_bounds__(1024) k_scan_partials(uint32_t *partial, uint32_t nb) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = Op::identity();
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    const uint32_t e = base + threadIdx.x;
+    const uint32_t v = e < nb ? partial[e] : Op::identity();
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl = Op::apply(incl, t);
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = s_carry;
+    for (int w = 0; w < warp; ++w) woff = Op::apply(woff, s_w[w]);
+    uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if (lane == 0) excl = Op::identity();
+    excl = Op::apply(woff, excl);
+    if (e < nb) partial[e] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = Op::apply(woff, incl);
+    __syncthreads();
+  }
+}
+
+// phase 3.  MODE 0: out[e] = exclusive prefix sum.
+//           MODE 1 (bucket fill): in = bucket_begin candidates (0xFFFFFFFF for
+//           empty), out_begin = min(inclusive suffix min, n_incell);
+//           out_end[c] = end candidate or out_begin[c] when the bucket is empty.
+template <class Op, bool REVERSE, int MODE>
+__global__ void __launch_bounds__(SC_THREADS)
+k_scan_apply(const uint32_t *in, uint64_t m, const uint32_t *__restrict__ partial, uint32_t *out,
+             uint32_t *end_io, const DevScalars *sc) {
+  __shared__ uint32_t s_w[SC_THREADS / 32];
+  __shared__ uint32_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t base = (uint64_t)blockIdx.x * SC_TILE;
+  if (threadIdx.x == 0) s_carry = partial[blockIdx.x];
+  __syncthreads();
+  for (int j = 0; j < SC_IPT; ++j) {
+    const uint64_t e = base + (uint64_t)j * SC_THREADS + threadIdx.x;
+    const uint64_t src = REVERSE ? (m - 1 - e) : e;
+    const uint32_t v = e < m ? in[src] : Op::identity();
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl = Op::apply(incl, t);
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = s_carry;
+    for (int w = 0; w < warp; ++w) woff = Op::apply(woff, s_w[w]);
+    if (MODE == 0) {
+      uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+      if (lane == 0) excl = Op::identity();
+      if (e < m) out[src] = Op::apply(woff, excl);
+    } else {
+      if (e < m) {
+        uint32_t bb = Op::apply(woff, incl);
+        const uint32_t lim = sc->n_incell;
+        if (bb > lim) bb = lim;
+        out[src] = bb;
+        if (end_io[src] == 0xFFFFFFFFu) end_io[src] = bb;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == SC_THREADS - 1) s_carry = Op::apply(woff, incl);
+    __syncthreads();
+  }
+}
+
+template <class Op, bool REVERSE, int MODE>
+static cudaError_t device_scan(Handle *h, const uint32_t *in, uint64_t m, uint32_t *out,
+                               uint32_t *end_io) {
+  if (m == 0) return cudaSuccess;
+  const uint32_t nb = (uint32_t)((m + SC_TILE - 1) / SC_TILE);
+  cudaError_t e = h->scan_tmp.reserve((size_t)nb * sizeof(uint32_t));
+  if (e != cudaSuccess) return e;
+  uint32_t *partial = h->scan_tmp.as<uint32_t>();
+  k_scan_reduce<Op, REVERSE><<<nb, SC_THREADS, 0, h->stream>>>(in, m, partial);
+  k_scan_partials<Op><<<1, 1024, 0, h->stream>>>(partial, nb);
+  k_scan_apply<Op, REVERSE, MODE><<<nb, SC_THREADS, 0, h->stream>>>(in, m, partial, out, end_io,
+                                                                    h->d_scalars);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// k3: run boundaries of the sorted keys.  Equivalent to lower_bound /
+// upper_bound of every bucket id in the sorted key array
+// (src/CellListOrdered.h:229-239) once empty buckets are filled by the
+// suffix-min pass above.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_boundaries(const uint32_t *__restrict__ keys, uint32_t n, uint32_t ncells, uint32_t dead_key,
+             uint32_t *__restrict__ bb, uint32_t *__restrict__ be, DevScalars *sc) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t k = keys[p];
+  const uint32_t kprev = p > 0 ? keys[p - 1] : 0xFFFFFFFFu;
+  const uint32_t knext = p + 1 < n ? keys[p + 1] : 0xFFFFFFFFu;
+  if (p == 0 || k != kprev) {
+    if (k < ncells) bb[k] = p;
+    if (k >= ncells && (p == 0 || kprev < ncells)) sc->n_incell = p;
+    if (k == dead_key) sc->n_alive = p;
+  }
+  if (k != knext || p + 1 == n) {
+    if (k < ncells) be[k] = p + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k4: gather.  8-byte-word columns: one thread per output word, so the stores
+// of a warp are one contiguous 256-byte span; the loads of one element are
+// contiguous too.  Other element sizes fall back to a byte-granular variant.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gather_words(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
+               const int32_t *__restrict__ order, uint64_t n_out, uint32_t words) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_out * words) return;
+  const uint64_t k = g / words;
+  const uint32_t w = (uint32_t)(g - k * words);
+  dst[g] = src[(uint64_t)order[k] * words + w];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gather_small(const T *__restrict__ src, T *__restrict__ dst, const int32_t *__restrict__ order,
+               uint64_t n_out) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_out) dst[k] = src[order[k]];
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_bytes(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+               const int32_t *__restrict__ order, uint64_t n_out, uint32_t eb) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_out * eb) return;
+  const uint64_t k = g / eb;
+  const uint32_t w = (uint32_t)(g - k * eb);
+  dst[g] = src[(uint64_t)order[k] * eb + w];
+}
+
+static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
+                   const size_t *elem_bytes, const int32_t *order, size_t n_out) {
+  if (n_out == 0) return ABR_OK;
+  for (int c = 0; c < ncols; ++c) {
+    const size_t eb = elem_bytes[c];
+    if (eb == 0 || !src[c] || !dst[c]) return set_error(h, ABR_ERR_INVALID, "gather: null column");
+    const bool aligned8 = (eb % 8 == 0) && ((uintptr_t)src[c] % 8 == 0) && ((uintptr_t)dst[c] % 8 == 0);
+    if (aligned8) {
+      const uint32_t words = (uint32_t)(eb / 8);
+      k_gather_words<<<grid_for((uint64_t)n_out * words, 256), 256, 0, h->stream>>>(
+          (const uint64_t *)src[c], (uint64_t *)dst[c], order, n_out, words);
+    } else if (eb == 4 && (uintptr_t)src[c] % 4 == 0 && (uintptr_t)dst[c] % 4 == 0) {
+      k_gather_small<uint32_t><<<grid_for(n_out, 256), 256, 0, h->stream>>>(
+          (const uint32_t *)src[c], (uint32_t *)dst[c], order, n_out);
+    } else if (eb == 1) {
+      k_gather_small<uint8_t><<<grid_for(n_out, 256), 256, 0, h->stream>>>(
+          (const uint8_t *)src[c], (uint8_t *)dst[c], order, n_out);
+    } else {
+      k_gather_bytes<<<grid_for((uint64_t)n_out * eb, 256), 256, 0, h->stream>>>(
+          (const uint8_t *)src[c], (uint8_t *)dst[c], order, n_out, (uint32_t)eb);
+    }
+  }
+  ABR_CUDA(h, cudaGetLastError());
+  return ABR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host driver of the build
+// ---------------------------------------------------------------------------
+// CellListOrdered::set_domain_impl (src/CellListOrdered.h:132-186), host math.
+static void set_domain_impl(Handle *h, size_t n) {
+  if (h->grid_forced) return;
+  if (n < 0.5 * h->size_calculated_with_n || n > 2 * h->size_calculated_with_n) {
+    h->size_calculated_with_n = n;
+    const int D = h->D;
+    if (h->n_leaf > n) {
+      for (int d = 0; d < D; ++d) h->size[d] = 1;
+    } else {
+      double total_volume = 1.0;
+      for (int d = 0; d < D; ++d) total_volume *= (h->bmax[d] - h->bmin[d]);
+      const double box_volume = h->n_leaf / double(n) * total_volume;
+      const double box_side_length = std::pow(box_volume, 1.0 / D);
+      for (int d = 0; d < D; ++d) {
+        h->size[d] = static_cast<unsigned int>(std::floor((h->bmax[d] - h->bmin[d]) / box_side_length));
+        if (h->size[d] == 0) h->size[d] = 1;
+      }
+    }
+    for (int d = 0; d < D; ++d) {
+      h->side[d] = (h->bmax[d] - h->bmin[d]) / h->size[d];
+      h->inv_side[d] = 1.0 / h->side[d];
+    }
+  }
+}
+
+void host_set_domain_impl(Handle *h, size_t n) { set_domain_impl(h, n); }
+
+Grid Handle::grid() const {
+  Grid g;
+  g.D = D;
+  uint64_t prod = 1, bound = 0;
+  for (int d = 0; d < MAXD; ++d) {
+    const bool in = d < D;
+    g.size[d] = in ? (int)size[d] : 1;
+    g.end[d] = g.size[d] - 1;
+    g.periodic[d] = in ? (periodic[d] ? 1 : 0) : 0;
+    g.bmin[d] = in ? bmin[d] : 0.0;
+    g.bmax[d] = in ? bmax[d] : 1.0;
+    g.side[d] = in ? side[d] : 1.0;
+    g.inv_side[d] = in ? inv_side[d] : 1.0;
+    g.L[d] = g.bmax[d] - g.bmin[d];
+    if (in) prod *= size[d];
+  }
+  // largest key an alive particle can get is collapse(size) (every v[d] == size[d])
+  for (int d = 0; d < D; ++d) bound = bound * size[d] + size[d];
+  g.ncells = (uint32_t)prod;
+  g.key_bound = (uint32_t)(bound + 1);
+  return g;
+}
+
+int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *order_out,
+                   size_t *n_alive_host) {
+  if (!h->domain_set) return set_error(h, ABR_ERR_STATE, "build: domain has not been set");
+  if (n >= 0x7FFFFFFFull) return set_error(h, ABR_ERR_UNSUPPORTED, "build: n must fit in int32");
+  const int D = h->D;
+  h->built = false;
+  if (n == 0) { // update_n == 0 -> return false (src/NeighbourSearchBase.h:375-376)
+    // the reference keeps whatever bucket arrays it had (all ranges empty after
+    // set_domain_impl's resize); give the query the same: empty buckets
+    uint64_t prod = 1;
+    for (int d = 0; d < D; ++d) prod *= h->size[d];
+    ABR_CUDA(h, h->bucket_begin.reserve(prod * sizeof(uint32_t)));
+    ABR_CUDA(h, h->bucket_end.reserve(prod * sizeof(uint32_t)));
+    ABR_CUDA(h, cudaMemsetAsync(h->bucket_begin.p, 0, prod * sizeof(uint32_t), h->stream));
+    ABR_CUDA(h, cudaMemsetAsync(h->bucket_end.p, 0, prod * sizeof(uint32_t), h->stream));
+    ABR_CUDA(h, h->keys[0].reserve(sizeof(uint32_t)));
+    h->sorted_keys = h->keys[0].as<uint32_t>();
+    h->ncells = prod;
+    h->n_aliased = 0;
+    h->n_alive_last = 0;
+    h->built = true;
+    if (n_alive_host) *n_alive_host = 0;
+    return ABR_OK;
+  }
+
+  // The reference sizes the grid with the number of ALIVE particles
+  // (m_alive_indices.size(), src/CellListOrdered.h:133), known only after
+  // enforce_domain.  The grid does not influence which particles die, so k1 is
+  // run with the grid computed from n and, if particles died and the recompute
+  // rule picks a different grid for n_alive, once more (rare).
+  size_t n_for_grid = n;
+  const size_t saved_calc = h->size_calculated_with_n;
+  uint32_t saved_size[MAXD];
+  double saved_side[MAXD], saved_inv[MAXD];
+  for (int d = 0; d < MAXD; ++d) {
+    saved_size[d] = h->size[d];
+    saved_side[d] = h->side[d];
+    saved_inv[d] = h->inv_side[d];
+  }
+
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    set_domain_impl(h, n_for_grid);
+    const Grid g = h->grid();
+    uint64_t prod = 1;
+    for (int d = 0; d < D; ++d) prod *= h->size[d];
+    if (prod >= 0x7FFFFFF0ull || (uint64_t)g.key_bound >= 0xFFFFFFF0ull)
+      return set_error(h, ABR_ERR_UNSUPPORTED, "build: too many buckets for 32-bit keys");
+    h->ncells = prod;
+
+    const uint32_t n32 = (uint32_t)n;
+    const uint32_t num_tiles = (n32 + RS_TILE - 1) / RS_TILE;
+    for (int i = 0; i < 2; ++i) {
+      ABR_CUDA(h, h->keys[i].reserve(n * sizeof(uint32_t)));
+      ABR_CUDA(h, h->idx[i].reserve(n * sizeof(uint32_t)));
+    }
+    ABR_CUDA(h, h->tile_hist.reserve((size_t)RADIX * num_tiles * sizeof(uint32_t)));
+    ABR_CUDA(h, h->bucket_begin.reserve(prod * sizeof(uint32_t)));
+    ABR_CUDA(h, h->bucket_end.reserve(prod * sizeof(uint32_t)));
+
+    // scalars: n_alive = n_incell = n by default (no dead / no overflow keys)
+    DevScalars init;
+    memset(&init, 0, sizeof(init));
+    init.n_alive = n32;
+    init.n_incell = n32;
+    *h->h_scalars = init;
+    ABR_CUDA(h, cudaMemcpyAsync(h->d_scalars, h->h_scalars, sizeof(DevScalars), cudaMemcpyHostToDevice, h->stream));
+
+    uint32_t *keys0 = h->keys[0].as<uint32_t>();
+    const unsigned gb = grid_for(n, 256);
+    switch (D) {
+    case 1: k_enforce_key<1><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+    case 2: k_enforce_key<2><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+    default: k_enforce_key<3><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+    }
+
+    // LSD radix sort over the bits of key_bound
+    int bits = 1;
+    while (bits < 32 && (g.key_bound >> bits) != 0) ++bits;
+    const int passes = (bits + 7) / 8;
+    int cur = 0;
+    uint32_t *hist = h->tile_hist.as<uint32_t>();
+    for (int pass = 0; pass < passes; ++pass) {
+      const int shift = pass * 8;
+      const uint32_t *kin = h->keys[cur].as<uint32_t>();
+      const uint32_t *iin = pass == 0 ? nullptr : h->idx[cur].as<uint32_t>();
+      uint32_t *kout = h->keys[cur ^ 1].as<uint32_t>();
+      uint32_t *iout = (pass == passes - 1) ? reinterpret_cast<uint32_t *>(order_out)
+                                            : h->idx[cur ^ 1].as<uint32_t>();
+      k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, n32, shift, num_tiles, hist);
+      cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
+      if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
+      k_radix_scatter<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, iin, kout, iout, hist, shift, n32, num_tiles);
+      cur ^= 1;
+    }
+    h->sorted_keys = h->keys[cur].as<uint32_t>();
+
+    // bucket ranges
+    uint32_t *bb = h->bucket_begin.as<uint32_t>();
+    uint32_t *be = h->bucket_end.as<uint32_t>();
+    ABR_CUDA(h, cudaMemsetAsync(bb, 0xFF, prod * sizeof(uint32_t), h->stream));
+    ABR_CUDA(h, cudaMemsetAsync(be, 0xFF, prod * sizeof(uint32_t), h->stream));
+    k_boundaries<<<gb, 256, 0, h->stream>>>(h->sorted_keys, n32, (uint32_t)prod, g.key_bound, bb, be, h->d_scalars);
+    cudaError_t e = device_scan<OpMin, true, 1>(h, bb, prod, bb, be);
+    if (e != cudaSuccess) return check_cuda(h, e, "bucket fill");
+
+    ABR_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+    ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+    const size_t n_alive = h->h_scalars->n_alive;
+    h->n_aliased = h->h_scalars->n_aliased;
+
+    if (attempt == 0 && n_alive != n && !h->grid_forced) {
+      // would the reference (which sees n_alive) have chosen another grid?
+      uint32_t got_size[MAXD];
+      for (int d = 0; d < MAXD; ++d) got_size[d] = h->size[d];
+      h->size_calculated_with_n = saved_calc;
+      for (int d = 0; d < MAXD; ++d) {
+        h->size[d] = saved_size[d];
+        h->side[d] = saved_side[d];
+        h->inv_side[d] = saved_inv[d];
+      }
+      set_domain_impl(h, n_alive);
+      bool same = true;
+      for (int d = 0; d < D; ++d) same &= (got_size[d] == h->size[d]);
+      if (!same) {
+        // redo with the grid the reference would use; positions are already
+        // wrapped and dead flags set, a second k1 pass is idempotent
+        h->size_calculated_with_n = saved_calc;
+        for (int d = 0; d < MAXD; ++d) {
+          h->size[d] = saved_size[d];
+          h->side[d] = saved_side[d];
+          h->inv_side[d] = saved_inv[d];
+        }
+        n_for_grid = n_alive;
+        continue;
+      }
+    }
+    h->n_alive_last = n_alive;
+    h->built = true;
+    if (n_alive_host) *n_alive_host = n_alive;
+    return ABR_OK;
+  }
+  return set_error(h, ABR_ERR_STATE, "build: grid did not converge");
+}
+
+} // namespace abr

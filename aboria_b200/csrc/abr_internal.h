@@ -1,0 +1,122 @@
+// Internal declarations shared by the translation units of libabr.so.
+#ifndef ABR_INTERNAL_H_
+#define ABR_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "abr.h"
+#include "aboria_b200/detail/grid.cuh"
+
+namespace abr {
+
+// grow-only device scratch buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+// device-resident scalars written by the build / matvec kernels
+struct DevScalars {
+  uint32_t n_alive;        // first position holding the dead key
+  uint32_t n_incell;       // first position with key >= ncells
+  uint32_t n_aliased;      // alive particles whose bucket index vector overflowed (v[d] >= size[d])
+  uint32_t work_counter;   // dynamic tile scheduler of the tiled matvec
+  uint32_t danger_count;   // rows handed to the exact per-row walk
+  uint32_t pad[3];
+  unsigned long long pair_count;
+};
+
+struct Handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+
+  // --- neighbour_search_base / CellListOrdered host state -----------------
+  bool domain_set = false;
+  int D = 3;
+  double bmin[MAXD], bmax[MAXD];
+  bool periodic[MAXD];
+  double n_leaf = 10.0;
+  uint32_t size[MAXD] = {1, 1, 1};
+  double side[MAXD], inv_side[MAXD];
+  size_t size_calculated_with_n = (size_t)-1;
+  size_t n_alive_last = 0; // m_alive_indices.size()
+  bool grid_forced = false;
+
+  // --- device state ---------------------------------------------------------
+  DevBuf keys[2], idx[2], tile_hist, scan_tmp;
+  DevBuf bucket_begin, bucket_end;
+  DevBuf danger_list;
+  DevScalars *d_scalars = nullptr;
+  DevScalars *h_scalars = nullptr; // pinned mirror
+  const uint32_t *sorted_keys = nullptr;
+  uint64_t ncells = 0;
+  bool built = false;
+  uint32_t n_aliased = 0;
+
+  // query binding
+  const double *pos_sorted = nullptr;
+  size_t n_sorted = 0;
+
+  uint64_t counters[4] = {0, 0, 0, 0};
+
+  Grid grid() const;
+};
+
+int set_error(Handle *h, int code, const std::string &msg);
+int check_cuda(Handle *h, cudaError_t e, const char *what);
+
+// abr_build.cu
+int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *order_out,
+                   size_t *n_alive_host);
+int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
+                   const size_t *elem_bytes, const int32_t *order, size_t n_out);
+
+// abr_matvec.cu
+struct MatvecCall {
+  const double *row_pos;
+  size_t n_rows;
+  int rows_are_cols;
+  double radius;
+  const double *radius_per_row;
+  const double *b;
+  double *y;
+  // stats mode
+  uint32_t *count;
+  uint64_t *hash;
+  int force_path; // -1 auto, 0 tiled, 1 walk
+};
+int run_builtin_matvec(Handle *h, const MatvecCall &c, const abr_kernel_desc *k);
+int run_pair_stats(Handle *h, const MatvecCall &c);
+int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, const void *functor,
+                      int BR, int BC);
+
+} // namespace abr
+
+#define ABR_CUDA(h, expr)                                        \
+  do {                                                           \
+    cudaError_t e__ = (expr);                                    \
+    if (e__ != cudaSuccess) return abr::check_cuda(h, e__, #expr); \
+  } while (0)
+
+#endif

@@ -1,0 +1,168 @@
+// Host planner + built-in functor dispatch of the sparse kernel product.
+// Kernels live in include/aboria_b200/detail/matvec_kernels.cuh.
+#include <cmath>
+#include <cstring>
+
+#include "abr_internal.h"
+#include "aboria_b200/device_kernel.cuh"
+
+namespace abr {
+
+// Fills the plan: picks the tiled kernel when its preconditions hold, and the
+// rounding-safety margins that decide which rows go to the exact walk.
+static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p) {
+  if (!h->built) return set_error(h, ABR_ERR_STATE, "matvec: cell list has not been built");
+  if (!h->pos_sorted && h->n_sorted > 0) return set_error(h, ABR_ERR_STATE, "matvec: abr_query_set_particles not called");
+  if (c.n_rows >= 0xFFFFFFFFull) return set_error(h, ABR_ERR_UNSUPPORTED, "matvec: too many rows");
+  memset(p, 0, sizeof(*p));
+  p->q.g = h->grid();
+  p->q.pos = h->pos_sorted;
+  p->q.bucket_begin = h->bucket_begin.as<uint32_t>();
+  p->q.bucket_end = h->bucket_end.as<uint32_t>();
+  p->q.n = (uint32_t)h->n_sorted;
+  p->row_pos = c.row_pos;
+  p->n_rows = (uint32_t)c.n_rows;
+  p->rows_are_cols = c.rows_are_cols;
+  p->radius = c.radius;
+  p->radius_per_row = c.radius_per_row;
+  p->b = c.b;
+  p->y = c.y;
+  p->stat_count = c.count;
+  p->stat_hash = c.hash;
+  p->stream = h->stream;
+  p->sm_count = h->sm_count;
+  p->work_counter = &h->d_scalars->work_counter;
+  p->danger_count = &h->d_scalars->danger_count;
+
+  const int D = h->D;
+  bool tiled = c.rows_are_cols && !c.radius_per_row && h->n_aliased == 0 &&
+               c.row_pos == h->pos_sorted && c.n_rows == h->n_sorted && c.radius > 0 &&
+               std::isfinite(c.radius);
+  if (c.force_path == 1) tiled = false;
+  if (c.force_path == 0 && !tiled)
+    return set_error(h, ABR_ERR_INVALID, "tiled path needs rows_are_cols, a constant radius and no aliased keys");
+  if (tiled) {
+    // absolute slack of any coordinate computed on the path (a few ulps of the
+    // largest magnitude involved), see DESIGN.md "exactness of the tiled kernel"
+    double xmax = 0;
+    for (int d = 0; d < D; ++d)
+      xmax = std::fmax(xmax, std::fmax(std::fabs(h->bmin[d]), std::fabs(h->bmax[d])) + (h->bmax[d] - h->bmin[d]));
+    xmax += c.radius;
+    const double delta = 256.0 * 2.220446049250313e-16 * xmax;
+    const double R = c.radius;
+    p->r2 = R * R; // pow(r,2) == r*r
+    p->r2lo = (R > 4 * delta) ? (R - 4 * delta) * (R - 4 * delta) : -1.0;
+    double stencil = 1;
+    for (int d = 0; d < D; ++d) {
+      const double wr = std::ceil(R * h->inv_side[d]);
+      if (!(wr < 1e6)) {
+        tiled = false;
+        break;
+      }
+      p->w[d] = (int)wr;
+      if (p->w[d] < 1) p->w[d] = 1;
+      p->tolf[d] = std::fmax(1e-9, 8.0 * delta * h->inv_side[d]);
+      if (p->tolf[d] > 0.125) tiled = false;
+      stencil *= (2.0 * p->w[d] + 1.0);
+    }
+    if (stencil > 8192.0) tiled = false; // radius >> bucket side: the walk is the better kernel
+    if (!tiled && c.force_path == 0)
+      return set_error(h, ABR_ERR_INVALID, "tiled path not applicable for this radius / grid");
+  }
+  p->use_tiled = tiled ? 1 : 0;
+  if (tiled) {
+    ABR_CUDA(h, h->danger_list.reserve((size_t)c.n_rows * sizeof(uint32_t)));
+    p->danger_list = h->danger_list.as<uint32_t>();
+    p->danger_capacity = (uint32_t)c.n_rows;
+    ABR_CUDA(h, cudaMemsetAsync(&h->d_scalars->work_counter, 0, 2 * sizeof(uint32_t), h->stream));
+  }
+  (void)BR;
+  return ABR_OK;
+}
+
+template <int D, class F, bool STATS>
+static int launch_checked(Handle *h, const abr_matvec_plan &p, const F &f) {
+  const int e = launch_plan<D, F, STATS>(p, f);
+  if (e != 0) return check_cuda(h, (cudaError_t)e, "matvec launch");
+  h->counters[2] = p.use_tiled ? 2 : 1;
+  return ABR_OK;
+}
+
+template <int D> static int dispatch_builtin(Handle *h, const abr_matvec_plan &p, const abr_kernel_desc *k) {
+  using namespace functors;
+  switch (k->kernel_id) {
+  case ABR_K_CONST_SUM:
+    if (k->block_rows != 1 || k->block_cols != 1) break;
+    return launch_checked<D, ConstSum, false>(h, p, ConstSum{k->row_vars[0], k->col_vars[0]});
+  case ABR_K_CONST_SUM_DIFF:
+    if (k->block_rows != 2 || k->block_cols != 1) break;
+    return launch_checked<D, ConstSumDiff, false>(h, p, ConstSumDiff{k->row_vars[0], k->col_vars[0]});
+  case ABR_K_INV_DIST:
+    if (k->block_rows != 1 || k->block_cols != 1) break;
+    return launch_checked<D, InvDist, false>(h, p, InvDist{k->params[0]});
+  case ABR_K_INV_DIST_AA:
+    if (k->block_rows != 1 || k->block_cols != 1) break;
+    return launch_checked<D, InvDistAA, false>(h, p, InvDistAA{k->params[0], k->row_vars[0], k->col_vars[0]});
+  case ABR_K_WENDLAND_C2:
+    if (k->block_rows != 1 || k->block_cols != 1) break;
+    return launch_checked<D, WendlandC2, false>(h, p, WendlandC2{k->params[0]});
+  case ABR_K_LJ_FORCE:
+    if (k->block_rows != D || k->block_cols != 1) break;
+    return launch_checked<D, LJForce<D>, false>(h, p, LJForce<D>{k->params[0], k->params[1]});
+  case ABR_K_SPH_DENSITY:
+    if (k->block_rows != 1 || k->block_cols != 1) break;
+    return launch_checked<D, SphDensity<D>, false>(h, p, SphDensity<D>{k->params[0], k->params[1], k->params[2]});
+  case ABR_K_SPH_PRESSURE:
+    if (k->block_rows != D || k->block_cols != 1) break;
+    return launch_checked<D, SphPressure<D>, false>(
+        h, p, SphPressure<D>{k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]});
+  default:
+    return set_error(h, ABR_ERR_INVALID, "matvec: unknown kernel_id");
+  }
+  return set_error(h, ABR_ERR_INVALID, "matvec: block_rows/block_cols do not match the kernel");
+}
+
+int run_builtin_matvec(Handle *h, const MatvecCall &c, const abr_kernel_desc *k) {
+  if (!k) return set_error(h, ABR_ERR_INVALID, "matvec: null kernel descriptor");
+  if (c.n_rows == 0) return ABR_OK;
+  if (!c.row_pos || !c.b || !c.y) return set_error(h, ABR_ERR_INVALID, "matvec: null pointer");
+  abr_matvec_plan p;
+  int rc = make_plan(h, c, k->block_rows, &p);
+  if (rc) return rc;
+  switch (h->D) {
+  case 1: return dispatch_builtin<1>(h, p, k);
+  case 2: return dispatch_builtin<2>(h, p, k);
+  default: return dispatch_builtin<3>(h, p, k);
+  }
+}
+
+int run_pair_stats(Handle *h, const MatvecCall &c) {
+  if (c.n_rows == 0) return ABR_OK;
+  if (!c.row_pos) return set_error(h, ABR_ERR_INVALID, "pair_stats: null pointer");
+  abr_matvec_plan p;
+  int rc = make_plan(h, c, 1, &p);
+  if (rc) return rc;
+  StatsFunctor f;
+  switch (h->D) {
+  case 1: return launch_checked<1, StatsFunctor, true>(h, p, f);
+  case 2: return launch_checked<2, StatsFunctor, true>(h, p, f);
+  default: return launch_checked<3, StatsFunctor, true>(h, p, f);
+  }
+}
+
+int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, const void *functor,
+                      int BR, int BC) {
+  if (!launch || !functor) return set_error(h, ABR_ERR_INVALID, "custom matvec: null launcher/functor");
+  if (c.n_rows == 0) return ABR_OK;
+  if (!c.row_pos || !c.b || !c.y) return set_error(h, ABR_ERR_INVALID, "matvec: null pointer");
+  (void)BC;
+  abr_matvec_plan p;
+  int rc = make_plan(h, c, BR, &p);
+  if (rc) return rc;
+  const int e = launch(&p, functor);
+  if (e != 0) return check_cuda(h, (cudaError_t)e, "custom matvec launch");
+  h->counters[2] = p.use_tiled ? 2 : 1;
+  return ABR_OK;
+}
+
+} // namespace abr

@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference interface for the hot path, on top of the
+C-ABI (include/abr.h).  Names and argument meaning follow the reference:
+
+  Particles.init_neighbour_search(low, high, periodic, n_particles_in_leaf=10)
+      src/Particles.h:445-455
+  Particles.update_positions()            src/Particles.h:526-531 (+ reorder :694-724)
+  Particles.get_query()                   src/Particles.h (CellListOrderedQuery POD)
+  create_sparse_operator(rows, cols, radius, kernel)   src/Operators.h:478-516
+  K * b / K.evaluate(y, b)                src/Operators.h:153, src/Kernels.h:720-751
+
+torch is used for device memory and streams only; all compute is in libabr.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AbrError, KernelDesc, check
+from .kernels import Kernel
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Query:
+    """Device view handed to kernels (CellListOrderedQuery, src/CellListOrdered.h:285-599)."""
+
+    def __init__(self, particles):
+        self.particles = particles
+
+    @property
+    def bucket_begin(self):
+        return self.particles._bucket_view()[1]
+
+    @property
+    def bucket_end(self):
+        return self.particles._bucket_view()[2]
+
+    @property
+    def bucket_indices(self):
+        return self.particles._bucket_view()[0]
+
+
+class Particles:
+    """Struct-of-columns particle container on one GPU (Particles<VAR,D,...,
+    CellListOrdered>, src/Particles.h:108-112).  Columns: position (n x D f64),
+    id (int64, the reference's size_t), alive (uint8), plus user variables."""
+
+    def __init__(self, D=3, n=0, variables=None, device=None):
+        if D < 1 or D > _lib.MAX_D:
+            raise ValueError("D must be 1, 2 or 3")
+        if not torch.cuda.is_available():
+            raise AbrError("aboria_b200 needs a CUDA device; there is no CPU fallback")
+        self.D = D
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._lib = _lib.lib()
+        self._h = C.c_void_p()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._lib.abr_create(C.byref(self._h), self.device.index or 0, C.c_void_p(stream))
+        if rc != 0:
+            raise AbrError(f"abr_create failed ({rc}): {self._lib.abr_last_error_string(None).decode()}")
+        self.columns = {}
+        self._other = {}
+        self.columns["position"] = torch.zeros((n, D), dtype=torch.float64, device=self.device)
+        self.columns["id"] = torch.arange(n, dtype=torch.int64, device=self.device)
+        self.columns["alive"] = torch.ones(n, dtype=torch.uint8, device=self.device)
+        for name, spec in (variables or {}).items():
+            dtype, shape = spec if isinstance(spec, tuple) else (spec, ())
+            self.columns[name] = torch.zeros((n,) + tuple(shape), dtype=dtype, device=self.device)
+        self.searchable = False
+        self._order = None
+        self.n_buckets = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.abr_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- container ---------------------------------------------------------
+    def size(self):
+        return self.columns["position"].shape[0]
+
+    __len__ = size
+
+    def get(self, name):
+        """get<variable>(particles)"""
+        return self.columns[name]
+
+    def set(self, name, value):
+        t = torch.as_tensor(value, device=self.device)
+        cur = self.columns.get(name)
+        if cur is not None:
+            t = t.to(cur.dtype)
+        if name != "position" and name in self.columns and t.shape[0] != self.size():
+            raise ValueError("column length mismatch")
+        self.columns[name] = t.contiguous()
+
+    def resize_from_positions(self, pos):
+        """Replace the whole set by n new particles at `pos` (host or device)."""
+        pos = torch.as_tensor(pos, dtype=torch.float64)
+        n = pos.shape[0]
+        self.columns["position"] = pos.to(self.device, non_blocking=True).contiguous()
+        self.columns["id"] = torch.arange(n, dtype=torch.int64, device=self.device)
+        self.columns["alive"] = torch.ones(n, dtype=torch.uint8, device=self.device)
+        for name in list(self.columns):
+            if name not in ("position", "id", "alive"):
+                old = self.columns[name]
+                self.columns[name] = torch.zeros((n,) + tuple(old.shape[1:]), dtype=old.dtype, device=self.device)
+
+    # -- neighbour search ----------------------------------------------------
+    def _sync_stream(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._h, self._lib.abr_set_stream(self._h, C.c_void_p(stream)))
+
+    def init_neighbour_search(self, low, high, periodic, n_particles_in_leaf=10.0):
+        D = self.D
+        low = np.ascontiguousarray(np.broadcast_to(np.asarray(low, dtype=np.float64), (D,)))
+        high = np.ascontiguousarray(np.broadcast_to(np.asarray(high, dtype=np.float64), (D,)))
+        per = np.ascontiguousarray(np.broadcast_to(np.asarray(periodic), (D,)).astype(np.uint8))
+        check(self._h, self._lib.abr_domain_set(self._h, D, low.ctypes.data, high.ctypes.data, per.ctypes.data, float(n_particles_in_leaf)))
+        self.low, self.high, self.periodic = low, high, per
+        self.update_positions()
+        self.searchable = True
+
+    def force_grid(self, low, high, periodic, size):
+        D = self.D
+        low = np.ascontiguousarray(np.broadcast_to(np.asarray(low, dtype=np.float64), (D,)))
+        high = np.ascontiguousarray(np.broadcast_to(np.asarray(high, dtype=np.float64), (D,)))
+        per = np.ascontiguousarray(np.broadcast_to(np.asarray(periodic), (D,)).astype(np.uint8))
+        size = np.ascontiguousarray(np.broadcast_to(np.asarray(size), (D,)).astype(np.uint32))
+        check(self._h, self._lib.abr_domain_force_grid(self._h, D, low.ctypes.data, high.ctypes.data, per.ctypes.data, size.ctypes.data))
+        self.low, self.high, self.periodic = low, high, per
+        self.update_positions()
+        self.searchable = True
+
+    def grid(self):
+        size = np.zeros(self.D, dtype=np.uint32)
+        side = np.zeros(self.D, dtype=np.float64)
+        nb = C.c_uint64()
+        check(self._h, self._lib.abr_domain_get(self._h, size.ctypes.data, side.ctypes.data, C.byref(nb)))
+        return size, side, nb.value
+
+    def update_positions(self):
+        """wrap / kill, build the ordered cell list, reorder every column."""
+        self._sync_stream()
+        n = self.size()
+        pos = self.columns["position"]
+        alive = self.columns["alive"]
+        order = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        n_alive = C.c_size_t(0)
+        check(self._h, self._lib.abr_celllist_build(self._h, _ptr(pos), _ptr(alive), n, _ptr(order), C.byref(n_alive)))
+        na = n_alive.value
+        self._order = order[:na]
+        # reorder: gather every column into the other buffer and swap
+        names = list(self.columns)
+        src = [self.columns[k] for k in names]
+        dst = [torch.empty((na,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for t in src]
+        if na > 0:
+            nc = len(names)
+            SP = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
+            DP = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
+            EB = (C.c_size_t * nc)(*[t.element_size() * int(np.prod(t.shape[1:], dtype=np.int64)) for t in src])
+            check(self._h, self._lib.abr_gather_columns(self._h, nc, SP, DP, EB, _ptr(order), na))
+        self._other = dict(zip(names, src))
+        self.columns = dict(zip(names, dst))
+        check(self._h, self._lib.abr_query_set_particles(self._h, _ptr(self.columns["position"]), na))
+        self.n_buckets = self.grid()[2]
+        return na
+
+    def get_alive_indicies(self):
+        """m_alive_indices after the sort: new[k] = old[order[k]]"""
+        return self._order
+
+    def get_query(self):
+        return Query(self)
+
+    def _bucket_view(self):
+        ki, bb, be = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nb = C.c_uint64()
+        check(self._h, self._lib.abr_celllist_get(self._h, C.byref(ki), C.byref(bb), C.byref(be), C.byref(nb)))
+        n = self.size()
+
+        check(self._h, self._lib.abr_synchronize(self._h))
+
+        def view(ptr, count):
+            if count == 0 or not ptr.value:
+                return torch.empty(0, dtype=torch.int32, device=self.device)
+            return torch.as_tensor(_DevArray(ptr.value, count, "<i4"), device=self.device).clone()
+
+        return view(ki, n), view(bb, nb.value), view(be, nb.value)
+
+    def last_counters(self):
+        c = (C.c_uint64 * 4)()
+        check(self._h, self._lib.abr_last_counters(self._h, C.byref(c)))
+        return dict(walk_rows=int(c[0]), aliased=int(c[1]), launches=int(c[2]))
+
+    def pair_stats(self, radius, rows=None, path=-1, radius_per_row=None):
+        """per-row neighbour count and pair-set hash of euclidean_search"""
+        self._sync_stream()
+        rows_are_cols = rows is None
+        rp = self.columns["position"] if rows is None else torch.as_tensor(rows, dtype=torch.float64, device=self.device).contiguous()
+        n = rp.shape[0]
+        cnt = torch.zeros(n, dtype=torch.int32, device=self.device)
+        hs = torch.zeros(n, dtype=torch.int64, device=self.device)
+        rpr = None
+        if radius_per_row is not None:
+            rpr = torch.as_tensor(radius_per_row, dtype=torch.float64, device=self.device).contiguous()
+        check(self._h, self._lib.abr_pair_stats(self._h, _ptr(rp), n, int(rows_are_cols), float(radius), _ptr(rpr), int(path), _ptr(cnt), _ptr(hs)))
+        return cnt, hs
+
+
+class _DevArray:
+    """borrowed device memory exposed through __cuda_array_interface__"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class SparseOperator:
+    """MatrixReplacement<1,1,tuple<KernelSparse[Const]>> (src/Operators.h:75-291)."""
+
+    def __init__(self, rows, cols, radius, kernel, radius_per_row=None):
+        if not isinstance(kernel, Kernel):
+            raise TypeError("kernel must be an aboria_b200.kernels.Kernel")
+        self.row_particles = rows
+        self.col_particles = cols
+        self.radius = float(radius) if radius is not None else 0.0
+        self.radius_per_row = radius_per_row
+        self.kernel = kernel
+
+    def rows(self):
+        return self.row_particles.size() * self.kernel.block_rows
+
+    def cols(self):
+        return self.col_particles.size() * self.kernel.block_cols
+
+    def _desc(self):
+        k = self.kernel
+        d = KernelDesc()
+        d.kernel_id, d.block_rows, d.block_cols = k.kernel_id, k.block_rows, k.block_cols
+        for i, p in enumerate(k.params):
+            d.params[i] = p
+        keep = []
+        for i, name in enumerate(k.row_vars):
+            t = self.row_particles.get(name)
+            keep.append(t)
+            d.row_vars[i] = t.data_ptr()
+        for i, name in enumerate(k.col_vars):
+            t = self.col_particles.get(name)
+            keep.append(t)
+            d.col_vars[i] = t.data_ptr()
+        return d, keep
+
+    def evaluate(self, y, b, count_pairs=False):
+        """y += K b, device tensors (KernelSparse::evaluate, src/Kernels.h:720-751)."""
+        cols, rows = self.col_particles, self.row_particles
+        if not cols.searchable:
+            raise AbrError("column particle set has no neighbour search (call init_neighbour_search)")
+        if b.shape[0] != self.cols() or y.shape[0] != self.rows():
+            raise ValueError("vector has incompatible size")
+        if b.dtype != torch.float64 or y.dtype != torch.float64 or not b.is_contiguous() or not y.is_contiguous():
+            raise ValueError("b and y must be contiguous float64 device tensors")
+        cols._sync_stream()
+        d, keep = self._desc()
+        rpr = None
+        if self.radius_per_row is not None:
+            rpr = torch.as_tensor(self.radius_per_row, dtype=torch.float64, device=cols.device).contiguous()
+        npairs = C.c_uint64(0)
+        rp = rows.get("position")
+        rc = cols._lib.abr_sparse_matvec(cols._h, _ptr(rp), rows.size(), int(rows is cols), C.byref(d), self.radius, _ptr(rpr), _ptr(b), _ptr(y),
+                                         C.byref(npairs) if count_pairs else None)
+        check(cols._h, rc)
+        del keep
+        return npairs.value if count_pairs else None
+
+    def matvec(self, b):
+        """y = K * b  (Eigen zeroes y first, src/detail/Operators.h:219-232)."""
+        y = torch.zeros(self.rows(), dtype=torch.float64, device=self.col_particles.device)
+        self.evaluate(y, b)
+        return y
+
+    __mul__ = matvec
+    __matmul__ = matvec
+
+    def matvec_host(self, b_host, out_host=None):
+        """Host-buffer entry: copies b to the device, applies K, copies y back.
+        b_host / out_host are (ideally pinned) CPU tensors or numpy arrays."""
+        dev = self.col_particles.device
+        bt = torch.as_tensor(b_host, dtype=torch.float64)
+        b = bt.to(dev, non_blocking=True)
+        y = self.matvec(b)
+        if out_host is None:
+            return y.cpu()
+        out_host.copy_(y, non_blocking=False)
+        return out_host
+
+
+def create_sparse_operator(row_particles, col_particles, radius, kernel):
+    """create_sparse_operator(rows, cols, radius | radius_function, f)
+    (src/Operators.h:478-516).  `radius` may be a float or a per-row array
+    (the FRadius overload evaluated on the row particles)."""
+    if np.isscalar(radius):
+        return SparseOperator(row_particles, col_particles, radius, kernel)
+    return SparseOperator(row_particles, col_particles, None, kernel, radius_per_row=radius)

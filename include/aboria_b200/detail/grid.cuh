@@ -1,0 +1,228 @@
+// Device-side view of the ordered cell list (the CellListOrderedQuery POD,
+// /root/reference/src/CellListOrdered.h:285-599) and the exact per-row search
+// walk (search_iterator + lattice_iterator_within_distance).
+//
+// Everything here must be compiled WITHOUT floating-point contraction
+// (nvcc -fmad=false): the acceptance predicate ||dx||^2 <= r^2 and the bucket
+// index arithmetic have to round exactly like the reference's un-fused host
+// code.
+#ifndef ABORIA_B200_DETAIL_GRID_CUH_
+#define ABORIA_B200_DETAIL_GRID_CUH_
+
+#include <stdint.h>
+
+namespace abr {
+
+constexpr int MAXD = 3;
+
+// by-value kernel argument; mirrors the fields of CellListOrderedQuery
+// (src/CellListOrdered.h:305-365) that the search path reads
+struct Grid {
+  int D;
+  int size[MAXD];      // m_size
+  int end[MAXD];       // m_end_bucket = m_size - 1
+  int periodic[MAXD];  // m_periodic
+  double bmin[MAXD], bmax[MAXD];
+  double side[MAXD];      // m_bucket_side_length
+  double inv_side[MAXD];  // 1.0 / side (src/detail/SpatialUtil.h:116)
+  double L[MAXD];         // bmax - bmin (one rounding, as in Search.h:188-190)
+  uint32_t ncells;        // m_size.prod()
+  uint32_t key_bound;     // keys of alive particles are < key_bound; dead = key_bound
+};
+
+struct Query {
+  Grid g;
+  const double *pos;            // sorted positions, n x D AoS
+  const uint32_t *bucket_begin; // m_bucket_begin
+  const uint32_t *bucket_end;   // m_bucket_end
+  uint32_t n;
+};
+
+// src/detail/SpatialUtil.h:49-59 collapse_index_vector (last dim fastest,
+// unsigned multiplier)
+template <int D> __host__ __device__ inline int collapse_index(const Grid &g, const int *v) {
+  int index = 0;
+  unsigned int multiplier = 1;
+#pragma unroll
+  for (int i = D - 1; i >= 0; --i) {
+    if (i != D - 1) multiplier *= (unsigned)g.size[i + 1];
+    index += multiplier * v[i];
+  }
+  return index;
+}
+
+// src/detail/SpatialUtil.h:118-131: floor((r - bmin) * inv_side) per dim
+template <int D> __device__ inline int point_to_bucket(const Grid &g, const double *r) {
+  int v[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) v[d] = (int)floor((r[d] - g.bmin[d]) * g.inv_side[d]);
+  return collapse_index<D>(g, v);
+}
+
+// ---------------------------------------------------------------------------
+// lattice_iterator_within_distance<Query,2,IdentityTransform>
+// (src/NeighbourSearchBase.h:1720-2009), restated for the device.
+// ---------------------------------------------------------------------------
+template <int D> struct BucketWalk {
+  const Grid &g;
+  double qp[D];
+  double half[D];
+  double r2;
+  int quadrant;
+  bool valid;
+  int mn[D];
+  int index[D];
+
+  __device__ inline bool qbit(int i) const { return 1 == ((quadrant >> i) & 1); }
+
+  // :1884-1892 with find_bucket_centre = (v + 0.5) * side + bmin
+  __device__ inline double min_dist2(const int *b) const {
+    double acc = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double centre = ((double)b[i] + 0.5) * g.side[i] + g.bmin[i];
+      const double t = fmax(fabs(centre - qp[i]) - half[i], 0.0);
+      acc = acc + t * t;
+    }
+    return acc;
+  }
+  // :1950-1958
+  __device__ inline bool outside_domain() const {
+    double acc = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double dx = 0.5 * (g.bmin[i] + g.bmax[i]) - qp[i];
+      const double hl = 0.5 * (g.bmax[i] - g.bmin[i]);
+      const double t = fmax(fabs(dx) - hl, 0.0);
+      acc = acc + t * t;
+    }
+    return acc > r2;
+  }
+  // :1895-1947
+  __device__ inline void reset_min_and_index() {
+    bool no_buckets = true;
+    while (valid && no_buckets) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+        mn[i] = (int)floor((qp[i] + (qbit(i) ? 0.5 : -0.5) * g.side[i] - g.bmin[i]) * g.inv_side[i]);
+      no_buckets = min_dist2(mn) > r2;
+      if (!no_buckets) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          if (qbit(i)) {
+            if (mn[i] < 0) {
+              mn[i] = 0;
+            } else if (mn[i] > g.end[i]) {
+              no_buckets = true;
+              mn[i] = g.end[i];
+            }
+          } else {
+            if (mn[i] < 0) {
+              no_buckets = true;
+              mn[i] = 0;
+            } else if (mn[i] > g.end[i]) {
+              mn[i] = g.end[i];
+            }
+          }
+        }
+      }
+      if (no_buckets) {
+        ++quadrant;
+        if (quadrant >= (1 << D)) valid = false;
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) index[i] = mn[i];
+      }
+    }
+  }
+  // :1779-1804
+  __device__ inline BucketWalk(const Grid &grid, const double *point, double R2)
+      : g(grid), r2(R2), quadrant(0), valid(true) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) qp[i] = point[i];
+    if (outside_domain()) {
+      valid = false;
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) half[i] = 0.5 * g.side[i];
+      reset_min_and_index();
+    }
+  }
+  // :1960-2004
+  __device__ inline void increment() {
+#pragma unroll
+    for (int i = D - 1; i >= 0; --i) {
+      bool potential = true;
+      if (qbit(i)) {
+        ++index[i];
+        potential = index[i] <= g.end[i];
+      } else {
+        --index[i];
+        potential = index[i] >= 0;
+      }
+      if (potential) potential = min_dist2(index) <= r2;
+      if (potential) break;
+      index[i] = mn[i];
+      if (i == 0) {
+        ++quadrant;
+        if (quadrant < (1 << D)) {
+          reset_min_and_index();
+        } else {
+          valid = false;
+        }
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// search_iterator<Query,2> (src/Search.h:66-496) as a visitor: image lattice
+// (last dim fastest, :152-159) x buckets near cur = r + image*L (:188-190) x
+// particles of the bucket, accept iff !(sum dx^2 > R2) (:438-446).
+// visit(j, dx, image_linear_index)
+// ---------------------------------------------------------------------------
+template <int D, typename Visit>
+__device__ inline void search_walk(const Query &q, const double *r, double R, Visit &&visit) {
+  const Grid &g = q.g;
+  const double R2 = R * R;
+  int img[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) img[i] = g.periodic[i] ? -1 : 0;
+  int image_counter = 0;
+  while (true) {
+    double cur[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) cur[i] = r[i] + (double)img[i] * g.L[i];
+    for (BucketWalk<D> b(g, cur, R2); b.valid; b.increment()) {
+      const unsigned c = (unsigned)collapse_index<D>(g, b.index);
+      const unsigned jb = q.bucket_begin[c], je = q.bucket_end[c];
+      for (unsigned j = jb; j < je; ++j) {
+        double dx[D];
+        double acc = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) dx[i] = q.pos[(size_t)j * D + i] - cur[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc = acc + dx[i] * dx[i];
+        if (!(acc > R2)) visit(j, dx, acc, image_counter);
+      }
+    }
+    ++image_counter;
+    int i = D - 1;
+    for (; i >= 0; --i) {
+      const int hi = g.periodic[i] ? 2 : 1;
+      if (++img[i] < hi) break;
+      img[i] = g.periodic[i] ? -1 : 0;
+    }
+    if (i < 0) break;
+  }
+}
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+} // namespace abr
+#endif

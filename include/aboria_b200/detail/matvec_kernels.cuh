@@ -1,0 +1,377 @@
+// Sparse kernel operator product y += K b for sm_100a
+// (KernelSparse::evaluate, /root/reference/src/Kernels.h:720-751).
+//
+// Two kernels, both templated on the dimension and on a device functor F
+// (the user's lambda f(dx, a_i, b_j), src/detail/Kernels.h:336-357):
+//
+//  * tiled_kernel  — the hot path when the row set is the column set
+//    (create_sparse_operator(p, p, r, f)).  One warp per target bucket; the
+//    candidates are the contiguous particle runs of the neighbouring buckets
+//    (last dimension contiguous in the sorted array), 32 candidates per step
+//    (one per lane, positions and b_j in registers), the rows of the target
+//    bucket are broadcast from shared memory.  The acceptance test is the
+//    reference's exact un-fused fp64 predicate.  Partial sums live in a
+//    per-warp shared-memory table part[row][lane] and are reduced once per
+//    bucket in a fixed order (deterministic results).
+//    Rows whose result could depend on rounding in the reference's bucket
+//    iterator (a coordinate within `tolf` of a bucket face / centre, or an
+//    accepted pair within `r2lo..r2` of the cut-off) are NOT finished here:
+//    they are appended to a list and recomputed by walk_kernel, which restates
+//    the reference iterator exactly.  So the pair set is the reference's, always.
+//
+//  * walk_kernel — one thread per row, the reference's search_iterator walk
+//    (grid.cuh).  Used for arbitrary row sets, per-row radii, the listed rows
+//    above, and whenever the tiled preconditions do not hold.
+//
+// No tensor cores: this is a gather + pointwise fp64 path (north_star).
+#ifndef ABORIA_B200_DETAIL_MATVEC_KERNELS_CUH_
+#define ABORIA_B200_DETAIL_MATVEC_KERNELS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aboria_b200/detail/grid.cuh"
+
+// opaque in abr.h
+struct abr_matvec_plan {
+  abr::Query q;
+  // rows
+  const double *row_pos;
+  uint32_t n_rows;
+  int rows_are_cols;
+  double radius;
+  const double *radius_per_row;
+  const double *b;
+  double *y;
+  // tiled path
+  int use_tiled;
+  int w[abr::MAXD];        // stencil half width per dimension
+  double r2, r2lo;         // cut-off^2 and the "rounding sensitive" lower edge
+  double tolf[abr::MAXD];  // fractional bucket coordinate tolerance
+  uint32_t *work_counter;
+  uint32_t *danger_count;
+  uint32_t *danger_list;
+  uint32_t danger_capacity;
+  // stats (pair_stats): when non-null the kernels count/hash instead of evaluating F
+  uint32_t *stat_count;
+  uint64_t *stat_hash;
+  // launch
+  cudaStream_t stream;
+  int sm_count;
+  int walk_only_list; // walk kernel processes danger_list instead of all rows
+};
+
+namespace abr {
+
+constexpr int TILED_WARPS = 8;
+constexpr int TILED_THREADS = TILED_WARPS * 32;
+constexpr int ROW_BATCH = 32;
+
+// functor used by pair_stats; never evaluated
+struct StatsFunctor {
+  static constexpr int BR = 1, BC = 1;
+  __device__ void operator()(const double *, double, uint32_t, uint32_t, double *blk) const { blk[0] = 0; }
+};
+
+template <int D> __device__ inline int image_linear_index(const Grid &g, const int *img) {
+  // position of `img` in the reference's periodic lattice_iterator
+  // (src/Search.h:152-159; last dimension fastest)
+  int idx = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) idx = idx * (g.periodic[d] ? 3 : 1) + (g.periodic[d] ? img[d] + 1 : 0);
+  return idx;
+}
+
+// ---------------------------------------------------------------------------
+// walk_kernel
+// ---------------------------------------------------------------------------
+template <int D, class F, bool STATS>
+__global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, const F f) {
+  constexpr int BR = F::BR, BC = F::BC;
+  const uint32_t total = p.walk_only_list ? min(*p.danger_count, p.danger_capacity) : p.n_rows;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t i = p.walk_only_list ? p.danger_list[t] : t;
+    double r[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) r[d] = p.row_pos[(size_t)i * D + d];
+    const double R = p.radius_per_row ? p.radius_per_row[i] : p.radius;
+    if (STATS) {
+      uint32_t cnt = 0;
+      uint64_t hs = 0;
+      search_walk<D>(p.q, r, R, [&](unsigned j, const double *, double, int image) {
+        ++cnt;
+        hs += mix64((uint64_t)j * 81u + (uint64_t)image);
+      });
+      if (p.stat_count) p.stat_count[i] = cnt;
+      if (p.stat_hash) p.stat_hash[i] = hs;
+    } else {
+      double acc[BR];
+#pragma unroll
+      for (int a = 0; a < BR; ++a) acc[a] = p.y[(size_t)i * BR + a];
+      search_walk<D>(p.q, r, R, [&](unsigned j, const double *dx, double d2, int) {
+        double blk[BR * BC];
+        f(dx, d2, i, j, blk);
+#pragma unroll
+        for (int a = 0; a < BR; ++a) {
+          double s = 0;
+#pragma unroll
+          for (int c = 0; c < BC; ++c) s += blk[a * BC + c] * p.b[(size_t)j * BC + c];
+          acc[a] += s;
+        }
+      });
+#pragma unroll
+      for (int a = 0; a < BR; ++a) p.y[(size_t)i * BR + a] = acc[a];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tiled_kernel
+// ---------------------------------------------------------------------------
+template <int D, class F, bool STATS> struct TiledSmem {
+  static constexpr int NACC = STATS ? 2 : F::BR;
+  // per warp: rows (unshifted / shifted, padded to 4 doubles), partial table
+  double rows0[TILED_WARPS][ROW_BATCH][4];
+  double rowsS[TILED_WARPS][ROW_BATCH][4];
+  unsigned long long part[TILED_WARPS][NACC][ROW_BATCH][32];
+  uint32_t danger[TILED_WARPS];
+  uint32_t chunk_base;
+};
+
+constexpr uint32_t TILED_CHUNK = 64; // buckets claimed per scheduler step by a CTA
+
+template <int D, class F, bool STATS>
+__global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_plan p, const F f) {
+  constexpr int BR = F::BR, BC = F::BC;
+  constexpr int NACC = STATS ? 2 : BR;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto &sm = *reinterpret_cast<TiledSmem<D, F, STATS> *>(smem_raw);
+  const Grid &g = p.q.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double *__restrict__ pos = p.q.pos;
+  const uint32_t *__restrict__ bbeg = p.q.bucket_begin;
+  const uint32_t *__restrict__ bend = p.q.bucket_end;
+  const double R2 = p.r2, R2LO = p.r2lo;
+  constexpr int L = D - 1; // last (fastest, memory-contiguous) dimension
+
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) sm.chunk_base = atomicAdd(p.work_counter, TILED_CHUNK);
+    __syncthreads();
+    const uint32_t chunk = sm.chunk_base;
+    if (chunk >= g.ncells) break;
+    const uint32_t chunk_end = min(chunk + TILED_CHUNK, g.ncells);
+
+    for (uint32_t cell = chunk + warp; cell < chunk_end; cell += TILED_WARPS) {
+      const uint32_t rb = bbeg[cell], re = bend[cell];
+      if (rb == re) continue;
+      // bucket coordinates of the target (inverse of collapse_index)
+      int tc[D];
+      {
+        uint32_t rem = cell;
+#pragma unroll
+        for (int d = D - 1; d >= 0; --d) {
+          tc[d] = (int)(rem % (uint32_t)g.size[d]);
+          rem /= (uint32_t)g.size[d];
+        }
+      }
+      for (uint32_t r0 = rb; r0 < re; r0 += ROW_BATCH) {
+        const int nr = (int)min((uint32_t)ROW_BATCH, re - r0);
+        // ---- load the rows of this batch, flag rounding-sensitive ones ----
+        bool my_danger = false;
+        if (lane < nr) {
+          double r[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            r[d] = pos[(size_t)(r0 + lane) * D + d];
+            sm.rows0[warp][lane][d] = r[d];
+            const double fl = (r[d] - g.bmin[d]) * g.inv_side[d];
+            const double fr = fl - floor(fl);
+            my_danger |= ((int)floor(fl) != tc[d]) | (fr < p.tolf[d]) | (fr > 1.0 - p.tolf[d]) |
+                         (fabs(fr - 0.5) < p.tolf[d]);
+          }
+        }
+        if (lane == 0) sm.danger[warp] = 0;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+          for (int i = 0; i < nr; ++i) sm.part[warp][a][i][lane] = 0ull;
+        __syncwarp();
+
+        // ---- neighbouring buckets: offsets in the D-1 slow dims, runs in the last ----
+        int o[D > 1 ? D - 1 : 1];
+#pragma unroll
+        for (int d = 0; d < D - 1; ++d) o[d] = -p.w[d];
+        bool more = true;
+        while (more) {
+          // resolve the slow dimensions (wrap -> image) once per run family
+          int nc[D], img[D];
+          bool ok_slow = true;
+#pragma unroll
+          for (int d = 0; d < D - 1; ++d) {
+            int u = tc[d] + o[d];
+            img[d] = 0;
+            if (u < 0) {
+              u += g.size[d];
+              img[d] = 1;
+            } else if (u >= g.size[d]) {
+              u -= g.size[d];
+              img[d] = -1;
+            }
+            ok_slow &= (u >= 0) & (u < g.size[d]) & (img[d] == 0 || g.periodic[d]);
+            nc[d] = u;
+          }
+          if (ok_slow) {
+            // last dimension: up to three image segments of the unwrapped range
+            const int zlo = tc[L] - p.w[L], zhi = tc[L] + p.w[L];
+            const int S = g.size[L];
+            for (int m = (g.periodic[L] ? -1 : 0); m <= (g.periodic[L] ? 1 : 0); ++m) {
+              // unwrapped indices [m*S, m*S + S - 1] map to buckets [0,S-1] with image -m
+              const int a = max(zlo, m * S), bnd = min(zhi, m * S + S - 1);
+              if (a > bnd) continue;
+              img[L] = -m;
+              nc[L] = a - m * S;
+              const uint32_t c_lo = (uint32_t)collapse_index<D>(g, nc);
+              const uint32_t c_hi = c_lo + (uint32_t)(bnd - a);
+              const uint32_t jb = bbeg[c_lo], je = bend[c_hi];
+              if (jb >= je) continue;
+              bool shifted = false;
+#pragma unroll
+              for (int d = 0; d < D; ++d) shifted |= (img[d] != 0);
+              const double(*rowp)[4] = sm.rows0[warp];
+              if (shifted) {
+                __syncwarp();
+                if (lane < nr) {
+#pragma unroll
+                  for (int d = 0; d < D; ++d)
+                    sm.rowsS[warp][lane][d] = sm.rows0[warp][lane][d] + (double)img[d] * g.L[d];
+                }
+                __syncwarp();
+                rowp = sm.rowsS[warp];
+              }
+              const int image_id = STATS ? image_linear_index<D>(g, img) : 0;
+              for (uint32_t cb = jb; cb < je; cb += 32) {
+                const uint32_t j = cb + lane;
+                const bool valid = j < je;
+                double pj[D], bj[BC];
+#pragma unroll
+                for (int d = 0; d < D; ++d) pj[d] = valid ? pos[(size_t)j * D + d] : 0.0;
+                if (!STATS) {
+#pragma unroll
+                  for (int c = 0; c < BC; ++c) bj[c] = valid ? p.b[(size_t)j * BC + c] : 0.0;
+                }
+                for (int i = 0; i < nr; ++i) {
+                  double dx[D];
+                  double acc = 0;
+#pragma unroll
+                  for (int d = 0; d < D; ++d) dx[d] = pj[d] - rowp[i][d];
+#pragma unroll
+                  for (int d = 0; d < D; ++d) acc = acc + dx[d] * dx[d];
+                  if (valid && !(acc > R2)) {
+                    if (acc > R2LO) atomicOr(&sm.danger[warp], 1u << i);
+                    if (STATS) {
+                      sm.part[warp][0][i][lane] += 1ull;
+                      sm.part[warp][1][i][lane] += mix64((uint64_t)j * 81u + (uint64_t)image_id);
+                    } else {
+                      double blk[BR * BC];
+                      f(dx, acc, r0 + i, j, blk);
+#pragma unroll
+                      for (int a2 = 0; a2 < BR; ++a2) {
+                        double s = 0;
+#pragma unroll
+                        for (int c = 0; c < BC; ++c) s += blk[a2 * BC + c] * bj[c];
+                        double *slot = reinterpret_cast<double *>(&sm.part[warp][a2][i][lane]);
+                        *slot += s;
+                      }
+                    }
+                  }
+                }
+              }
+            }
+          }
+          // next offset tuple in the slow dimensions (odometer)
+          more = false;
+#pragma unroll
+          for (int d = D - 2; d >= 0; --d) {
+            if (!more) {
+              if (++o[d] <= p.w[d]) {
+                more = true;
+              } else {
+                o[d] = -p.w[d];
+              }
+            }
+          }
+        }
+        __syncwarp();
+
+        // ---- reduce part[row][*] in a fixed (skewed, conflict-free) order ----
+        const uint32_t dmask = sm.danger[warp] | __ballot_sync(0xFFFFFFFFu, my_danger);
+        if (lane < nr) {
+          const bool dangerous = (dmask >> lane) & 1u;
+          if (dangerous) {
+            const uint32_t slot = atomicAdd(p.danger_count, 1u);
+            if (slot < p.danger_capacity) p.danger_list[slot] = r0 + lane;
+          } else if (STATS) {
+            unsigned long long c = 0, hsum = 0;
+            for (int k = 0; k < 32; ++k) {
+              c += sm.part[warp][0][lane][(k + lane) & 31];
+              hsum += sm.part[warp][1][lane][(k + lane) & 31];
+            }
+            if (p.stat_count) p.stat_count[r0 + lane] = (uint32_t)c;
+            if (p.stat_hash) p.stat_hash[r0 + lane] = hsum;
+          } else {
+#pragma unroll
+            for (int a2 = 0; a2 < NACC; ++a2) {
+              double s = 0;
+              for (int k = 0; k < 32; ++k)
+                s += *reinterpret_cast<double *>(&sm.part[warp][a2][lane][(k + lane) & 31]);
+              p.y[(size_t)(r0 + lane) * BR + a2] += s;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// launcher, instantiated per (D, Functor) — in libabr.so for the built-in
+// functors, in the user's nvcc-compiled TU for custom ones.
+// ---------------------------------------------------------------------------
+template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_plan &p, const F &f) {
+  cudaError_t e;
+  if (p.use_tiled) {
+    using SM = TiledSmem<D, F, STATS>;
+    const size_t smem = sizeof(SM);
+    auto kern = tiled_kernel<D, F, STATS>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILED_THREADS, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const unsigned max_chunks = (p.q.g.ncells + TILED_CHUNK - 1) / TILED_CHUNK;
+    unsigned grid = (unsigned)(p.sm_count * per_sm);
+    if (grid > max_chunks) grid = max_chunks;
+    if (grid < 1) grid = 1;
+    kern<<<grid, TILED_THREADS, smem, p.stream>>>(p, f);
+    // rows handed over by the tiled kernel: exact per-row walk
+    abr_matvec_plan p2 = p;
+    p2.walk_only_list = 1;
+    walk_kernel<D, F, STATS><<<p.sm_count, 128, 0, p.stream>>>(p2, f);
+  } else {
+    const unsigned grid = (unsigned)((p.n_rows + 127) / 128);
+    if (grid > 0) walk_kernel<D, F, STATS><<<grid, 128, 0, p.stream>>>(p, f);
+  }
+  e = cudaGetLastError();
+  return (int)e;
+}
+
+template <int D, class F> struct sparse_launcher {
+  static int launch(const abr_matvec_plan *plan, const void *functor_host) {
+    return launch_plan<D, F, false>(*plan, *static_cast<const F *>(functor_host));
+  }
+};
+
+} // namespace abr
+#endif

@@ -1,0 +1,141 @@
+// Device functors for the sparse kernel operator: the built-in set selected
+// by abr_kernel_desc::kernel_id, and the pattern a user follows for a custom
+// one (the reference takes a host lambda f(dx, a, b),
+// /root/reference/src/Operators.h:478-516; a GPU needs it as a device functor
+// compiled by nvcc).
+//
+// A functor provides
+//     static constexpr int BR, BC;                       // block size
+//     __device__ void operator()(const double *dx,       // r_b - r_a (periodic image applied)
+//                                double d2,              // sum dx^2, same order as the cut-off test
+//                                uint32_t i, uint32_t j, // row / column particle index
+//                                double *blk) const;     // BR x BC, row major
+// and captures whatever per-particle columns it needs as raw device pointers
+// (get<variable>(a) -> col[i]).
+//
+// Custom functor in a user .cu file:
+//     struct MyKernel { static constexpr int BR = 1, BC = 1; const double *w;
+//       __device__ void operator()(const double *dx, double d2, uint32_t i, uint32_t j, double *blk) const
+//       { blk[0] = w[i] * w[j] * exp(-d2); } };
+//     MyKernel k{w_dev};
+//     abr_sparse_matvec_custom(h, pos, n, 1, &abr::sparse_launcher<3, MyKernel>::launch, &k,
+//                              1, 1, radius, nullptr, b, y, nullptr);
+#ifndef ABORIA_B200_DEVICE_KERNEL_CUH_
+#define ABORIA_B200_DEVICE_KERNEL_CUH_
+
+#include "abr.h"
+#include "aboria_b200/detail/matvec_kernels.cuh"
+
+namespace abr {
+namespace functors {
+
+// tests/operators.h:842-847
+struct ConstSum {
+  static constexpr int BR = 1, BC = 1;
+  const double *s1, *s2;
+  __device__ void operator()(const double *, double, uint32_t i, uint32_t j, double *blk) const {
+    blk[0] = s1[i] + s2[j];
+  }
+};
+// tests/operators.h:905-911
+struct ConstSumDiff {
+  static constexpr int BR = 2, BC = 1;
+  const double *s1, *s2;
+  __device__ void operator()(const double *, double, uint32_t i, uint32_t j, double *blk) const {
+    blk[0] = s1[i] + s2[j];
+    blk[1] = s1[i] - s2[j];
+  }
+};
+// 1/(|dx| + eps)
+struct InvDist {
+  static constexpr int BR = 1, BC = 1;
+  double eps;
+  __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
+    blk[0] = 1.0 / (sqrt(d2) + eps);
+  }
+};
+// tests/operators.h:251-256
+struct InvDistAA {
+  static constexpr int BR = 1, BC = 1;
+  double eps;
+  const double *ai, *aj;
+  __device__ void operator()(const double *, double d2, uint32_t i, uint32_t j, double *blk) const {
+    blk[0] = (ai[i] * aj[j]) / (sqrt(d2) + eps);
+  }
+};
+// tests/rbf_interpolation.h:310-313: pow(2 - r/h, 4) * (1 + 2 r/h)
+struct WendlandC2 {
+  static constexpr int BR = 1, BC = 1;
+  double h;
+  __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
+    const double r = sqrt(d2);
+    const double t = 2.0 - r / h;
+    const double t2 = t * t;
+    blk[0] = (t2 * t2) * (1.0 + 2.0 * r / h);
+  }
+};
+// SURVEY §8d c3 (tests/md.h:166-174 pattern): Lennard-Jones force, D x 1 block
+template <int D> struct LJForce {
+  static constexpr int BR = D, BC = 1;
+  double sigma, eps;
+  __device__ void operator()(const double *dx, double d2, uint32_t, uint32_t, double *blk) const {
+    if (d2 == 0) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) blk[d] = 0.0;
+      return;
+    }
+    const double r = sqrt(d2);
+    const double sr = sigma / r;
+    const double sr2 = sr * sr;
+    const double sr6 = sr2 * sr2 * sr2;
+    const double fmag = 24.0 * eps * (2.0 * sr6 * sr6 - sr6) / (r * r);
+#pragma unroll
+    for (int d = 0; d < D; ++d) blk[d] = fmag * dx[d];
+  }
+};
+// tests/sph.h:154-165 W_fun (Wendland), times the particle mass
+template <int D> struct SphDensity {
+  static constexpr int BR = 1, BC = 1;
+  double h, mass, wcon;
+  __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
+    const double q = sqrt(d2) / h;
+    double W = 0.0;
+    if (q <= 2.0) {
+      double hD = h;
+#pragma unroll
+      for (int d = 1; d < D; ++d) hD *= h;
+      const double t = 2.0 - q;
+      const double t2 = t * t;
+      W = (1 / hD) * wcon * (t2 * t2) * (1.0 + 2.0 * q);
+    }
+    blk[0] = mass * W;
+  }
+};
+// tests/sph.h:140-152 F_fun and the pressure term of :333-339, D x 1 block
+template <int D> struct SphPressure {
+  static constexpr int BR = D, BC = 1;
+  double h, mass, wcon;
+  const double *pdr2_i, *pdr2_j;
+  __device__ void operator()(const double *dx, double d2, uint32_t i, uint32_t j, double *blk) const {
+    double Fv = 0.0;
+    const double r = sqrt(d2);
+    if (r != 0) {
+      const double q = r / h;
+      if (q <= 2.0) {
+        double hD2 = h * h;
+#pragma unroll
+        for (int d = 0; d < D; ++d) hD2 *= h;
+        const double t = 2.0 - q;
+        const double t3 = t * t * t;
+        Fv = (1 / hD2) * wcon * (-4 * t3 * (1 + 2 * q) + 2 * (t3 * t)) / q;
+      }
+    }
+    const double c = mass * (pdr2_i[i] + pdr2_j[j]) * Fv;
+#pragma unroll
+    for (int d = 0; d < D; ++d) blk[d] = c * dx[d];
+  }
+};
+
+} // namespace functors
+} // namespace abr
+#endif

@@ -1,0 +1,177 @@
+/* abr.h — C-ABI of the B200-native ordered cell list + sparse kernel matvec.
+ *
+ * This is the drop-in boundary for ONE hot path of Aboria (reference at
+ * /root/reference): CellListOrdered build followed by
+ * create_sparse_operator(...) * b.  The reference has no FFI; its seam is C++
+ * template substitution.  Each entry point below names the
+ * reference interface it replaces (file:line under /root/reference).  The C++
+ * shim in include/aboria_b200/Aboria.h keeps the reference's own names
+ * (Particles, init_neighbour_search, create_sparse_operator, K*b) on top of
+ * these calls; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array argument is a DEVICE pointer
+ *    unless its name ends in _host.
+ *  - all work is enqueued on the handle's CUDA stream; functions that return a
+ *    value through a *_host pointer synchronise that stream first.
+ *  - return value 0 = ok, nonzero = error (abr_last_error_string explains).
+ *    The reference prints and raises SIGTRAP (src/Log.h:47-62) and never
+ *    returns codes; the C++ shim turns a nonzero code into the same CHECK.
+ *  - there is NO CPU fallback: every call fails with ABR_ERR_CUDA when no
+ *    CUDA device / kernel image is available.
+ */
+#ifndef ABR_H_
+#define ABR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABR_MAX_D 3
+#define ABR_MAX_VARS 4
+#define ABR_MAX_PARAMS 8
+
+enum abr_status {
+  ABR_OK = 0,
+  ABR_ERR_INVALID = 1, /* bad argument */
+  ABR_ERR_CUDA = 2,    /* CUDA runtime error / no device */
+  ABR_ERR_STATE = 3,   /* call order (e.g. matvec before build) */
+  ABR_ERR_UNSUPPORTED = 4
+};
+
+/* Built-in device functors for F(dx, a_i, b_j) (src/detail/Kernels.h:336-357).
+ * Values mirror the reference tests' lambdas; custom functors go through
+ * abr_sparse_matvec_custom + include/aboria_b200/device_kernel.cuh. */
+enum abr_kernel_id {
+  ABR_K_CONST_SUM = 0,      /* s1(a)+s2(b)                 tests/operators.h:842-847 */
+  ABR_K_CONST_SUM_DIFF = 1, /* 2x1 (s1(a)+s2(b), s1(a)-s2(b)) tests/operators.h:905-911 */
+  ABR_K_INV_DIST = 2,       /* 1/(|dx|+p0)                 SURVEY §8d c1 */
+  ABR_K_INV_DIST_AA = 3,    /* a_i a_j/(|dx|+p0)           tests/operators.h:251-256 */
+  ABR_K_WENDLAND_C2 = 4,    /* (2-|dx|/p0)^4 (1+2|dx|/p0)  tests/rbf_interpolation.h:310-313 */
+  ABR_K_LJ_FORCE = 5,       /* Dx1: 24 p1 (2(p0/r)^12-(p0/r)^6)/r^2 dx  tests/md.h:166-174 pattern */
+  ABR_K_SPH_DENSITY = 6,    /* p1 * W(|dx|, p0), p2 = WCON tests/sph.h:154-165 */
+  ABR_K_SPH_PRESSURE = 7,   /* Dx1: p1 (rv0_i + cv0_j) F(|dx|,p0) dx    tests/sph.h:140-152, :333-339 */
+  ABR_K_COUNT_ = 8
+};
+
+/* Describes the kernel function of one sparse operator block
+ * (KernelSparse<Row,Col,FRadius,FWithDx>, src/Kernels.h:578-607). */
+typedef struct abr_kernel_desc {
+  int32_t kernel_id;                       /* enum abr_kernel_id */
+  int32_t block_rows, block_cols;          /* BR, BC (src/Kernels.h:599-600) */
+  int32_t reserved;
+  double params[ABR_MAX_PARAMS];           /* captured scalars of the lambda */
+  const double *row_vars[ABR_MAX_VARS];    /* per-row-particle variable columns */
+  const double *col_vars[ABR_MAX_VARS];    /* per-col-particle variable columns */
+} abr_kernel_desc;
+
+typedef struct abr_handle_s *abr_handle;
+
+/* One handle per (GPU, particle set): owns what the search object owns in the
+ * reference — m_bucket_begin/end/indices (src/CellListOrdered.h:272-283) and
+ * m_alive_indices (src/NeighbourSearchBase.h) — plus scratch.  `stream` is a
+ * cudaStream_t (NULL = legacy default stream). */
+int abr_create(abr_handle *out, int device, void *stream);
+int abr_destroy(abr_handle h);
+int abr_set_stream(abr_handle h, void *stream);
+int abr_synchronize(abr_handle h);
+const char *abr_last_error_string(abr_handle h);
+const char *abr_version(void);
+
+/* neighbour_search_base::set_domain + CellListOrdered::set_domain_impl
+ * (src/NeighbourSearchBase.h:252-268, src/CellListOrdered.h:132-186).  Host
+ * scalar math in the reference's expression order, including the rule that the
+ * grid is only recomputed when the alive count leaves [1/2, 2] x the count it
+ * was last computed with (:134-135).  Arrays are HOST pointers of length D. */
+int abr_domain_set(abr_handle h, int D, const double *bmin_host, const double *bmax_host,
+                   const uint8_t *periodic_host, double n_particles_in_leaf);
+/* m_size, m_bucket_side_length, number of buckets (host out, length D). */
+int abr_domain_get(abr_handle h, uint32_t *size_host, double *side_host, uint64_t *n_buckets_host);
+/* Bypass the occupancy rule and fix the grid (tests that build
+ * point_to_bucket_index by hand, tests/utils.h:76-93; slab ranks). */
+int abr_domain_force_grid(abr_handle h, int D, const double *bmin_host, const double *bmax_host,
+                          const uint8_t *periodic_host, const uint32_t *size_host);
+
+/* neighbour_search_base::update_positions (src/NeighbourSearchBase.h:350-495)
+ * for the ordered case + CellListOrdered::update_positions_impl
+ * (src/CellListOrdered.h:190-259):
+ *   pos   n x D AoS doubles, wrapped IN PLACE (enforce_domain_lambda :185-238)
+ *   alive n bytes, cleared IN PLACE for particles outside a non-periodic
+ *         domain or with non-finite coordinates
+ *   order_out  n int32: on return order_out[0..n_alive) = m_alive_indices after
+ *         sort_by_key, i.e. new[k] = old[order[k]]; stable within a bucket.
+ *   n_alive_host: number of alive particles (host; stream is synchronised).
+ * Bucket arrays stay owned by the handle (abr_celllist_get). */
+int abr_celllist_build(abr_handle h, double *pos, uint8_t *alive, size_t n, int32_t *order_out,
+                       size_t *n_alive_host);
+/* Device views of m_bucket_indices (sorted keys, n_alive), m_bucket_begin,
+ * m_bucket_end (n_buckets each) as left by the last build. */
+int abr_celllist_get(abr_handle h, const uint32_t **bucket_indices, const uint32_t **bucket_begin,
+                     const uint32_t **bucket_end, uint64_t *n_buckets_host);
+
+/* Particles::reorder -> detail::gather of every column
+ * (src/Particles.h:694-724, src/detail/Algorithms.h:718-745):
+ * dst[c][k] = src[c][order[k]] for k < n_out, element size elem_bytes[c].
+ * Out of place; the caller owns both buffers and swaps them (data.swap(other_data)).
+ * src/dst/elem_bytes are HOST arrays of ncols entries holding device pointers. */
+int abr_gather_columns(abr_handle h, int ncols, const void *const *src_host, void *const *dst_host,
+                       const size_t *elem_bytes_host, const int32_t *order, size_t n_out);
+
+/* neighbour_search_base::update_iterators (src/NeighbourSearchBase.h:504-512):
+ * point the query at the reordered position column (n_alive x D). */
+int abr_query_set_particles(abr_handle h, const double *pos_sorted, size_t n);
+
+/* KernelSparse::evaluate (src/Kernels.h:720-751): y += K b, where rows i with
+ * position row_pos[i] search the handle's (column) cell list within
+ * radius (or radius_per_row[i], FRadius of src/detail/Kernels.h:336-357) and
+ *   y[i*BR + p] += sum_q F(dx, a_i, b_j)(p,q) * b[j*BC + q].
+ * rows_are_cols != 0 asserts row_pos is the handle's own sorted position array
+ * (the create_sparse_operator(particles, particles, ...) case) and selects the
+ * cell-tiled kernel; otherwise rows are arbitrary points (no search structure
+ * needed on the row set, tests/rbf_interpolation.h:326).
+ * n_pairs_host (optional): accepted (i,j,image) pair count (synchronises). */
+int abr_sparse_matvec(abr_handle h, const double *row_pos, size_t n_rows, int rows_are_cols,
+                      const abr_kernel_desc *kernel_host, double radius,
+                      const double *radius_per_row, const double *b, double *y,
+                      uint64_t *n_pairs_host);
+
+/* Neighbour-set diagnostics used by the parity tests: per row the number of
+ * accepted (j,image) pairs of euclidean_search (src/Search.h:839-845) and an
+ * order-independent 64-bit hash of that set.  path 0 = cell-tiled kernel (needs
+ * rows_are_cols), path 1 = per-row iterator walk. */
+int abr_pair_stats(abr_handle h, const double *row_pos, size_t n_rows, int rows_are_cols,
+                   double radius, const double *radius_per_row, int path, uint32_t *count,
+                   uint64_t *hash);
+
+/* Counters of the last abr_sparse_matvec / abr_pair_stats on the tiled path:
+ * [0] rows re-done by the exact per-row walk (rounding-sensitive rows),
+ * [1] accepted pairs, [2] kernels launched by the last call. */
+int abr_last_counters(abr_handle h, uint64_t counters_host[4]);
+
+/* Custom device functor (user TU compiled by nvcc, see
+ * include/aboria_b200/device_kernel.cuh): `launch` is
+ * abr::sparse_launcher<D, Functor>::launch and `functor_host` points at the
+ * functor object (copied by value into the kernel arguments). */
+struct abr_matvec_plan; /* opaque, filled by the library */
+typedef int (*abr_launch_fn)(const struct abr_matvec_plan *plan, const void *functor_host);
+int abr_sparse_matvec_custom(abr_handle h, const double *row_pos, size_t n_rows, int rows_are_cols,
+                             abr_launch_fn launch, const void *functor_host, int block_rows,
+                             int block_cols, double radius, const double *radius_per_row,
+                             const double *b, double *y, uint64_t *n_pairs_host);
+
+/* Thin device-memory helpers so that C/C++ hosts need no CUDA headers. */
+int abr_malloc(abr_handle h, void **ptr_out, size_t bytes);
+int abr_free(abr_handle h, void *ptr);
+int abr_memcpy_h2d(abr_handle h, void *dst, const void *src_host, size_t bytes);
+int abr_memcpy_d2h(abr_handle h, void *dst_host, const void *src, size_t bytes);
+int abr_memset(abr_handle h, void *dst, int value, size_t bytes);
+int abr_host_alloc_pinned(void **ptr_out, size_t bytes);
+int abr_host_free_pinned(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABR_H_ */

@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle
+on identical seeded inputs.  Bit-exact for orders, keys, bucket ranges and
+neighbour pair sets; rel. L2 <= 1e-12 for product vectors (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import aboria_b200 as ab
+from aboria_b200 import kernels as K
+from aboria_b200 import synth
+from oracle import oracle as orc
+from util import assert_build_equal, build_both, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("D,N,nn,periodic", [
+    (1, 14, 1, False), (1, 14, 1, True), (1, 1000, 10, True), (1, 1000, 100, False),
+    (2, 1000, 10, True), (2, 1000, 10, False), (2, 1000, 1, True),
+    (3, 1, 10, True), (3, 3, 10, False), (3, 1000, 100, True), (3, 1000, 10, False), (3, 1000, 1, True),
+    (3, 5000, 10, True), (3, 100000, 10, True), (2, 100000, 10, False)])
+def test_build_parity(D, N, nn, periodic):
+    rng = np.random.default_rng(100 * D + N + nn)
+    pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+    o, out, p = build_both(pos, -1.0, 1.0, periodic, nn)
+    assert_build_equal(o, out, p)
+
+
+def test_build_dead_wrap_and_columns():
+    # out-of-domain, NaN/inf, pre-dead particles; periodic wrap; all columns follow
+    rng = np.random.default_rng(5)
+    N = 20000
+    pos = rng.uniform(-0.3, 1.3, size=(N, 3))
+    pos[::97, 1] = np.nan
+    pos[5::131, 2] = np.inf
+    alive = np.ones(N, dtype=np.uint8)
+    alive[3::50] = 0
+    periodic = [True, False, True]
+    vars_ = {"a": torch.float64, "v": (torch.float64, (3,)), "flag": torch.uint8, "rng": (torch.uint8, (104,)), "k": torch.int32}
+    pos0 = pos.copy()
+    o, out, p = build_both(pos, 0.0, 1.0, periodic, 10.0, alive=alive, variables=None)
+    assert_build_equal(o, out, p)
+    assert 0 < out["n_alive"] < N
+    # now with user columns: every column is gathered by the same order
+    p2 = ab.Particles(3, N, variables=vars_)
+    p2.set("position", torch.from_numpy(pos0.copy()))
+    p2.set("alive", torch.from_numpy(alive.copy()))
+    cols = {"a": rng.random(N), "v": rng.random((N, 3)), "flag": rng.integers(0, 255, N).astype(np.uint8),
+            "rng": rng.integers(0, 255, (N, 104)).astype(np.uint8), "k": rng.integers(0, 1 << 30, N).astype(np.int32)}
+    for k, v in cols.items():
+        p2.set(k, torch.from_numpy(v))
+    p2.init_neighbour_search(0.0, 1.0, periodic, 10.0)
+    order = out["order"]
+    for k, v in cols.items():
+        assert np.array_equal(p2.get(k).cpu().numpy(), v[order]), k
+    assert np.all(p2.get("alive").cpu().numpy() == 1)
+
+
+def test_build_empty_and_regrid():
+    p = ab.Particles(3, 0)
+    p.init_neighbour_search(0.0, 1.0, True)
+    assert p.size() == 0
+    # re-initialising with a very different n recomputes the grid (src/CellListOrdered.h:134-135)
+    pos = synth.uniform_positions(4000, 3)
+    o, out, p = build_both(pos, 0.0, 1.0, True)
+    assert_build_equal(o, out, p)
+    pos2 = synth.uniform_positions(5000, 3, seed=3)  # within [1/2, 2] x 4000: grid is kept
+    o_out = o.init_neighbour_search(pos2, 0.0, 1.0, True)
+    p.resize_from_positions(pos2)
+    p.init_neighbour_search(0.0, 1.0, True)
+    assert_build_equal(o, o_out, p)
+    pos3 = synth.uniform_positions(20000, 3, seed=4)  # outside: recomputed
+    o_out = o.init_neighbour_search(pos3, 0.0, 1.0, True)
+    p.resize_from_positions(pos3)
+    p.init_neighbour_search(0.0, 1.0, True)
+    assert_build_equal(o, o_out, p)
+
+
+def _stats_equal(o, out, p, r):
+    cnt_o, hs_o = o.pair_stats(out["pos"], r)
+    for path in (0, 1):
+        try:
+            cnt, hs = p.pair_stats(r, path=path)
+        except ab.AbrError:
+            assert path == 0  # tiled path may be inapplicable; the walk never is
+            continue
+        assert np.array_equal(cnt.cpu().numpy().view(np.uint32), cnt_o), (path, r)
+        assert np.array_equal(hs.cpu().numpy().view(np.uint64), hs_o), (path, r)
+    return cnt_o
+
+
+@pytest.mark.parametrize("D,N,r,nn,periodic", [
+    (1, 14, 0.1, 1, False), (1, 14, 0.1, 1, True), (1, 1000, 0.1, 10, True), (1, 1000, 0.1, 100, False),
+    (2, 1000, 0.5, 10, True), (2, 1000, 0.5, 10, False), (2, 1000, 0.2, 1, True), (2, 1000, 0.2, 1, False),
+    (3, 1000, 0.2, 100, True), (3, 1000, 0.2, 100, False), (3, 1000, 0.2, 10, True), (3, 1000, 0.2, 10, False),
+    (3, 1000, 0.2, 1, True), (3, 1000, 0.2, 1, False), (3, 1000, 1.2, 10, True), (2, 300, 2.5, 10, True)])
+def test_pair_sets_random(D, N, r, nn, periodic):
+    # the reference's helper_d_random cases (tests/neighbours.h:1273-1327) plus
+    # radii beyond L/2 (same particle through several images)
+    rng = np.random.default_rng(77 + D * 1000 + N + nn + int(periodic))
+    pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+    o, out, p = build_both(pos, -1.0, 1.0, periodic, nn)
+    cnt = _stats_equal(o, out, p, r)
+    brute = orc.brute_force_counts(out["pos"], [-1.0] * D, [1.0] * D, periodic, r)
+    assert np.array_equal(cnt, brute)
+
+
+@pytest.mark.parametrize("D,n,r,nn", [(1, 100, 1.5, 10), (2, 50, 1.0001, 10), (2, 50, 1.5, 10), (2, 20, 2.1, 10), (3, 10, 1.9, 10), (3, 10, 1.0001, 10),
+                                      (2, 32, 1.0, 1), (3, 12, 1.0, 1), (3, 12, 2.0, 8)])
+def test_pair_sets_lattice(D, n, r, nn):
+    # regular lattices (tests/neighbours.h:627-686, :1252-1260), including radii
+    # EXACTLY equal to lattice distances with particles on bucket centres/faces:
+    # the rounding-sensitive rows must be handed to the exact walk
+    idx = np.indices((n,) * D).reshape(D, -1).T[:, ::-1]
+    pos = idx.astype(np.float64) + 0.5
+    o, out, p = build_both(pos, 0.0, float(n), True, nn)
+    _stats_equal(o, out, p, r)
+    pos = idx.astype(np.float64)  # on bucket faces
+    o, out, p = build_both(pos, 0.0, float(n), True, nn)
+    _stats_equal(o, out, p, r)
+
+
+def test_sparse_operator_golden():
+    # tests/operators.h:810-933
+    diameter = 0.1
+    pos = np.array([[0, 0, 0], [diameter * 0.9, 0, 0], [diameter * 1.8, 0, 0]], dtype=np.float64)
+    p = ab.Particles(3, 3, variables={"scalar1": torch.float64, "scalar2": torch.float64})
+    p.set("position", torch.from_numpy(pos))
+    p.set("scalar1", torch.full((3,), 1.0, dtype=torch.float64))
+    p.set("scalar2", torch.full((3,), 2.0, dtype=torch.float64))
+    p.init_neighbour_search(-1.0, 1.0, False)
+    C1 = ab.create_sparse_operator(p, p, diameter, K.const_sum("scalar1", "scalar2"))
+    v = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64, device=p.device)
+    ids = p.get("id").cpu().numpy()
+    ans = (C1 * v).cpu().numpy()
+    expect = np.zeros(3)
+    for i in range(3):
+        for j in range(3):
+            if {int(ids[i]), int(ids[j])} != {0, 2}:
+                expect[i] += 3.0 * float(v[j])
+    assert np.array_equal(ans, expect)
+    assert list(ids) == [0, 1, 2] and list(ans) == [9.0, 18.0, 15.0]
+    y = torch.zeros(3, dtype=torch.float64, device=p.device)
+    assert C1.evaluate(y, v, count_pairs=True) == 7
+    C2 = ab.create_sparse_operator(p, p, diameter, K.const_sum_diff("scalar1", "scalar2"))
+    ans2 = (C2 * v).cpu().numpy()
+    assert list(ans2[:3]) == [9.0, -3.0, 18.0]
+    assert list(ans2) == [9.0, -3.0, 18.0, -6.0, 15.0, -5.0]
+
+
+def _matvec_both(o, out, p, kern, okid, params, r, BR=1, row_vars=(), col_vars=(), seed=1):
+    n = out["n_alive"]
+    b = synth.vector(n, seed=synth.SEED + seed)
+    y_o, npairs = o.sparse_matvec(out["pos"], okid, params, r, b, BR=BR, BC=1, row_vars=row_vars, col_vars=col_vars)
+    op = ab.create_sparse_operator(p, p, r, kern)
+    bt = torch.from_numpy(b).to(p.device)
+    y = (op * bt).cpu().numpy()
+    return y, y_o, npairs, op, bt
+
+
+def test_matvec_c1_inverse_distance():
+    # BASELINE config c1: N=1e5 uniform periodic unit cube, r=0.05, 1/(|dx|+0.1)
+    pos = synth.uniform_positions(100000, 3)
+    o, out, p = build_both(pos, 0.0, 1.0, True)
+    assert_build_equal(o, out, p)
+    y, y_o, npairs, op, bt = _matvec_both(o, out, p, K.inv_dist(0.1), orc.K_INV_DIST, [0.1], 0.05)
+    assert rel_l2(y, y_o) <= TOL
+    assert 4.5e6 < npairs < 6.0e6
+    y2 = torch.zeros_like(bt)
+    assert op.evaluate(y2, bt, count_pairs=True) == npairs
+    # by particle id: undo the reorder and compare in the original numbering
+    ids = p.get("id").cpu().numpy()
+    y_by_id = np.zeros_like(y)
+    y_by_id[ids] = y
+    yo_by_id = np.zeros_like(y_o)
+    yo_by_id[out["order"]] = y_o
+    assert rel_l2(y_by_id, yo_by_id) <= TOL
+    # evaluate accumulates (y += K b): applying twice doubles
+    op.evaluate(y2, bt)
+    assert rel_l2(y2.cpu().numpy(), 2 * y_o) <= TOL
+    assert p.last_counters()["launches"] == 2  # tiled kernel + exact-walk kernel
+
+
+def test_matvec_all_kernels_small():
+    N = 20000
+    rng = np.random.default_rng(11)
+    for D, periodic in ((3, True), (3, False), (2, True), (2, False), (1, True)):
+        pos = rng.random((N if D > 1 else 2000, D))
+        vars_ = {"a": torch.float64, "pdr2": torch.float64}
+        o, out, p0 = build_both(pos, 0.0, 1.0, periodic, 10.0, variables=None)
+        n = out["n_alive"]
+        p = ab.Particles(D, pos.shape[0], variables=vars_)
+        p.set("position", torch.from_numpy(pos.copy()))
+        a = rng.random(pos.shape[0])
+        pd = rng.random(pos.shape[0])
+        p.set("a", torch.from_numpy(a))
+        p.set("pdr2", torch.from_numpy(pd))
+        p.init_neighbour_search(0.0, 1.0, periodic, 10.0)
+        a_s, pd_s = a[out["order"]], pd[out["order"]]
+        side = o.grid()[1][0]
+        r = 1.3 * side
+        h = r / 2
+        cases = [
+            (K.inv_dist(0.1), orc.K_INV_DIST, [0.1], 1, (), ()),
+            (K.inv_dist_aa(0.1, "a"), orc.K_INV_DIST_AA, [0.1], 1, (a_s,), (a_s,)),
+            (K.wendland_c2(h), orc.K_WENDLAND_C2, [h], 1, (), ()),
+            (K.lj_force(D, 0.4 * r, 1.0), orc.K_LJ_FORCE, [0.4 * r, 1.0], D, (), ()),
+            (K.sph_density(h, 0.5, 1.3), orc.K_SPH_DENSITY, [h, 0.5, 1.3], 1, (), ()),
+            (K.sph_pressure(D, h, 0.5, 1.3, "pdr2"), orc.K_SPH_PRESSURE, [h, 0.5, 1.3], D, (pd_s,), (pd_s,)),
+        ]
+        for kern, okid, params, BR, rv, cv in cases:
+            y, y_o, npairs, op, bt = _matvec_both(o, out, p, kern, okid, params, r, BR=BR, row_vars=rv, col_vars=cv)
+            assert rel_l2(y, y_o) <= TOL, (D, periodic, okid, rel_l2(y, y_o))
+            assert npairs > n
+
+
+def test_matvec_rows_not_cols_and_row_radius():
+    # G_test = create_sparse_operator(test, knots, ...) (tests/rbf_interpolation.h:326):
+    # the row set has no search structure and may lie outside the domain
+    rng = np.random.default_rng(3)
+    N, M = 30000, 5000
+    pos = rng.random((N, 2))
+    o, out, p = build_both(pos, 0.0, 1.0, False)
+    rows = rng.uniform(-0.05, 1.05, size=(M, 2))
+    h = 0.5 * np.sqrt(30.0 / (np.pi * N))
+    b = synth.vector(N)
+    y_o, _ = o.sparse_matvec(rows, orc.K_WENDLAND_C2, [h], 2 * h, b)
+    test = ab.Particles(2, M)
+    test.set("position", torch.from_numpy(rows.copy()))
+    G = ab.create_sparse_operator(test, p, 2 * h, K.wendland_c2(h))
+    y = (G * torch.from_numpy(b).to(p.device)).cpu().numpy()
+    assert rel_l2(y, y_o) <= TOL
+    # per-row radius (the FRadius overload, src/Operators.h:478-489)
+    rpr = rng.uniform(0.5 * h, 3 * h, size=M)
+    y_o2, _ = o.sparse_matvec(rows, orc.K_WENDLAND_C2, [h], 0.0, b, radius_per_row=rpr)
+    G2 = ab.create_sparse_operator(test, p, rpr, K.wendland_c2(h))
+    y2 = (G2 * torch.from_numpy(b).to(p.device)).cpu().numpy()
+    assert rel_l2(y2, y_o2) <= TOL
+    cnt_o, hs_o = o.pair_stats(rows, 0.0, radius_per_row=rpr)
+    cnt, hs = p.pair_stats(0.0, rows=rows, path=1, radius_per_row=rpr)
+    assert np.array_equal(cnt.cpu().numpy().view(np.uint32), cnt_o)
+    assert np.array_equal(hs.cpu().numpy().view(np.uint64), hs_o)
+
+
+def test_clustered_cloud():
+    # c4-style clustered cloud at reduced N: heavy buckets, periodic (1,1,0)
+    N = 200000
+    pos = synth.clustered_positions(N)
+    o, out, p = build_both(pos, 0.0, 1.0, [True, True, False])
+    assert_build_equal(o, out, p)
+    h = 1.5 * N ** (-1.0 / 3.0)
+    _stats_equal(o, out, p, 2 * h)
+    y, y_o, npairs, op, bt = _matvec_both(o, out, p, K.sph_density(h, 1.0 / N, 21.0 / (256.0 * np.pi)), orc.K_SPH_DENSITY, [h, 1.0 / N, 21.0 / (256.0 * np.pi)], 2 * h)
+    assert rel_l2(y, y_o) <= TOL
+
+
+def test_large_properties():
+    # BASELINE-size properties where the oracle is too slow: c3-sized N=4M LJ-like
+    # cloud.  (1) tiled and walk kernels give identical pair sets; (2) the pair
+    # relation is symmetric: sum_i count_i == sum over symmetric kernel;
+    # (3) linearity K(2b) == 2 K b exactly; (4) symmetric kernel: x.(K y) == y.(K x).
+    N = 4_000_000
+    L = (N / 0.8442) ** (1.0 / 3.0)
+    dev = torch.device("cuda:0")
+    pos = synth.torch_uniform_positions(N, 3, 0.0, L, synth.SEED, 0, dev)
+    p = ab.Particles(3, 0)
+    p.columns["position"] = pos
+    p.columns["id"] = torch.arange(N, dtype=torch.int64, device=dev)
+    p.columns["alive"] = torch.ones(N, dtype=torch.uint8, device=dev)
+    p.init_neighbour_search(0.0, L, True, 13.2)
+    q = p.get_query()
+    keys = q.bucket_indices
+    assert bool((keys[1:] >= keys[:-1]).all())
+    assert int((q.bucket_end.long() - q.bucket_begin.long()).sum()) == N
+    ids = p.get("id")
+    assert bool((torch.sort(ids).values == torch.arange(N, device=dev)).all())
+    r = 2.5
+    cnt0, hs0 = p.pair_stats(r, path=0)
+    sub = torch.arange(0, N, 97, device=dev)
+    cnt1, hs1 = p.pair_stats(r, rows=p.get("position")[sub].contiguous(), path=1)
+    assert bool((cnt0[sub] == cnt1).all()) and bool((hs0[sub] == hs1).all())
+    mean = float(cnt0.double().mean())
+    assert abs(mean - (4.0 / 3.0 * np.pi * r**3 * 0.8442)) / mean < 0.01
+    op = ab.create_sparse_operator(p, p, r, K.inv_dist(0.1))
+    x = torch.from_numpy(synth.vector(N, seed=5)).to(dev)
+    yv = torch.from_numpy(synth.vector(N, seed=6)).to(dev)
+    Kx, Ky = op * x, op * yv
+    assert bool(((op * (2 * x)) == 2 * Kx).all())
+    lhs, rhs = float(torch.dot(x, Ky)), float(torch.dot(yv, Kx))
+    assert abs(lhs - rhs) / abs(lhs) < 1e-12
