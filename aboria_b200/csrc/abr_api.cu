@@ -18,6 +18,7 @@ int check_cuda(Handle *h, cudaError_t e, const char *what) {
   return ABR_ERR_CUDA;
 }
 void host_set_domain_impl(Handle *h, size_t n);
+int probe_fp64_peak(Handle *h, double *tflops);
 
 } // namespace abr
 
@@ -258,7 +259,7 @@ int abr_last_counters(abr_handle hh, uint64_t counters[4]) {
   counters[0] = h->h_scalars->danger_count;
   counters[1] = h->n_aliased;
   counters[2] = h->counters[2];
-  counters[3] = 0;
+  counters[3] = h->launches;
   return ABR_OK;
 }
 
@@ -273,6 +274,13 @@ int abr_sparse_matvec_custom(abr_handle hh, const double *row_pos, size_t n_rows
   if (rc) return rc;
   if (n_pairs_host) *n_pairs_host = 0;
   return ABR_OK;
+}
+
+int abr_probe_fp64_peak(abr_handle hh, double *tflops_host) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !tflops_host) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  return abr::probe_fp64_peak(h, tflops_host);
 }
 
 int abr_malloc(abr_handle hh, void **ptr, size_t bytes) {

@@ -331,6 +331,7 @@ static cudaError_t device_scan(Handle *h, const uint32_t *in, uint64_t m, uint32
   k_scan_partials<Op><<<1, 1024, 0, h->stream>>>(partial, nb);
   k_scan_apply<Op, REVERSE, MODE><<<nb, SC_THREADS, 0, h->stream>>>(in, m, partial, out, end_io,
                                                                     h->d_scalars);
+  h->launches += 3;
   return cudaGetLastError();
 }
 
@@ -391,6 +392,44 @@ k_gather_bytes(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
   dst[g] = src[(uint64_t)order[k] * eb + w];
 }
 
+// fp64 FMA throughput probe: the denominator of the matvec's fp64 roofline
+// (MEASURED_PEAKS.json has no fp64 entry; SURVEY.md §8d asks for a DFMA microbenchmark)
+__global__ void __launch_bounds__(256) k_dfma_probe(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+int probe_fp64_peak(Handle *h, double *tflops) {
+  const int blocks = h->sm_count * 8, iters = 1 << 14;
+  double *out = nullptr;
+  ABR_CUDA(h, cudaMalloc(&out, (size_t)blocks * 256 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, h->stream);
+    k_dfma_probe<<<blocks, 256, 0, h->stream>>>(out, iters);
+    cudaEventRecord(e1, h->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  ABR_CUDA(h, cudaGetLastError());
+  const double flops = 2.0 * 8.0 * (double)iters * blocks * 256.0;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return ABR_OK;
+}
+
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
@@ -415,6 +454,7 @@ int gather_columns(Handle *h, int ncols, const void *const *src, void *const *ds
           (const uint8_t *)src[c], (uint8_t *)dst[c], order, n_out, (uint32_t)eb);
     }
   }
+  h->launches += (uint64_t)ncols;
   ABR_CUDA(h, cudaGetLastError());
   return ABR_OK;
 }
@@ -546,6 +586,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     case 2: k_enforce_key<2><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
     default: k_enforce_key<3><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
     }
+    h->launches += 1;
 
     // LSD radix sort over the bits of key_bound
     int bits = 1;
@@ -564,6 +605,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
       cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
       if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
       k_radix_scatter<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, iin, kout, iout, hist, shift, n32, num_tiles);
+      h->launches += 2;
       cur ^= 1;
     }
     h->sorted_keys = h->keys[cur].as<uint32_t>();
@@ -574,6 +616,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     ABR_CUDA(h, cudaMemsetAsync(bb, 0xFF, prod * sizeof(uint32_t), h->stream));
     ABR_CUDA(h, cudaMemsetAsync(be, 0xFF, prod * sizeof(uint32_t), h->stream));
     k_boundaries<<<gb, 256, 0, h->stream>>>(h->sorted_keys, n32, (uint32_t)prod, g.key_bound, bb, be, h->d_scalars);
+    h->launches += 1;
     cudaError_t e = device_scan<OpMin, true, 1>(h, bb, prod, bb, be);
     if (e != cudaSuccess) return check_cuda(h, e, "bucket fill");
 

@@ -79,6 +79,7 @@ struct Handle {
   size_t n_sorted = 0;
 
   uint64_t counters[4] = {0, 0, 0, 0};
+  uint64_t launches = 0; // kernels launched since abr_create
 
   Grid grid() const;
 };

@@ -54,14 +54,17 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p)
     p->r2lo = (R > 4 * delta) ? (R - 4 * delta) * (R - 4 * delta) : -1.0;
     double stencil = 1;
     for (int d = 0; d < D; ++d) {
-      const double wr = std::ceil(R * h->inv_side[d]);
+      // half width of the bucket stencil.  The 1e-9 keeps r == k * side (a
+      // common choice) at k instead of k + 1 when the product rounds up; rows
+      // closer than tolf (>= 4e-9) to a bucket face are recomputed exactly anyway.
+      const double wr = std::ceil(R * h->inv_side[d] - 1e-9);
       if (!(wr < 1e6)) {
         tiled = false;
         break;
       }
       p->w[d] = (int)wr;
       if (p->w[d] < 1) p->w[d] = 1;
-      p->tolf[d] = std::fmax(1e-9, 8.0 * delta * h->inv_side[d]);
+      p->tolf[d] = std::fmax(4e-9, 8.0 * delta * h->inv_side[d]);
       if (p->tolf[d] > 0.125) tiled = false;
       stencil *= (2.0 * p->w[d] + 1.0);
     }
@@ -85,6 +88,7 @@ static int launch_checked(Handle *h, const abr_matvec_plan &p, const F &f) {
   const int e = launch_plan<D, F, STATS>(p, f);
   if (e != 0) return check_cuda(h, (cudaError_t)e, "matvec launch");
   h->counters[2] = p.use_tiled ? 2 : 1;
+  h->launches += h->counters[2];
   return ABR_OK;
 }
 
@@ -162,6 +166,7 @@ int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, cons
   const int e = launch(&p, functor);
   if (e != 0) return check_cuda(h, (cudaError_t)e, "custom matvec launch");
   h->counters[2] = p.use_tiled ? 2 : 1;
+  h->launches += h->counters[2];
   return ABR_OK;
 }
 

@@ -198,7 +198,14 @@ class Particles:
     def last_counters(self):
         c = (C.c_uint64 * 4)()
         check(self._h, self._lib.abr_last_counters(self._h, C.byref(c)))
-        return dict(walk_rows=int(c[0]), aliased=int(c[1]), launches=int(c[2]))
+        return dict(walk_rows=int(c[0]), aliased=int(c[1]), launches=int(c[2]), total_launches=int(c[3]))
+
+    def probe_fp64_peak(self):
+        """measured DFMA throughput of this device in TFLOP/s"""
+        self._sync_stream()
+        v = C.c_double()
+        check(self._h, self._lib.abr_probe_fp64_peak(self._h, C.byref(v)))
+        return v.value
 
     def pair_stats(self, radius, rows=None, path=-1, radius_per_row=None):
         """per-row neighbour count and pair-set hash of euclidean_search"""

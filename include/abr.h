@@ -148,7 +148,9 @@ int abr_pair_stats(abr_handle h, const double *row_pos, size_t n_rows, int rows_
 
 /* Counters of the last abr_sparse_matvec / abr_pair_stats on the tiled path:
  * [0] rows re-done by the exact per-row walk (rounding-sensitive rows),
- * [1] accepted pairs, [2] kernels launched by the last call. */
+ * [1] particles whose bucket index overflowed in the last build (forces the
+ *     exact walk), [2] kernels launched by the last matvec call,
+ * [3] kernels launched by this handle since abr_create. */
 int abr_last_counters(abr_handle h, uint64_t counters_host[4]);
 
 /* Custom device functor (user TU compiled by nvcc, see
@@ -161,6 +163,10 @@ int abr_sparse_matvec_custom(abr_handle h, const double *row_pos, size_t n_rows,
                              abr_launch_fn launch, const void *functor_host, int block_rows,
                              int block_cols, double radius, const double *radius_per_row,
                              const double *b, double *y, uint64_t *n_pairs_host);
+
+/* Measures the device's fp64 FMA throughput (TFLOP/s, FMA = 2 flop) with a
+ * register-resident DFMA loop; the denominator of the matvec's fp64 roofline. */
+int abr_probe_fp64_peak(abr_handle h, double *tflops_host);
 
 /* Thin device-memory helpers so that C/C++ hosts need no CUDA headers. */
 int abr_malloc(abr_handle h, void **ptr_out, size_t bytes);

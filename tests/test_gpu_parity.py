@@ -281,7 +281,7 @@ def test_large_properties():
     cnt1, hs1 = p.pair_stats(r, rows=p.get("position")[sub].contiguous(), path=1)
     assert bool((cnt0[sub] == cnt1).all()) and bool((hs0[sub] == hs1).all())
     mean = float(cnt0.double().mean())
-    assert abs(mean - (4.0 / 3.0 * np.pi * r**3 * 0.8442)) / mean < 0.01
+    assert abs(mean - (1.0 + 4.0 / 3.0 * np.pi * r**3 * 0.8442)) / mean < 0.01  # +1: self pair
     op = ab.create_sparse_operator(p, p, r, K.inv_dist(0.1))
     x = torch.from_numpy(synth.vector(N, seed=5)).to(dev)
     yv = torch.from_numpy(synth.vector(N, seed=6)).to(dev)
