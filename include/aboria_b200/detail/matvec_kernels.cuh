@@ -65,7 +65,6 @@ namespace abr {
 
 constexpr int TILED_WARPS = 8;
 constexpr int TILED_THREADS = TILED_WARPS * 32;
-constexpr int ROW_BATCH = 32;
 
 // functor used by pair_stats; never evaluated
 struct StatsFunctor {
@@ -128,30 +127,89 @@ __global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, cons
 // ---------------------------------------------------------------------------
 // tiled_kernel
 // ---------------------------------------------------------------------------
-template <int D, class F, bool STATS> struct TiledSmem {
+// does the functor read dx?  (default yes; functors that only need |dx|^2 set
+// `static constexpr bool NEEDS_DX = false` and save three subtractions per pair)
+template <class F, class = void> struct needs_dx { static constexpr bool value = true; };
+template <class F> struct needs_dx<F, decltype((void)F::NEEDS_DX)> { static constexpr bool value = F::NEEDS_DX; };
+
+constexpr int QCAP = 64; // accepted-pair ring buffer per warp (power of two, >= 2*32)
+
+template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
-  // per warp: rows (unshifted / shifted, padded to 4 doubles), partial table
-  double rows0[TILED_WARPS][ROW_BATCH][4];
-  double rowsS[TILED_WARPS][ROW_BATCH][4];
-  unsigned long long part[TILED_WARPS][NACC][ROW_BATCH][32];
+  static constexpr int RB = NACC == 1 ? 32 : 16; // rows per batch
+};
+
+template <int D, class F, bool STATS> struct TiledSmem {
+  static constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
+  static constexpr int RB = TiledCfg<D, F, STATS>::RB;
+  // per warp: rows (unshifted / shifted, padded to 4 doubles), partial-sum
+  // table, accepted-pair queue
+  double rows0[TILED_WARPS][RB][4];
+  double rowsS[TILED_WARPS][RB][4];
+  unsigned long long part[TILED_WARPS][NACC][RB][32];
+  double q_d2[TILED_WARPS][QCAP];
+  uint2 q_ji[TILED_WARPS][QCAP]; // (column index j, row slot | image id << 8)
   uint32_t danger[TILED_WARPS];
   uint32_t chunk_base;
 };
 
 constexpr uint32_t TILED_CHUNK = 64; // buckets claimed per scheduler step by a CTA
 
+// Evaluate F for up to 32 queued pairs, one per lane (full lane utilisation:
+// the expensive part of the product — sqrt, divide, the user's math — runs on
+// compacted pairs instead of on the ~15 % of lanes that pass the cut-off test).
+template <int D, class F, bool STATS, class SM>
+__device__ __forceinline__ void drain_queue(SM &sm, const abr_matvec_plan &p, const F &f, int warp, int lane,
+                                            uint32_t head, uint32_t count, uint32_t r0, const double (*rowp)[4]) {
+  constexpr int BR = F::BR, BC = F::BC;
+  __syncwarp();
+  if ((uint32_t)lane < count) {
+    const uint32_t e = (head + lane) & (QCAP - 1);
+    const double d2 = sm.q_d2[warp][e];
+    const uint2 ji = sm.q_ji[warp][e];
+    const uint32_t j = ji.x, i = ji.y & 0xFFu;
+    if (d2 > p.r2lo) atomicOr(&sm.danger[warp], 1u << i);
+    if (STATS) {
+      sm.part[warp][0][i][lane] += 1ull;
+      sm.part[warp][1][i][lane] += mix64((uint64_t)j * 81u + (uint64_t)(ji.y >> 8));
+    } else {
+      double dx[D];
+      if (needs_dx<F>::value) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) dx[d] = p.q.pos[(size_t)j * D + d] - rowp[i][d];
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) dx[d] = 0.0;
+      }
+      double blk[BR * BC];
+      f(dx, d2, r0 + i, j, blk);
+#pragma unroll
+      for (int a2 = 0; a2 < BR; ++a2) {
+        double s = 0;
+#pragma unroll
+        for (int c = 0; c < BC; ++c) s += blk[a2 * BC + c] * p.b[(size_t)j * BC + c];
+        double *slot = reinterpret_cast<double *>(&sm.part[warp][a2][i][lane]);
+        *slot += s;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int D, class F, bool STATS>
 __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_plan p, const F f) {
-  constexpr int BR = F::BR, BC = F::BC;
-  constexpr int NACC = STATS ? 2 : BR;
+  constexpr int BR = F::BR;
+  constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
+  constexpr int RB = TiledCfg<D, F, STATS>::RB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<TiledSmem<D, F, STATS> *>(smem_raw);
   const Grid &g = p.q.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
   const double *__restrict__ pos = p.q.pos;
   const uint32_t *__restrict__ bbeg = p.q.bucket_begin;
   const uint32_t *__restrict__ bend = p.q.bucket_end;
-  const double R2 = p.r2, R2LO = p.r2lo;
+  const double R2 = p.r2;
   constexpr int L = D - 1; // last (fastest, memory-contiguous) dimension
 
   while (true) {
@@ -175,17 +233,16 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
           rem /= (uint32_t)g.size[d];
         }
       }
-      for (uint32_t r0 = rb; r0 < re; r0 += ROW_BATCH) {
-        const int nr = (int)min((uint32_t)ROW_BATCH, re - r0);
+      for (uint32_t r0 = rb; r0 < re; r0 += RB) {
+        const int nr = (int)min((uint32_t)RB, re - r0);
         // ---- load the rows of this batch, flag rounding-sensitive ones ----
         bool my_danger = false;
         if (lane < nr) {
-          double r[D];
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            r[d] = pos[(size_t)(r0 + lane) * D + d];
-            sm.rows0[warp][lane][d] = r[d];
-            const double fl = (r[d] - g.bmin[d]) * g.inv_side[d];
+            const double r = pos[(size_t)(r0 + lane) * D + d];
+            sm.rows0[warp][lane][d] = r;
+            const double fl = (r - g.bmin[d]) * g.inv_side[d];
             const double fr = fl - floor(fl);
             my_danger |= ((int)floor(fl) != tc[d]) | (fr < p.tolf[d]) | (fr > 1.0 - p.tolf[d]) |
                          (fabs(fr - 0.5) < p.tolf[d]);
@@ -196,6 +253,7 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
         for (int a = 0; a < NACC; ++a)
           for (int i = 0; i < nr; ++i) sm.part[warp][a][i][lane] = 0ull;
         __syncwarp();
+        uint32_t qhead = 0, qtail = 0; // warp-uniform ring-buffer cursors
 
         // ---- neighbouring buckets: offsets in the D-1 slow dims, runs in the last ----
         int o[D > 1 ? D - 1 : 1];
@@ -239,7 +297,12 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
               for (int d = 0; d < D; ++d) shifted |= (img[d] != 0);
               const double(*rowp)[4] = sm.rows0[warp];
               if (shifted) {
-                __syncwarp();
+                // queued pairs refer to the current row image: finish them first
+                while (qtail != qhead) {
+                  const uint32_t cnt = min(32u, qtail - qhead);
+                  drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, sm.rows0[warp]);
+                  qhead += cnt;
+                }
                 if (lane < nr) {
 #pragma unroll
                   for (int d = 0; d < D; ++d)
@@ -248,42 +311,41 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
                 __syncwarp();
                 rowp = sm.rowsS[warp];
               }
-              const int image_id = STATS ? image_linear_index<D>(g, img) : 0;
+              const uint32_t image_tag = STATS ? ((uint32_t)image_linear_index<D>(g, img) << 8) : 0u;
               for (uint32_t cb = jb; cb < je; cb += 32) {
                 const uint32_t j = cb + lane;
                 const bool valid = j < je;
-                double pj[D], bj[BC];
+                double pj[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) pj[d] = valid ? pos[(size_t)j * D + d] : 0.0;
-                if (!STATS) {
-#pragma unroll
-                  for (int c = 0; c < BC; ++c) bj[c] = valid ? p.b[(size_t)j * BC + c] : 0.0;
-                }
+#pragma unroll 2
                 for (int i = 0; i < nr; ++i) {
-                  double dx[D];
                   double acc = 0;
 #pragma unroll
-                  for (int d = 0; d < D; ++d) dx[d] = pj[d] - rowp[i][d];
-#pragma unroll
-                  for (int d = 0; d < D; ++d) acc = acc + dx[d] * dx[d];
-                  if (valid && !(acc > R2)) {
-                    if (acc > R2LO) atomicOr(&sm.danger[warp], 1u << i);
-                    if (STATS) {
-                      sm.part[warp][0][i][lane] += 1ull;
-                      sm.part[warp][1][i][lane] += mix64((uint64_t)j * 81u + (uint64_t)image_id);
-                    } else {
-                      double blk[BR * BC];
-                      f(dx, acc, r0 + i, j, blk);
-#pragma unroll
-                      for (int a2 = 0; a2 < BR; ++a2) {
-                        double s = 0;
-#pragma unroll
-                        for (int c = 0; c < BC; ++c) s += blk[a2 * BC + c] * bj[c];
-                        double *slot = reinterpret_cast<double *>(&sm.part[warp][a2][i][lane]);
-                        *slot += s;
-                      }
-                    }
+                  for (int d = 0; d < D; ++d) {
+                    const double dxd = pj[d] - rowp[i][d];
+                    acc = acc + dxd * dxd;
                   }
+                  const bool ok = valid && !(acc > R2);
+                  const uint32_t mask = __ballot_sync(0xFFFFFFFFu, ok);
+                  if (ok) {
+                    const uint32_t e = (qtail + __popc(mask & lane_lt)) & (QCAP - 1);
+                    sm.q_d2[warp][e] = acc;
+                    sm.q_ji[warp][e] = make_uint2(j, (uint32_t)i | image_tag);
+                  }
+                  qtail += __popc(mask);
+                  if (qtail - qhead >= 32u) {
+                    drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, 32u, r0, rowp);
+                    qhead += 32u;
+                  }
+                }
+              }
+              if (shifted) {
+                // leave no pair of a shifted image in the queue (rowsS is reused)
+                while (qtail != qhead) {
+                  const uint32_t cnt = min(32u, qtail - qhead);
+                  drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, rowp);
+                  qhead += cnt;
                 }
               }
             }
@@ -300,6 +362,11 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
               }
             }
           }
+        }
+        while (qtail != qhead) {
+          const uint32_t cnt = min(32u, qtail - qhead);
+          drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, sm.rows0[warp]);
+          qhead += cnt;
         }
         __syncwarp();
 

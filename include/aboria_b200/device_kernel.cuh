@@ -15,6 +15,7 @@
 //
 // Custom functor in a user .cu file:
 //     struct MyKernel { static constexpr int BR = 1, BC = 1; const double *w;
+//       static constexpr bool NEEDS_DX = false;   // optional: dx itself is not read
 //       __device__ void operator()(const double *dx, double d2, uint32_t i, uint32_t j, double *blk) const
 //       { blk[0] = w[i] * w[j] * exp(-d2); } };
 //     MyKernel k{w_dev};
@@ -31,6 +32,7 @@ namespace functors {
 
 // tests/operators.h:842-847
 struct ConstSum {
+  static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   const double *s1, *s2;
   __device__ void operator()(const double *, double, uint32_t i, uint32_t j, double *blk) const {
@@ -39,6 +41,7 @@ struct ConstSum {
 };
 // tests/operators.h:905-911
 struct ConstSumDiff {
+  static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 2, BC = 1;
   const double *s1, *s2;
   __device__ void operator()(const double *, double, uint32_t i, uint32_t j, double *blk) const {
@@ -48,6 +51,7 @@ struct ConstSumDiff {
 };
 // 1/(|dx| + eps)
 struct InvDist {
+  static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   double eps;
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
@@ -56,6 +60,7 @@ struct InvDist {
 };
 // tests/operators.h:251-256
 struct InvDistAA {
+  static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   double eps;
   const double *ai, *aj;
@@ -65,6 +70,7 @@ struct InvDistAA {
 };
 // tests/rbf_interpolation.h:310-313: pow(2 - r/h, 4) * (1 + 2 r/h)
 struct WendlandC2 {
+  static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   double h;
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
@@ -95,6 +101,7 @@ template <int D> struct LJForce {
 };
 // tests/sph.h:154-165 W_fun (Wendland), times the particle mass
 template <int D> struct SphDensity {
+  static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   double h, mass, wcon;
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
