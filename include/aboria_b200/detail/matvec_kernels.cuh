@@ -136,19 +136,21 @@ constexpr int QCAP = 64; // accepted-pair ring buffer per warp (power of two, >=
 
 template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
-  static constexpr int RB = NACC == 1 ? 32 : 16; // rows per batch
+  static constexpr int RB = 16; // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows)
 };
 
 template <int D, class F, bool STATS> struct TiledSmem {
   static constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
   static constexpr int RB = TiledCfg<D, F, STATS>::RB;
   // per warp: rows (unshifted / shifted, padded to 4 doubles), partial-sum
-  // table, accepted-pair queue
+  // table, accepted-pair queue, candidate-run directory
   double rows0[TILED_WARPS][RB][4];
   double rowsS[TILED_WARPS][RB][4];
   unsigned long long part[TILED_WARPS][NACC][RB][32];
   double q_d2[TILED_WARPS][QCAP];
   uint2 q_ji[TILED_WARPS][QCAP]; // (column index j, row slot | image id << 8)
+  uint32_t run_pref[TILED_WARPS][32];  // inclusive prefix of run lengths
+  uint32_t run_delta[TILED_WARPS][32]; // j = k + run_delta[run]
   uint32_t danger[TILED_WARPS];
   uint32_t chunk_base;
 };
@@ -196,8 +198,39 @@ __device__ __forceinline__ void drain_queue(SM &sm, const abr_matvec_plan &p, co
   __syncwarp();
 }
 
+// One step of the hot loop: this lane's candidate j against the nr rows of the
+// batch.  Exact un-fused predicate; accepted pairs are pushed to the queue.
+template <int D, class F, bool STATS, class SM>
+__device__ __forceinline__ void test_rows(SM &sm, const abr_matvec_plan &p, const F &f, int warp, int lane,
+                                          uint32_t lane_lt, const double *pj, uint32_t j, bool valid, int nr,
+                                          const double (*rowp)[4], uint32_t image_tag, uint32_t r0, uint32_t &qhead,
+                                          uint32_t &qtail) {
+  const double R2 = p.r2;
+#pragma unroll 2
+  for (int i = 0; i < nr; ++i) {
+    double acc = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double dxd = pj[d] - rowp[i][d];
+      acc = acc + dxd * dxd;
+    }
+    const bool ok = valid && !(acc > R2);
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, ok);
+    if (ok) {
+      const uint32_t e = (qtail + __popc(mask & lane_lt)) & (QCAP - 1);
+      sm.q_d2[warp][e] = acc;
+      sm.q_ji[warp][e] = make_uint2(j, (uint32_t)i | image_tag);
+    }
+    qtail += __popc(mask);
+    if (qtail - qhead >= 32u) {
+      drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, 32u, r0, rowp);
+      qhead += 32u;
+    }
+  }
+}
+
 template <int D, class F, bool STATS>
-__global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_plan p, const F f) {
+__global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matvec_plan p, const F f) {
   constexpr int BR = F::BR;
   constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
   constexpr int RB = TiledCfg<D, F, STATS>::RB;
@@ -209,8 +242,15 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
   const double *__restrict__ pos = p.q.pos;
   const uint32_t *__restrict__ bbeg = p.q.bucket_begin;
   const uint32_t *__restrict__ bend = p.q.bucket_end;
-  const double R2 = p.r2;
   constexpr int L = D - 1; // last (fastest, memory-contiguous) dimension
+  // number of offset tuples in the D-1 slow dimensions
+  int nslow = 1;
+#pragma unroll
+  for (int d = 0; d < D - 1; ++d) nslow *= 2 * p.w[d] + 1;
+  int img0[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) img0[d] = 0;
+  const uint32_t image_tag0 = STATS ? ((uint32_t)image_linear_index<D>(g, img0) << 8) : 0u;
 
   while (true) {
     __syncthreads();
@@ -233,6 +273,13 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
           rem /= (uint32_t)g.size[d];
         }
       }
+      const int zlo = tc[L] - p.w[L], zhi = tc[L] + p.w[L];
+      const int S = g.size[L];
+      // does any neighbour of this bucket lie across a periodic boundary / outside?
+      bool boundary = (zlo < 0) | (zhi >= S);
+#pragma unroll
+      for (int d = 0; d < D - 1; ++d) boundary |= (tc[d] - p.w[d] < 0) | (tc[d] + p.w[d] >= g.size[d]);
+
       for (uint32_t r0 = rb; r0 < re; r0 += RB) {
         const int nr = (int)min((uint32_t)RB, re - r0);
         // ---- load the rows of this batch, flag rounding-sensitive ones ----
@@ -255,110 +302,136 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
         __syncwarp();
         uint32_t qhead = 0, qtail = 0; // warp-uniform ring-buffer cursors
 
-        // ---- neighbouring buckets: offsets in the D-1 slow dims, runs in the last ----
-        int o[D > 1 ? D - 1 : 1];
+        // ---- phase 1: neighbour runs in the primary image, concatenated so that
+        //      every step tests 32 candidates (one run = the 2w+1 buckets along the
+        //      last dimension, contiguous in the sorted arrays) ----
+        for (int rbase = 0; rbase < nslow; rbase += 32) {
+          uint32_t len = 0, jb = 0;
+          const int rid = rbase + lane;
+          if (rid < nslow) {
+            int nc[D];
+            bool ok = true;
+            int rem = rid;
 #pragma unroll
-        for (int d = 0; d < D - 1; ++d) o[d] = -p.w[d];
-        bool more = true;
-        while (more) {
-          // resolve the slow dimensions (wrap -> image) once per run family
-          int nc[D], img[D];
-          bool ok_slow = true;
-#pragma unroll
-          for (int d = 0; d < D - 1; ++d) {
-            int u = tc[d] + o[d];
-            img[d] = 0;
-            if (u < 0) {
-              u += g.size[d];
-              img[d] = 1;
-            } else if (u >= g.size[d]) {
-              u -= g.size[d];
-              img[d] = -1;
+            for (int d = D - 2; d >= 0; --d) {
+              const int span = 2 * p.w[d] + 1;
+              const int u = tc[d] + (rem % span) - p.w[d];
+              rem /= span;
+              ok &= (u >= 0) & (u < g.size[d]);
+              nc[d] = u;
             }
-            ok_slow &= (u >= 0) & (u < g.size[d]) & (img[d] == 0 || g.periodic[d]);
-            nc[d] = u;
-          }
-          if (ok_slow) {
-            // last dimension: up to three image segments of the unwrapped range
-            const int zlo = tc[L] - p.w[L], zhi = tc[L] + p.w[L];
-            const int S = g.size[L];
-            for (int m = (g.periodic[L] ? -1 : 0); m <= (g.periodic[L] ? 1 : 0); ++m) {
-              // unwrapped indices [m*S, m*S + S - 1] map to buckets [0,S-1] with image -m
-              const int a = max(zlo, m * S), bnd = min(zhi, m * S + S - 1);
-              if (a > bnd) continue;
-              img[L] = -m;
-              nc[L] = a - m * S;
+            const int a = max(zlo, 0), bnd = min(zhi, S - 1);
+            if (ok && a <= bnd) {
+              nc[L] = a;
               const uint32_t c_lo = (uint32_t)collapse_index<D>(g, nc);
-              const uint32_t c_hi = c_lo + (uint32_t)(bnd - a);
-              const uint32_t jb = bbeg[c_lo], je = bend[c_hi];
-              if (jb >= je) continue;
-              bool shifted = false;
+              jb = bbeg[c_lo];
+              len = bend[c_lo + (uint32_t)(bnd - a)] - jb;
+            }
+          }
+          uint32_t pin = len;
 #pragma unroll
-              for (int d = 0; d < D; ++d) shifted |= (img[d] != 0);
-              const double(*rowp)[4] = sm.rows0[warp];
-              if (shifted) {
-                // queued pairs refer to the current row image: finish them first
-                while (qtail != qhead) {
-                  const uint32_t cnt = min(32u, qtail - qhead);
-                  drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, sm.rows0[warp]);
-                  qhead += cnt;
-                }
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pin, o);
+            if (lane >= o) pin += t;
+          }
+          const uint32_t total = __shfl_sync(0xFFFFFFFFu, pin, 31);
+          __syncwarp();
+          sm.run_pref[warp][lane] = pin;
+          sm.run_delta[warp][lane] = jb - (pin - len);
+          __syncwarp();
+          for (uint32_t kb = 0; kb < total; kb += 32) {
+            const uint32_t k = kb + lane;
+            const bool valid = k < total;
+            const uint32_t ks = valid ? k : total - 1;
+            uint32_t rho = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+              if (sm.run_pref[warp][rho + step - 1] <= ks) rho += step;
+            const uint32_t j = ks + sm.run_delta[warp][rho];
+            double pj[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pj[d] = pos[(size_t)j * D + d];
+            test_rows<D, F, STATS>(sm, p, f, warp, lane, lane_lt, pj, j, valid, nr, sm.rows0[warp], image_tag0, r0,
+                                   qhead, qtail);
+          }
+        }
+        // pairs queued so far belong to the primary image
+        if (boundary) {
+          while (qtail != qhead) {
+            const uint32_t cnt = min(32u, qtail - qhead);
+            drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, sm.rows0[warp]);
+            qhead += cnt;
+          }
+          // ---- phase 2 (buckets at a periodic boundary only): runs reached through
+          //      a periodic image; cur = r + image * L exactly as src/Search.h:188-190 ----
+          int o[D > 1 ? D - 1 : 1];
+#pragma unroll
+          for (int d = 0; d < D - 1; ++d) o[d] = -p.w[d];
+          bool more = true;
+          while (more) {
+            int nc[D], img[D];
+            bool ok_slow = true, slow_shifted = false;
+#pragma unroll
+            for (int d = 0; d < D - 1; ++d) {
+              int u = tc[d] + o[d];
+              img[d] = 0;
+              if (u < 0) {
+                u += g.size[d];
+                img[d] = 1;
+              } else if (u >= g.size[d]) {
+                u -= g.size[d];
+                img[d] = -1;
+              }
+              ok_slow &= (u >= 0) & (u < g.size[d]) & (img[d] == 0 || g.periodic[d]);
+              slow_shifted |= (img[d] != 0);
+              nc[d] = u;
+            }
+            if (ok_slow) {
+              for (int m = (g.periodic[L] ? -1 : 0); m <= (g.periodic[L] ? 1 : 0); ++m) {
+                if (m == 0 && !slow_shifted) continue; // primary image: done in phase 1
+                // unwrapped indices [m*S, m*S + S - 1] map to buckets [0,S-1] with image -m
+                const int a = max(zlo, m * S), bnd = min(zhi, m * S + S - 1);
+                if (a > bnd) continue;
+                img[L] = -m;
+                nc[L] = a - m * S;
+                const uint32_t c_lo = (uint32_t)collapse_index<D>(g, nc);
+                const uint32_t jb = bbeg[c_lo], je = bend[c_lo + (uint32_t)(bnd - a)];
+                if (jb >= je) continue;
+                __syncwarp();
                 if (lane < nr) {
 #pragma unroll
                   for (int d = 0; d < D; ++d)
                     sm.rowsS[warp][lane][d] = sm.rows0[warp][lane][d] + (double)img[d] * g.L[d];
                 }
                 __syncwarp();
-                rowp = sm.rowsS[warp];
-              }
-              const uint32_t image_tag = STATS ? ((uint32_t)image_linear_index<D>(g, img) << 8) : 0u;
-              for (uint32_t cb = jb; cb < je; cb += 32) {
-                const uint32_t j = cb + lane;
-                const bool valid = j < je;
-                double pj[D];
+                const uint32_t image_tag = STATS ? ((uint32_t)image_linear_index<D>(g, img) << 8) : 0u;
+                for (uint32_t cb = jb; cb < je; cb += 32) {
+                  const uint32_t j = min(cb + lane, je - 1);
+                  const bool valid = cb + lane < je;
+                  double pj[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) pj[d] = valid ? pos[(size_t)j * D + d] : 0.0;
-#pragma unroll 2
-                for (int i = 0; i < nr; ++i) {
-                  double acc = 0;
-#pragma unroll
-                  for (int d = 0; d < D; ++d) {
-                    const double dxd = pj[d] - rowp[i][d];
-                    acc = acc + dxd * dxd;
-                  }
-                  const bool ok = valid && !(acc > R2);
-                  const uint32_t mask = __ballot_sync(0xFFFFFFFFu, ok);
-                  if (ok) {
-                    const uint32_t e = (qtail + __popc(mask & lane_lt)) & (QCAP - 1);
-                    sm.q_d2[warp][e] = acc;
-                    sm.q_ji[warp][e] = make_uint2(j, (uint32_t)i | image_tag);
-                  }
-                  qtail += __popc(mask);
-                  if (qtail - qhead >= 32u) {
-                    drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, 32u, r0, rowp);
-                    qhead += 32u;
-                  }
+                  for (int d = 0; d < D; ++d) pj[d] = pos[(size_t)j * D + d];
+                  test_rows<D, F, STATS>(sm, p, f, warp, lane, lane_lt, pj, j, valid, nr, sm.rowsS[warp], image_tag,
+                                         r0, qhead, qtail);
                 }
-              }
-              if (shifted) {
-                // leave no pair of a shifted image in the queue (rowsS is reused)
+                // leave no pair of this image in the queue (rowsS is reused)
                 while (qtail != qhead) {
                   const uint32_t cnt = min(32u, qtail - qhead);
-                  drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, rowp);
+                  drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, sm.rowsS[warp]);
                   qhead += cnt;
                 }
               }
             }
-          }
-          // next offset tuple in the slow dimensions (odometer)
-          more = false;
+            // next offset tuple in the slow dimensions (odometer)
+            more = false;
 #pragma unroll
-          for (int d = D - 2; d >= 0; --d) {
-            if (!more) {
-              if (++o[d] <= p.w[d]) {
-                more = true;
-              } else {
-                o[d] = -p.w[d];
+            for (int d = D - 2; d >= 0; --d) {
+              if (!more) {
+                if (++o[d] <= p.w[d]) {
+                  more = true;
+                } else {
+                  o[d] = -p.w[d];
+                }
               }
             }
           }
