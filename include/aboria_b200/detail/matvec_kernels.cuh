@@ -63,7 +63,7 @@ struct abr_matvec_plan {
 
 namespace abr {
 
-constexpr int TILED_WARPS = 8;
+constexpr int TILED_WARPS = 4;
 constexpr int TILED_THREADS = TILED_WARPS * 32;
 
 // functor used by pair_stats; never evaluated
@@ -132,113 +132,142 @@ __global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, cons
 template <class F, class = void> struct needs_dx { static constexpr bool value = true; };
 template <class F> struct needs_dx<F, decltype((void)F::NEEDS_DX)> { static constexpr bool value = F::NEEDS_DX; };
 
-constexpr int QCAP = 64; // accepted-pair ring buffer per warp (power of two, >= 2*32)
+constexpr int QCAP = 8;   // accepted pairs a lane may hold before the warp drains
 
 template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
   static constexpr int RB = 16; // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows)
 };
 
-template <int D, class F, bool STATS> struct TiledSmem {
+// per-warp shared memory (a warp works on one target bucket at a time and never
+// synchronises with the other warps of its CTA)
+template <int D, class F, bool STATS> struct WarpSmem {
   static constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
   static constexpr int RB = TiledCfg<D, F, STATS>::RB;
-  // per warp: rows (unshifted / shifted, padded to 4 doubles), partial-sum
-  // table, accepted-pair queue, candidate-run directory
-  double rows0[TILED_WARPS][RB][4];
-  double rowsS[TILED_WARPS][RB][4];
-  unsigned long long part[TILED_WARPS][NACC][RB][32];
-  double q_d2[TILED_WARPS][QCAP];
-  uint2 q_ji[TILED_WARPS][QCAP]; // (column index j, row slot | image id << 8)
-  uint32_t run_pref[TILED_WARPS][32];  // inclusive prefix of run lengths
-  uint32_t run_delta[TILED_WARPS][32]; // j = k + run_delta[run]
-  uint32_t danger[TILED_WARPS];
-  uint32_t chunk_base;
+  double rows0[RB][4];                    // rows of the batch (x,y,z,pad)
+  double rowsS[RB][4];                    // rows shifted by a periodic image
+  unsigned long long part[NACC][RB][32];  // partial sums [row][lane]
+  uint2 lq[QCAP][32];                     // lane-private accepted-pair queues [slot][lane]: (j, row | image << 8)
+  uint32_t run_pref[32];                  // candidate-run directory: inclusive prefix of run lengths
+  uint32_t run_delta[32];                 //   j = k + run_delta[run]
+  uint32_t dq_pref[32];                   // drain directory: inclusive prefix of queue lengths
+  uint32_t danger;
+  uint32_t pad_[3];
 };
 
-constexpr uint32_t TILED_CHUNK = 64; // buckets claimed per scheduler step by a CTA
+constexpr uint32_t TILED_GRAB = 8; // consecutive buckets a warp claims per scheduler step
 
-// Evaluate F for up to 32 queued pairs, one per lane (full lane utilisation:
-// the expensive part of the product — sqrt, divide, the user's math — runs on
-// compacted pairs instead of on the ~15 % of lanes that pass the cut-off test).
+// Drain the lane-private queues: the queued (j, row) pairs of all lanes are
+// dealt out evenly, 32 per round, so the expensive part of the product (sqrt,
+// divide, the user's math) runs at full lane utilisation instead of on the ~15 %
+// of lanes that pass the cut-off test.  dx and |dx|^2 are recomputed here with
+// the same operations in the same order as in the test.
 template <int D, class F, bool STATS, class SM>
-__device__ __forceinline__ void drain_queue(SM &sm, const abr_matvec_plan &p, const F &f, int warp, int lane,
-                                            uint32_t head, uint32_t count, uint32_t r0, const double (*rowp)[4]) {
+__device__ __forceinline__ void drain_queues(SM &sm, const abr_matvec_plan &p, const F &f, int lane, uint32_t &cnt,
+                                             uint32_t r0, const double (*rowp)[4]) {
   constexpr int BR = F::BR, BC = F::BC;
+  uint32_t pin = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pin, o);
+    if (lane >= o) pin += t;
+  }
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, pin, 31);
   __syncwarp();
-  if ((uint32_t)lane < count) {
-    const uint32_t e = (head + lane) & (QCAP - 1);
-    const double d2 = sm.q_d2[warp][e];
-    const uint2 ji = sm.q_ji[warp][e];
-    const uint32_t j = ji.x, i = ji.y & 0xFFu;
-    if (d2 > p.r2lo) atomicOr(&sm.danger[warp], 1u << i);
-    if (STATS) {
-      sm.part[warp][0][i][lane] += 1ull;
-      sm.part[warp][1][i][lane] += mix64((uint64_t)j * 81u + (uint64_t)(ji.y >> 8));
-    } else {
+  sm.dq_pref[lane] = pin;
+  __syncwarp();
+  for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t k = base + lane;
+    if (k < total) {
+      uint32_t o = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1)
+        if (sm.dq_pref[o + step - 1] <= k) o += step;
+      const uint32_t local = k - (o ? sm.dq_pref[o - 1] : 0u);
+      const uint2 ji = sm.lq[local][o];
+      const uint32_t j = ji.x, i = ji.y & 0xFFu;
       double dx[D];
-      if (needs_dx<F>::value) {
+      double d2 = 0;
 #pragma unroll
-        for (int d = 0; d < D; ++d) dx[d] = p.q.pos[(size_t)j * D + d] - rowp[i][d];
-      } else {
-#pragma unroll
-        for (int d = 0; d < D; ++d) dx[d] = 0.0;
+      for (int d = 0; d < D; ++d) {
+        dx[d] = p.q.pos[(size_t)j * D + d] - rowp[i][d];
+        d2 = d2 + dx[d] * dx[d];
       }
-      double blk[BR * BC];
-      f(dx, d2, r0 + i, j, blk);
+      if (d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
+      if (STATS) {
+        sm.part[0][i][lane] += 1ull;
+        sm.part[1][i][lane] += mix64((uint64_t)j * 81u + (uint64_t)(ji.y >> 8));
+      } else {
+        double blk[BR * BC];
+        f(dx, d2, r0 + i, j, blk);
 #pragma unroll
-      for (int a2 = 0; a2 < BR; ++a2) {
-        double s = 0;
+        for (int a2 = 0; a2 < BR; ++a2) {
+          double s = 0;
 #pragma unroll
-        for (int c = 0; c < BC; ++c) s += blk[a2 * BC + c] * p.b[(size_t)j * BC + c];
-        double *slot = reinterpret_cast<double *>(&sm.part[warp][a2][i][lane]);
-        *slot += s;
+          for (int c = 0; c < BC; ++c) s += blk[a2 * BC + c] * p.b[(size_t)j * BC + c];
+          double *slot = reinterpret_cast<double *>(&sm.part[a2][i][lane]);
+          *slot += s;
+        }
       }
     }
   }
+  cnt = 0;
   __syncwarp();
 }
 
 // One step of the hot loop: this lane's candidate j against the nr rows of the
-// batch.  Exact un-fused predicate; accepted pairs are pushed to the queue.
+// batch.  Exact un-fused predicate; an accepted pair costs one predicated store
+// into the lane's own queue.
 template <int D, class F, bool STATS, class SM>
-__device__ __forceinline__ void test_rows(SM &sm, const abr_matvec_plan &p, const F &f, int warp, int lane,
-                                          uint32_t lane_lt, const double *pj, uint32_t j, bool valid, int nr,
-                                          const double (*rowp)[4], uint32_t image_tag, uint32_t r0, uint32_t &qhead,
-                                          uint32_t &qtail) {
+__device__ __forceinline__ void test_rows(SM &sm, const abr_matvec_plan &p, const F &f, int lane, const double *pj,
+                                          uint32_t j, bool valid, int nr, const double (*rowp)[4], uint32_t image_tag,
+                                          uint32_t r0, uint32_t &cnt) {
   const double R2 = p.r2;
-#pragma unroll 2
-  for (int i = 0; i < nr; ++i) {
-    double acc = 0;
+  int i = 0;
+  for (; i + 1 < nr; i += 2) {
+    double acc0 = 0, acc1 = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      const double dxd = pj[d] - rowp[i][d];
-      acc = acc + dxd * dxd;
+      const double a = pj[d] - rowp[i][d];
+      const double b = pj[d] - rowp[i + 1][d];
+      acc0 = acc0 + a * a;
+      acc1 = acc1 + b * b;
     }
-    const bool ok = valid && !(acc > R2);
-    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, ok);
-    if (ok) {
-      const uint32_t e = (qtail + __popc(mask & lane_lt)) & (QCAP - 1);
-      sm.q_d2[warp][e] = acc;
-      sm.q_ji[warp][e] = make_uint2(j, (uint32_t)i | image_tag);
+    if (valid && !(acc0 > R2)) {
+      sm.lq[cnt][lane] = make_uint2(j, (uint32_t)i | image_tag);
+      ++cnt;
     }
-    qtail += __popc(mask);
-    if (qtail - qhead >= 32u) {
-      drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, 32u, r0, rowp);
-      qhead += 32u;
+    if (valid && !(acc1 > R2)) {
+      sm.lq[cnt][lane] = make_uint2(j, (uint32_t)(i + 1) | image_tag);
+      ++cnt;
     }
+    if (__any_sync(0xFFFFFFFFu, cnt >= (uint32_t)(QCAP - 1))) drain_queues<D, F, STATS>(sm, p, f, lane, cnt, r0, rowp);
+  }
+  if (i < nr) {
+    double acc0 = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double a = pj[d] - rowp[i][d];
+      acc0 = acc0 + a * a;
+    }
+    if (valid && !(acc0 > R2)) {
+      sm.lq[cnt][lane] = make_uint2(j, (uint32_t)i | image_tag);
+      ++cnt;
+    }
+    if (__any_sync(0xFFFFFFFFu, cnt >= (uint32_t)(QCAP - 1))) drain_queues<D, F, STATS>(sm, p, f, lane, cnt, r0, rowp);
   }
 }
 
 template <int D, class F, bool STATS>
-__global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matvec_plan p, const F f) {
+__global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_plan p, const F f) {
   constexpr int BR = F::BR;
   constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
   constexpr int RB = TiledCfg<D, F, STATS>::RB;
+  using WS = WarpSmem<D, F, STATS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  auto &sm = *reinterpret_cast<TiledSmem<D, F, STATS> *>(smem_raw);
-  const Grid &g = p.q.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t lane_lt = (1u << lane) - 1u;
+  WS &sm = reinterpret_cast<WS *>(smem_raw)[warp];
+  const Grid &g = p.q.g;
   const double *__restrict__ pos = p.q.pos;
   const uint32_t *__restrict__ bbeg = p.q.bucket_begin;
   const uint32_t *__restrict__ bend = p.q.bucket_end;
@@ -253,14 +282,14 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
   const uint32_t image_tag0 = STATS ? ((uint32_t)image_linear_index<D>(g, img0) << 8) : 0u;
 
   while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) sm.chunk_base = atomicAdd(p.work_counter, TILED_CHUNK);
-    __syncthreads();
-    const uint32_t chunk = sm.chunk_base;
-    if (chunk >= g.ncells) break;
-    const uint32_t chunk_end = min(chunk + TILED_CHUNK, g.ncells);
+    // warp-level dynamic scheduler: no block barrier anywhere in this kernel
+    uint32_t grab = 0;
+    if (lane == 0) grab = atomicAdd(p.work_counter, TILED_GRAB);
+    grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
+    if (grab >= g.ncells) break;
+    const uint32_t grab_end = min(grab + TILED_GRAB, g.ncells);
 
-    for (uint32_t cell = chunk + warp; cell < chunk_end; cell += TILED_WARPS) {
+    for (uint32_t cell = grab; cell < grab_end; ++cell) {
       const uint32_t rb = bbeg[cell], re = bend[cell];
       if (rb == re) continue;
       // bucket coordinates of the target (inverse of collapse_index)
@@ -284,23 +313,24 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
         const int nr = (int)min((uint32_t)RB, re - r0);
         // ---- load the rows of this batch, flag rounding-sensitive ones ----
         bool my_danger = false;
+        __syncwarp();
         if (lane < nr) {
 #pragma unroll
           for (int d = 0; d < D; ++d) {
             const double r = pos[(size_t)(r0 + lane) * D + d];
-            sm.rows0[warp][lane][d] = r;
+            sm.rows0[lane][d] = r;
             const double fl = (r - g.bmin[d]) * g.inv_side[d];
             const double fr = fl - floor(fl);
             my_danger |= ((int)floor(fl) != tc[d]) | (fr < p.tolf[d]) | (fr > 1.0 - p.tolf[d]) |
                          (fabs(fr - 0.5) < p.tolf[d]);
           }
         }
-        if (lane == 0) sm.danger[warp] = 0;
+        if (lane == 0) sm.danger = 0;
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
-          for (int i = 0; i < nr; ++i) sm.part[warp][a][i][lane] = 0ull;
+          for (int i = 0; i < nr; ++i) sm.part[a][i][lane] = 0ull;
         __syncwarp();
-        uint32_t qhead = 0, qtail = 0; // warp-uniform ring-buffer cursors
+        uint32_t cnt = 0; // entries in this lane's queue
 
         // ---- phase 1: neighbour runs in the primary image, concatenated so that
         //      every step tests 32 candidates (one run = the 2w+1 buckets along the
@@ -336,8 +366,8 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
           }
           const uint32_t total = __shfl_sync(0xFFFFFFFFu, pin, 31);
           __syncwarp();
-          sm.run_pref[warp][lane] = pin;
-          sm.run_delta[warp][lane] = jb - (pin - len);
+          sm.run_pref[lane] = pin;
+          sm.run_delta[lane] = jb - (pin - len);
           __syncwarp();
           for (uint32_t kb = 0; kb < total; kb += 32) {
             const uint32_t k = kb + lane;
@@ -346,22 +376,17 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
             uint32_t rho = 0;
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1)
-              if (sm.run_pref[warp][rho + step - 1] <= ks) rho += step;
-            const uint32_t j = ks + sm.run_delta[warp][rho];
+              if (sm.run_pref[rho + step - 1] <= ks) rho += step;
+            const uint32_t j = ks + sm.run_delta[rho];
             double pj[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) pj[d] = pos[(size_t)j * D + d];
-            test_rows<D, F, STATS>(sm, p, f, warp, lane, lane_lt, pj, j, valid, nr, sm.rows0[warp], image_tag0, r0,
-                                   qhead, qtail);
+            test_rows<D, F, STATS>(sm, p, f, lane, pj, j, valid, nr, sm.rows0, image_tag0, r0, cnt);
           }
         }
         // pairs queued so far belong to the primary image
+        if (__any_sync(0xFFFFFFFFu, cnt != 0)) drain_queues<D, F, STATS>(sm, p, f, lane, cnt, r0, sm.rows0);
         if (boundary) {
-          while (qtail != qhead) {
-            const uint32_t cnt = min(32u, qtail - qhead);
-            drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, sm.rows0[warp]);
-            qhead += cnt;
-          }
           // ---- phase 2 (buckets at a periodic boundary only): runs reached through
           //      a periodic image; cur = r + image * L exactly as src/Search.h:188-190 ----
           int o[D > 1 ? D - 1 : 1];
@@ -400,8 +425,7 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
                 __syncwarp();
                 if (lane < nr) {
 #pragma unroll
-                  for (int d = 0; d < D; ++d)
-                    sm.rowsS[warp][lane][d] = sm.rows0[warp][lane][d] + (double)img[d] * g.L[d];
+                  for (int d = 0; d < D; ++d) sm.rowsS[lane][d] = sm.rows0[lane][d] + (double)img[d] * g.L[d];
                 }
                 __syncwarp();
                 const uint32_t image_tag = STATS ? ((uint32_t)image_linear_index<D>(g, img) << 8) : 0u;
@@ -411,15 +435,10 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
                   double pj[D];
 #pragma unroll
                   for (int d = 0; d < D; ++d) pj[d] = pos[(size_t)j * D + d];
-                  test_rows<D, F, STATS>(sm, p, f, warp, lane, lane_lt, pj, j, valid, nr, sm.rowsS[warp], image_tag,
-                                         r0, qhead, qtail);
+                  test_rows<D, F, STATS>(sm, p, f, lane, pj, j, valid, nr, sm.rowsS, image_tag, r0, cnt);
                 }
-                // leave no pair of this image in the queue (rowsS is reused)
-                while (qtail != qhead) {
-                  const uint32_t cnt = min(32u, qtail - qhead);
-                  drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, sm.rowsS[warp]);
-                  qhead += cnt;
-                }
+                // leave no pair of this image in the queues (rowsS is reused)
+                if (__any_sync(0xFFFFFFFFu, cnt != 0)) drain_queues<D, F, STATS>(sm, p, f, lane, cnt, r0, sm.rowsS);
               }
             }
             // next offset tuple in the slow dimensions (odometer)
@@ -436,15 +455,10 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
             }
           }
         }
-        while (qtail != qhead) {
-          const uint32_t cnt = min(32u, qtail - qhead);
-          drain_queue<D, F, STATS>(sm, p, f, warp, lane, qhead, cnt, r0, sm.rows0[warp]);
-          qhead += cnt;
-        }
         __syncwarp();
 
         // ---- reduce part[row][*] in a fixed (skewed, conflict-free) order ----
-        const uint32_t dmask = sm.danger[warp] | __ballot_sync(0xFFFFFFFFu, my_danger);
+        const uint32_t dmask = sm.danger | __ballot_sync(0xFFFFFFFFu, my_danger);
         if (lane < nr) {
           const bool dangerous = (dmask >> lane) & 1u;
           if (dangerous) {
@@ -453,8 +467,8 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
           } else if (STATS) {
             unsigned long long c = 0, hsum = 0;
             for (int k = 0; k < 32; ++k) {
-              c += sm.part[warp][0][lane][(k + lane) & 31];
-              hsum += sm.part[warp][1][lane][(k + lane) & 31];
+              c += sm.part[0][lane][(k + lane) & 31];
+              hsum += sm.part[1][lane][(k + lane) & 31];
             }
             if (p.stat_count) p.stat_count[r0 + lane] = (uint32_t)c;
             if (p.stat_hash) p.stat_hash[r0 + lane] = hsum;
@@ -462,8 +476,7 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
 #pragma unroll
             for (int a2 = 0; a2 < NACC; ++a2) {
               double s = 0;
-              for (int k = 0; k < 32; ++k)
-                s += *reinterpret_cast<double *>(&sm.part[warp][a2][lane][(k + lane) & 31]);
+              for (int k = 0; k < 32; ++k) s += *reinterpret_cast<double *>(&sm.part[a2][lane][(k + lane) & 31]);
               p.y[(size_t)(r0 + lane) * BR + a2] += s;
             }
           }
@@ -481,8 +494,7 @@ __global__ void __launch_bounds__(TILED_THREADS, 4) tiled_kernel(const abr_matve
 template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_plan &p, const F &f) {
   cudaError_t e;
   if (p.use_tiled) {
-    using SM = TiledSmem<D, F, STATS>;
-    const size_t smem = sizeof(SM);
+    const size_t smem = sizeof(WarpSmem<D, F, STATS>) * TILED_WARPS;
     auto kern = tiled_kernel<D, F, STATS>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -490,7 +502,7 @@ template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_pl
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILED_THREADS, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
-    const unsigned max_chunks = (p.q.g.ncells + TILED_CHUNK - 1) / TILED_CHUNK;
+    const unsigned max_chunks = (p.q.g.ncells + TILED_GRAB * TILED_WARPS - 1) / (TILED_GRAB * TILED_WARPS);
     unsigned grid = (unsigned)(p.sm_count * per_sm);
     if (grid > max_chunks) grid = max_chunks;
     if (grid < 1) grid = 1;
