@@ -37,7 +37,7 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p)
   const int D = h->D;
   bool tiled = c.rows_are_cols && !c.radius_per_row && h->n_aliased == 0 &&
                c.row_pos == h->pos_sorted && c.n_rows == h->n_sorted && c.radius > 0 &&
-               std::isfinite(c.radius);
+               std::isfinite(c.radius) && h->n_sorted < (1ull << 28); // queue entries pack (j << 4) | row
   if (c.force_path == 1) tiled = false;
   if (c.force_path == 0 && !tiled)
     return set_error(h, ABR_ERR_INVALID, "tiled path needs rows_are_cols, a constant radius and no aliased keys");

@@ -132,11 +132,14 @@ __global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, cons
 template <class F, class = void> struct needs_dx { static constexpr bool value = true; };
 template <class F> struct needs_dx<F, decltype((void)F::NEEDS_DX)> { static constexpr bool value = F::NEEDS_DX; };
 
-constexpr int QCAP = 8;   // accepted pairs a lane may hold before the warp drains
+constexpr int QCAP = 16;      // accepted pairs a lane may hold
+constexpr int QDRAIN = 12;    // drain when any lane holds this many (a test step adds <= 4)
+constexpr int QSTRIDE = QCAP + 1; // odd stride: lane-private columns fall into distinct banks
+constexpr int ROW_BITS = 4;
 
 template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
-  static constexpr int RB = 16; // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows)
+  static constexpr int RB = 1 << ROW_BITS; // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows)
 };
 
 // per-warp shared memory (a warp works on one target bucket at a time and never
@@ -147,7 +150,7 @@ template <int D, class F, bool STATS> struct WarpSmem {
   double rows0[RB][4];                    // rows of the batch (x,y,z,pad)
   double rowsS[RB][4];                    // rows shifted by a periodic image
   unsigned long long part[NACC][RB][32];  // partial sums [row][lane]
-  uint2 lq[QCAP][32];                     // lane-private accepted-pair queues [slot][lane]: (j, row | image << 8)
+  uint32_t lq[32][QSTRIDE];               // lane-private accepted-pair queues: (j << ROW_BITS) | row
   uint32_t run_pref[32];                  // candidate-run directory: inclusive prefix of run lengths
   uint32_t run_delta[32];                 //   j = k + run_delta[run]
   uint32_t dq_pref[32];                   // drain directory: inclusive prefix of queue lengths
@@ -162,9 +165,15 @@ constexpr uint32_t TILED_GRAB = 8; // consecutive buckets a warp claims per sche
 // divide, the user's math) runs at full lane utilisation instead of on the ~15 %
 // of lanes that pass the cut-off test.  dx and |dx|^2 are recomputed here with
 // the same operations in the same order as in the test.
+struct DrainCtx {
+  const double *pos;
+  const double *b;
+  double r2lo;
+};
+
 template <int D, class F, bool STATS, class SM>
-__device__ __forceinline__ void drain_queues(SM &sm, const abr_matvec_plan &p, const F &f, int lane, uint32_t &cnt,
-                                             uint32_t r0, const double (*rowp)[4]) {
+__device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, int lane, uint32_t cnt, uint32_t r0,
+                                          const double (*rowp)[4], uint32_t image_id) {
   constexpr int BR = F::BR, BC = F::BC;
   uint32_t pin = cnt;
 #pragma unroll
@@ -184,19 +193,19 @@ __device__ __forceinline__ void drain_queues(SM &sm, const abr_matvec_plan &p, c
       for (int step = 16; step > 0; step >>= 1)
         if (sm.dq_pref[o + step - 1] <= k) o += step;
       const uint32_t local = k - (o ? sm.dq_pref[o - 1] : 0u);
-      const uint2 ji = sm.lq[local][o];
-      const uint32_t j = ji.x, i = ji.y & 0xFFu;
+      const uint32_t ent = sm.lq[o][local];
+      const uint32_t j = ent >> ROW_BITS, i = ent & ((1u << ROW_BITS) - 1u);
       double dx[D];
       double d2 = 0;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        dx[d] = p.q.pos[(size_t)j * D + d] - rowp[i][d];
+        dx[d] = p.pos[(size_t)j * D + d] - rowp[i][d];
         d2 = d2 + dx[d] * dx[d];
       }
       if (d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
       if (STATS) {
         sm.part[0][i][lane] += 1ull;
-        sm.part[1][i][lane] += mix64((uint64_t)j * 81u + (uint64_t)(ji.y >> 8));
+        sm.part[1][i][lane] += mix64((uint64_t)j * 81u + (uint64_t)image_id);
       } else {
         double blk[BR * BC];
         f(dx, d2, r0 + i, j, blk);
@@ -211,50 +220,41 @@ __device__ __forceinline__ void drain_queues(SM &sm, const abr_matvec_plan &p, c
       }
     }
   }
-  cnt = 0;
   __syncwarp();
 }
 
-// One step of the hot loop: this lane's candidate j against the nr rows of the
-// batch.  Exact un-fused predicate; an accepted pair costs one predicated store
-// into the lane's own queue.
+// One step of the hot loop: this lane's TWO candidates (jA, jB) against the nr
+// rows of the batch, two rows at a time (one shared-memory row fetch feeds two
+// tests).  Exact un-fused predicate; an accepted pair costs one predicated
+// store into the lane's own queue.
 template <int D, class F, bool STATS, class SM>
-__device__ __forceinline__ void test_rows(SM &sm, const abr_matvec_plan &p, const F &f, int lane, const double *pj,
-                                          uint32_t j, bool valid, int nr, const double (*rowp)[4], uint32_t image_tag,
-                                          uint32_t r0, uint32_t &cnt) {
-  const double R2 = p.r2;
-  int i = 0;
-  for (; i + 1 < nr; i += 2) {
-    double acc0 = 0, acc1 = 0;
+__device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, double R2, const F &f, int lane, const double *pA,
+                                          const double *pB, uint32_t jA, uint32_t jB, bool vA, bool vB, int nr,
+                                          const double (*rowp)[4], uint32_t image_id, uint32_t r0, uint32_t &cnt) {
+  uint32_t *myq = sm.lq[lane];
+  const uint32_t eA = jA << ROW_BITS, eB = jB << ROW_BITS;
+  for (int i = 0; i < nr; i += 2) {
+    const bool second = i + 1 < nr; // odd tail: the second row of the pair is masked
+    const int i1 = second ? i + 1 : i;
+    double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      const double a = pj[d] - rowp[i][d];
-      const double b = pj[d] - rowp[i + 1][d];
-      acc0 = acc0 + a * a;
-      acc1 = acc1 + b * b;
+      const double r0d = rowp[i][d], r1d = rowp[i1][d];
+      const double ta0 = pA[d] - r0d, ta1 = pA[d] - r1d;
+      const double tb0 = pB[d] - r0d, tb1 = pB[d] - r1d;
+      a0 = a0 + ta0 * ta0;
+      a1 = a1 + ta1 * ta1;
+      b0 = b0 + tb0 * tb0;
+      b1 = b1 + tb1 * tb1;
     }
-    if (valid && !(acc0 > R2)) {
-      sm.lq[cnt][lane] = make_uint2(j, (uint32_t)i | image_tag);
-      ++cnt;
+    if (vA && !(a0 > R2)) myq[cnt++] = eA | (uint32_t)i;
+    if (vA && second && !(a1 > R2)) myq[cnt++] = eA | (uint32_t)i1;
+    if (vB && !(b0 > R2)) myq[cnt++] = eB | (uint32_t)i;
+    if (vB && second && !(b1 > R2)) myq[cnt++] = eB | (uint32_t)i1;
+    if (__any_sync(0xFFFFFFFFu, cnt >= (uint32_t)QDRAIN)) {
+      drain_queues<D, F, STATS>(sm, dc, f, lane, cnt, r0, rowp, image_id);
+      cnt = 0;
     }
-    if (valid && !(acc1 > R2)) {
-      sm.lq[cnt][lane] = make_uint2(j, (uint32_t)(i + 1) | image_tag);
-      ++cnt;
-    }
-    if (__any_sync(0xFFFFFFFFu, cnt >= (uint32_t)(QCAP - 1))) drain_queues<D, F, STATS>(sm, p, f, lane, cnt, r0, rowp);
-  }
-  if (i < nr) {
-    double acc0 = 0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const double a = pj[d] - rowp[i][d];
-      acc0 = acc0 + a * a;
-    }
-    if (valid && !(acc0 > R2)) {
-      sm.lq[cnt][lane] = make_uint2(j, (uint32_t)i | image_tag);
-      ++cnt;
-    }
-    if (__any_sync(0xFFFFFFFFu, cnt >= (uint32_t)(QCAP - 1))) drain_queues<D, F, STATS>(sm, p, f, lane, cnt, r0, rowp);
   }
 }
 
@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
   int img0[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) img0[d] = 0;
-  const uint32_t image_tag0 = STATS ? ((uint32_t)image_linear_index<D>(g, img0) << 8) : 0u;
+  const uint32_t image_id0 = STATS ? (uint32_t)image_linear_index<D>(g, img0) : 0u;
+  const DrainCtx dc{p.q.pos, p.b, p.r2lo};
+  const double R2 = p.r2;
 
   while (true) {
     // warp-level dynamic scheduler: no block barrier anywhere in this kernel
@@ -369,23 +371,33 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
           sm.run_pref[lane] = pin;
           sm.run_delta[lane] = jb - (pin - len);
           __syncwarp();
-          for (uint32_t kb = 0; kb < total; kb += 32) {
-            const uint32_t k = kb + lane;
-            const bool valid = k < total;
-            const uint32_t ks = valid ? k : total - 1;
-            uint32_t rho = 0;
+          for (uint32_t kb = 0; kb < total; kb += 64) {
+            // two candidates per lane: k and k + 32
+            uint32_t jj[2];
+            bool vv[2];
+            double pj[2][D];
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-              if (sm.run_pref[rho + step - 1] <= ks) rho += step;
-            const uint32_t j = ks + sm.run_delta[rho];
-            double pj[D];
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t k = kb + 32 * h + lane;
+              vv[h] = k < total;
+              const uint32_t ks = vv[h] ? k : total - 1;
+              uint32_t rho = 0;
 #pragma unroll
-            for (int d = 0; d < D; ++d) pj[d] = pos[(size_t)j * D + d];
-            test_rows<D, F, STATS>(sm, p, f, lane, pj, j, valid, nr, sm.rows0, image_tag0, r0, cnt);
+              for (int step = 16; step > 0; step >>= 1)
+                if (sm.run_pref[rho + step - 1] <= ks) rho += step;
+              jj[h] = ks + sm.run_delta[rho];
+#pragma unroll
+              for (int d = 0; d < D; ++d) pj[h][d] = pos[(size_t)jj[h] * D + d];
+            }
+            test_rows<D, F, STATS>(sm, dc, R2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
+                                   image_id0, r0, cnt);
           }
         }
         // pairs queued so far belong to the primary image
-        if (__any_sync(0xFFFFFFFFu, cnt != 0)) drain_queues<D, F, STATS>(sm, p, f, lane, cnt, r0, sm.rows0);
+        if (__any_sync(0xFFFFFFFFu, cnt != 0)) {
+          drain_queues<D, F, STATS>(sm, dc, f, lane, cnt, r0, sm.rows0, image_id0);
+          cnt = 0;
+        }
         if (boundary) {
           // ---- phase 2 (buckets at a periodic boundary only): runs reached through
           //      a periodic image; cur = r + image * L exactly as src/Search.h:188-190 ----
@@ -428,17 +440,26 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
                   for (int d = 0; d < D; ++d) sm.rowsS[lane][d] = sm.rows0[lane][d] + (double)img[d] * g.L[d];
                 }
                 __syncwarp();
-                const uint32_t image_tag = STATS ? ((uint32_t)image_linear_index<D>(g, img) << 8) : 0u;
-                for (uint32_t cb = jb; cb < je; cb += 32) {
-                  const uint32_t j = min(cb + lane, je - 1);
-                  const bool valid = cb + lane < je;
-                  double pj[D];
+                const uint32_t image_id = STATS ? (uint32_t)image_linear_index<D>(g, img) : 0u;
+                for (uint32_t cb = jb; cb < je; cb += 64) {
+                  uint32_t jj[2];
+                  bool vv[2];
+                  double pj[2][D];
 #pragma unroll
-                  for (int d = 0; d < D; ++d) pj[d] = pos[(size_t)j * D + d];
-                  test_rows<D, F, STATS>(sm, p, f, lane, pj, j, valid, nr, sm.rowsS, image_tag, r0, cnt);
+                  for (int h = 0; h < 2; ++h) {
+                    jj[h] = min(cb + 32 * h + lane, je - 1);
+                    vv[h] = cb + 32 * h + lane < je;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) pj[h][d] = pos[(size_t)jj[h] * D + d];
+                  }
+                  test_rows<D, F, STATS>(sm, dc, R2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
+                                         image_id, r0, cnt);
                 }
                 // leave no pair of this image in the queues (rowsS is reused)
-                if (__any_sync(0xFFFFFFFFu, cnt != 0)) drain_queues<D, F, STATS>(sm, p, f, lane, cnt, r0, sm.rowsS);
+                if (__any_sync(0xFFFFFFFFu, cnt != 0)) {
+                  drain_queues<D, F, STATS>(sm, dc, f, lane, cnt, r0, sm.rowsS, image_id);
+                  cnt = 0;
+                }
               }
             }
             // next offset tuple in the slow dimensions (odometer)
