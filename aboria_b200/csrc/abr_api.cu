@@ -178,7 +178,7 @@ int abr_celllist_build(abr_handle hh, double *pos, uint8_t *alive, size_t n, int
   if (!h) return ABR_ERR_INVALID;
   if (n > 0 && (!pos || !alive || !order_out)) return abr::set_error(h, ABR_ERR_INVALID, "build: null pointer");
   ABR_CUDA(h, cudaSetDevice(h->device));
-  return abr::build_celllist(h, pos, alive, n, order_out, n_alive_host);
+  return abr::build_celllist(h, pos, alive, n, order_out, n_alive_host, nullptr);
 }
 
 int abr_celllist_get(abr_handle hh, const uint32_t **bucket_indices, const uint32_t **bucket_begin, const uint32_t **bucket_end, uint64_t *n_buckets) {
@@ -198,7 +198,29 @@ int abr_gather_columns(abr_handle hh, int ncols, const void *const *src, void *c
   if (ncols < 0 || (ncols > 0 && (!src || !dst || !elem_bytes))) return abr::set_error(h, ABR_ERR_INVALID, "gather: null pointer");
   if (n_out > 0 && !order) return abr::set_error(h, ABR_ERR_INVALID, "gather: null order");
   ABR_CUDA(h, cudaSetDevice(h->device));
-  return abr::gather_columns(h, ncols, src, dst, elem_bytes, order, n_out);
+  return abr::gather_columns(h, ncols, src, dst, elem_bytes, order, n_out, nullptr);
+}
+
+int abr_update_positions(abr_handle hh, double *pos, uint8_t *alive, size_t n, int ncols, const void *const *src, void *const *dst,
+                         const size_t *elem_bytes, int32_t *order_out, size_t *n_alive_host) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (n > 0 && (!pos || !alive || !order_out)) return abr::set_error(h, ABR_ERR_INVALID, "update_positions: null pointer");
+  if (ncols <= 0 || !src || !dst || !elem_bytes) return abr::set_error(h, ABR_ERR_INVALID, "update_positions: no columns");
+  int pos_col = -1;
+  for (int c = 0; c < ncols; ++c)
+    if (src[c] == (const void *)pos) pos_col = c;
+  if (pos_col < 0 && n > 0) return abr::set_error(h, ABR_ERR_INVALID, "update_positions: the position column must be among the columns");
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::ReorderSpec spec{ncols, src, dst, elem_bytes};
+  size_t n_alive = 0;
+  int rc = abr::build_celllist(h, pos, alive, n, order_out, &n_alive, n > 0 ? &spec : nullptr);
+  if (rc) return rc;
+  if (n_alive_host) *n_alive_host = n_alive;
+  // update_iterators: the query now reads the reordered position column
+  h->pos_sorted = n > 0 ? static_cast<const double *>(dst[pos_col]) : nullptr;
+  h->n_sorted = n_alive;
+  return ABR_OK;
 }
 
 int abr_query_set_particles(abr_handle hh, const double *pos_sorted, size_t n) {

@@ -364,27 +364,48 @@ k_boundaries(const uint32_t *__restrict__ keys, uint32_t n, uint32_t ncells, uin
 // of a warp are one contiguous 256-byte span; the loads of one element are
 // contiguous too.  Other element sizes fall back to a byte-granular variant.
 // ---------------------------------------------------------------------------
+// n_dev (optional): device-side element count (the alive count of the build that
+// is still in flight), so the reorder can be enqueued without a host round trip.
 __global__ void __launch_bounds__(256)
 k_gather_words(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
-               const int32_t *__restrict__ order, uint64_t n_out, uint32_t words) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_out * words) return;
-  const uint64_t k = g / words;
-  const uint32_t w = (uint32_t)(g - k * words);
-  dst[g] = src[(uint64_t)order[k] * words + w];
+               const int32_t *__restrict__ order, uint64_t n_out, const uint32_t *__restrict__ n_dev,
+               uint32_t words) {
+  // stage 256 elements in shared memory, then store them as one contiguous,
+  // 16-byte-vectorised span (the loads are the random side of the gather)
+  extern __shared__ uint64_t s_stage[];
+  if (n_dev) n_out = min(n_out, (uint64_t)*n_dev);
+  const uint64_t k0 = (uint64_t)blockIdx.x * 256;
+  if (k0 >= n_out) return;
+  const uint32_t cnt = (uint32_t)min((uint64_t)256, n_out - k0);
+  if (threadIdx.x < cnt) {
+    const uint64_t *e = src + (uint64_t)order[k0 + threadIdx.x] * words;
+    for (uint32_t w = 0; w < words; ++w) s_stage[threadIdx.x * words + w] = e[w];
+  }
+  __syncthreads();
+  const uint32_t total = cnt * words;
+  uint64_t *out = dst + k0 * words; // 16-byte aligned: k0 * words * 8 is a multiple of 2048
+  if ((total & 1u) == 0 && ((uintptr_t)out & 15u) == 0) {
+    const ulonglong2 *sv = reinterpret_cast<const ulonglong2 *>(s_stage);
+    ulonglong2 *ov = reinterpret_cast<ulonglong2 *>(out);
+    for (uint32_t t = threadIdx.x; t < total / 2; t += 256) ov[t] = sv[t];
+  } else {
+    for (uint32_t t = threadIdx.x; t < total; t += 256) out[t] = s_stage[t];
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_gather_small(const T *__restrict__ src, T *__restrict__ dst, const int32_t *__restrict__ order,
-               uint64_t n_out) {
+               uint64_t n_out, const uint32_t *__restrict__ n_dev) {
+  if (n_dev) n_out = min(n_out, (uint64_t)*n_dev);
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n_out) dst[k] = src[order[k]];
 }
 
 __global__ void __launch_bounds__(256)
 k_gather_bytes(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
-               const int32_t *__restrict__ order, uint64_t n_out, uint32_t eb) {
+               const int32_t *__restrict__ order, uint64_t n_out, const uint32_t *__restrict__ n_dev, uint32_t eb) {
+  if (n_dev) n_out = min(n_out, (uint64_t)*n_dev);
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_out * eb) return;
   const uint64_t k = g / eb;
@@ -433,25 +454,25 @@ int probe_fp64_peak(Handle *h, double *tflops) {
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
-                   const size_t *elem_bytes, const int32_t *order, size_t n_out) {
+                   const size_t *elem_bytes, const int32_t *order, size_t n_out, const uint32_t *n_dev) {
   if (n_out == 0) return ABR_OK;
   for (int c = 0; c < ncols; ++c) {
     const size_t eb = elem_bytes[c];
     if (eb == 0 || !src[c] || !dst[c]) return set_error(h, ABR_ERR_INVALID, "gather: null column");
     const bool aligned8 = (eb % 8 == 0) && ((uintptr_t)src[c] % 8 == 0) && ((uintptr_t)dst[c] % 8 == 0);
-    if (aligned8) {
+    if (aligned8 && eb <= 128) { // staged path: 256 * eb bytes of shared memory (<= 32 KB)
       const uint32_t words = (uint32_t)(eb / 8);
-      k_gather_words<<<grid_for((uint64_t)n_out * words, 256), 256, 0, h->stream>>>(
-          (const uint64_t *)src[c], (uint64_t *)dst[c], order, n_out, words);
+      k_gather_words<<<grid_for(n_out, 256), 256, 256 * eb, h->stream>>>(
+          (const uint64_t *)src[c], (uint64_t *)dst[c], order, n_out, n_dev, words);
     } else if (eb == 4 && (uintptr_t)src[c] % 4 == 0 && (uintptr_t)dst[c] % 4 == 0) {
       k_gather_small<uint32_t><<<grid_for(n_out, 256), 256, 0, h->stream>>>(
-          (const uint32_t *)src[c], (uint32_t *)dst[c], order, n_out);
+          (const uint32_t *)src[c], (uint32_t *)dst[c], order, n_out, n_dev);
     } else if (eb == 1) {
       k_gather_small<uint8_t><<<grid_for(n_out, 256), 256, 0, h->stream>>>(
-          (const uint8_t *)src[c], (uint8_t *)dst[c], order, n_out);
+          (const uint8_t *)src[c], (uint8_t *)dst[c], order, n_out, n_dev);
     } else {
       k_gather_bytes<<<grid_for((uint64_t)n_out * eb, 256), 256, 0, h->stream>>>(
-          (const uint8_t *)src[c], (uint8_t *)dst[c], order, n_out, (uint32_t)eb);
+          (const uint8_t *)src[c], (uint8_t *)dst[c], order, n_out, n_dev, (uint32_t)eb);
     }
   }
   h->launches += (uint64_t)ncols;
@@ -513,7 +534,7 @@ Grid Handle::grid() const {
 }
 
 int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *order_out,
-                   size_t *n_alive_host) {
+                   size_t *n_alive_host, const ReorderSpec *reorder) {
   if (!h->domain_set) return set_error(h, ABR_ERR_STATE, "build: domain has not been set");
   if (n >= 0x7FFFFFFFull) return set_error(h, ABR_ERR_UNSUPPORTED, "build: n must fit in int32");
   const int D = h->D;
@@ -621,6 +642,13 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     if (e != cudaSuccess) return check_cuda(h, e, "bucket fill");
 
     ABR_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+    if (reorder) {
+      // Particles::reorder enqueued behind the build, bounded by the device-side
+      // alive count: the only host round trip of update_positions is the final one
+      int rc = gather_columns(h, reorder->ncols, reorder->src, reorder->dst, reorder->elem_bytes, order_out, n,
+                              &h->d_scalars->n_alive);
+      if (rc) return rc;
+    }
     ABR_CUDA(h, cudaStreamSynchronize(h->stream));
     const size_t n_alive = h->h_scalars->n_alive;
     h->n_aliased = h->h_scalars->n_aliased;

@@ -88,10 +88,16 @@ int set_error(Handle *h, int code, const std::string &msg);
 int check_cuda(Handle *h, cudaError_t e, const char *what);
 
 // abr_build.cu
+struct ReorderSpec {
+  int ncols;
+  const void *const *src;
+  void *const *dst;
+  const size_t *elem_bytes;
+};
 int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *order_out,
-                   size_t *n_alive_host);
+                   size_t *n_alive_host, const ReorderSpec *reorder);
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
-                   const size_t *elem_bytes, const int32_t *order, size_t n_out);
+                   const size_t *elem_bytes, const int32_t *order, size_t n_out, const uint32_t *n_dev);
 
 // abr_matvec.cu
 struct MatvecCall {

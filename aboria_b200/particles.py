@@ -154,22 +154,19 @@ class Particles:
         alive = self.columns["alive"]
         order = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
         n_alive = C.c_size_t(0)
-        check(self._h, self._lib.abr_celllist_build(self._h, _ptr(pos), _ptr(alive), n, _ptr(order), C.byref(n_alive)))
-        na = n_alive.value
-        self._order = order[:na]
-        # reorder: gather every column into the other buffer and swap
+        # reorder: every column is gathered into the other buffer (room for n), then swapped
         names = list(self.columns)
         src = [self.columns[k] for k in names]
-        dst = [torch.empty((na,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for t in src]
-        if na > 0:
-            nc = len(names)
-            SP = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
-            DP = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
-            EB = (C.c_size_t * nc)(*[t.element_size() * int(np.prod(t.shape[1:], dtype=np.int64)) for t in src])
-            check(self._h, self._lib.abr_gather_columns(self._h, nc, SP, DP, EB, _ptr(order), na))
+        dst = [torch.empty_like(t) for t in src]
+        nc = len(names)
+        SP = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
+        DP = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
+        EB = (C.c_size_t * nc)(*[t.element_size() * int(np.prod(t.shape[1:], dtype=np.int64)) for t in src])
+        check(self._h, self._lib.abr_update_positions(self._h, _ptr(pos), _ptr(alive), n, nc, SP, DP, EB, _ptr(order), C.byref(n_alive)))
+        na = n_alive.value
+        self._order = order[:na]
         self._other = dict(zip(names, src))
-        self.columns = dict(zip(names, dst))
-        check(self._h, self._lib.abr_query_set_particles(self._h, _ptr(self.columns["position"]), na))
+        self.columns = {k: t[:na] for k, t in zip(names, dst)}
         self.n_buckets = self.grid()[2]
         return na
 

@@ -28,6 +28,18 @@
 #include "aboria_b200/detail/matvec_kernels.cuh"
 
 namespace abr {
+
+// sqrt for a squared distance.  d2 == 0 (the self pair, present in every row of
+// create_sparse_operator(p, p, ...)) would send the whole warp through the
+// library's special-case path; route it around instead.  rsqrt * x is within
+// 2 ulp of sqrt(x) — far inside the 1e-12 relative L2 budget of the product.
+__device__ __forceinline__ double sqrt_d2(double d2) {
+  const bool pos = d2 > 0.0;
+  const double x = pos ? d2 : 1.0;
+  const double s = x * rsqrt(x);
+  return pos ? s : 0.0;
+}
+
 namespace functors {
 
 // tests/operators.h:842-847
@@ -55,7 +67,7 @@ struct InvDist {
   static constexpr int BR = 1, BC = 1;
   double eps;
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
-    blk[0] = 1.0 / (sqrt(d2) + eps);
+    blk[0] = __drcp_rn(sqrt_d2(d2) + eps);
   }
 };
 // tests/operators.h:251-256
@@ -65,7 +77,7 @@ struct InvDistAA {
   double eps;
   const double *ai, *aj;
   __device__ void operator()(const double *, double d2, uint32_t i, uint32_t j, double *blk) const {
-    blk[0] = (ai[i] * aj[j]) / (sqrt(d2) + eps);
+    blk[0] = (ai[i] * aj[j]) * __drcp_rn(sqrt_d2(d2) + eps);
   }
 };
 // tests/rbf_interpolation.h:310-313: pow(2 - r/h, 4) * (1 + 2 r/h)
@@ -74,7 +86,7 @@ struct WendlandC2 {
   static constexpr int BR = 1, BC = 1;
   double h;
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
-    const double r = sqrt(d2);
+    const double r = sqrt_d2(d2);
     const double t = 2.0 - r / h;
     const double t2 = t * t;
     blk[0] = (t2 * t2) * (1.0 + 2.0 * r / h);
@@ -90,7 +102,7 @@ template <int D> struct LJForce {
       for (int d = 0; d < D; ++d) blk[d] = 0.0;
       return;
     }
-    const double r = sqrt(d2);
+    const double r = sqrt_d2(d2);
     const double sr = sigma / r;
     const double sr2 = sr * sr;
     const double sr6 = sr2 * sr2 * sr2;
@@ -105,7 +117,7 @@ template <int D> struct SphDensity {
   static constexpr int BR = 1, BC = 1;
   double h, mass, wcon;
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
-    const double q = sqrt(d2) / h;
+    const double q = sqrt_d2(d2) / h;
     double W = 0.0;
     if (q <= 2.0) {
       double hD = h;
@@ -125,7 +137,7 @@ template <int D> struct SphPressure {
   const double *pdr2_i, *pdr2_j;
   __device__ void operator()(const double *dx, double d2, uint32_t i, uint32_t j, double *blk) const {
     double Fv = 0.0;
-    const double r = sqrt(d2);
+    const double r = sqrt_d2(d2);
     if (r != 0) {
       const double q = r / h;
       if (q <= 2.0) {

@@ -120,6 +120,17 @@ int abr_celllist_get(abr_handle h, const uint32_t **bucket_indices, const uint32
 int abr_gather_columns(abr_handle h, int ncols, const void *const *src_host, void *const *dst_host,
                        const size_t *elem_bytes_host, const int32_t *order, size_t n_out);
 
+/* Particles::update_positions (src/Particles.h:526-531) in one call:
+ * abr_celllist_build + abr_gather_columns of every column (the position column,
+ * recognised by src_host[c] == pos, must be among them) + update_iterators on
+ * the gathered position column.  The reorder is enqueued behind the build on
+ * the device (bounded by the device-side alive count), so the whole update
+ * costs ONE host synchronisation — the one that returns n_alive_host.
+ * dst columns must have room for n elements; their first n_alive are valid. */
+int abr_update_positions(abr_handle h, double *pos, uint8_t *alive, size_t n, int ncols,
+                         const void *const *src_host, void *const *dst_host,
+                         const size_t *elem_bytes_host, int32_t *order_out, size_t *n_alive_host);
+
 /* neighbour_search_base::update_iterators (src/NeighbourSearchBase.h:504-512):
  * point the query at the reordered position column (n_alive x D). */
 int abr_query_set_particles(abr_handle h, const double *pos_sorted, size_t n);
