@@ -55,6 +55,10 @@ int abr_create(abr_handle *out, int device, void *stream) {
     return ABR_ERR_CUDA;
   }
   cudaMemset(h->d_scalars, 0, sizeof(abr::DevScalars));
+  // the reorder is a random gather of 1..104-byte elements: ask L2 to fetch 32-byte
+  // sectors from HBM instead of the default 64 (a hint; measured in profiles/)
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  cudaGetLastError();
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
   for (int d = 0; d < abr::MAXD; ++d) {
@@ -137,6 +141,7 @@ int abr_domain_set(abr_handle hh, int D, const double *bmin, const double *bmax,
   if (rc) return rc;
   h->n_leaf = n_leaf;
   h->grid_forced = false;
+  h->windowed = false;
   // set_domain -> set_domain_impl with the current m_alive_indices.size()
   // (src/NeighbourSearchBase.h:252-268, src/CellListOrdered.h:132-139)
   abr::host_set_domain_impl(h, h->n_alive_last);
@@ -156,6 +161,59 @@ int abr_domain_force_grid(abr_handle hh, int D, const double *bmin, const double
     h->inv_side[d] = 1.0 / h->side[d];
   }
   h->grid_forced = true;
+  h->windowed = false;
+  return ABR_OK;
+}
+
+int abr_domain_set_window(abr_handle hh, int win_lo, int win_n, int own_lo, int own_n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (!h->domain_set || !h->grid_forced) return abr::set_error(h, ABR_ERR_STATE, "set_window: call abr_domain_force_grid (global grid) first");
+  if (h->D < 2) return abr::set_error(h, ABR_ERR_UNSUPPORTED, "set_window: slabs need D >= 2");
+  const int S0 = (int)h->size[0];
+  if (win_n < 1 || win_n > S0 || own_lo < 0 || own_n < 1 || own_lo + own_n > win_n || win_lo < -S0 || win_lo >= S0)
+    return abr::set_error(h, ABR_ERR_INVALID, "set_window: bad window");
+  if (!h->periodic[0] && (win_lo < 0 || win_lo + win_n > S0))
+    return abr::set_error(h, ABR_ERR_INVALID, "set_window: window leaves a non-periodic domain");
+  h->windowed = true;
+  h->win_lo = win_lo;
+  h->win_n = win_n;
+  h->own_lo = own_lo;
+  h->own_n = own_n;
+  h->built = false;
+  return ABR_OK;
+}
+
+int abr_grid_for(int D, const double *bmin, const double *bmax, double n_leaf, size_t n, uint32_t *size, double *side) {
+  // CellListOrdered::set_domain_impl (src/CellListOrdered.h:140-157) as a pure function
+  if (D < 1 || D > abr::MAXD || !bmin || !bmax || !size || !side || !(n_leaf > 0)) return ABR_ERR_INVALID;
+  if (n_leaf > n) {
+    for (int d = 0; d < D; ++d) size[d] = 1;
+  } else {
+    double total_volume = 1.0;
+    for (int d = 0; d < D; ++d) total_volume *= (bmax[d] - bmin[d]);
+    const double box_volume = n_leaf / double(n) * total_volume;
+    const double box_side_length = std::pow(box_volume, 1.0 / D);
+    for (int d = 0; d < D; ++d) {
+      size[d] = static_cast<unsigned int>(std::floor((bmax[d] - bmin[d]) / box_side_length));
+      if (size[d] == 0) size[d] = 1;
+    }
+  }
+  for (int d = 0; d < D; ++d) side[d] = (bmax[d] - bmin[d]) / size[d];
+  return ABR_OK;
+}
+
+int abr_celllist_adopt_sorted(abr_handle hh, double *pos_sorted, uint8_t *alive, size_t n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (n > 0 && (!pos_sorted || !alive)) return abr::set_error(h, ABR_ERR_INVALID, "adopt_sorted: null pointer");
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  size_t n_alive = 0;
+  int rc = abr::build_celllist(h, pos_sorted, alive, n, nullptr, &n_alive, nullptr, true);
+  if (rc) return rc;
+  if (n_alive != n) return abr::set_error(h, ABR_ERR_INVALID, "adopt_sorted: dead or out-of-domain particles in a sorted set");
+  h->pos_sorted = pos_sorted;
+  h->n_sorted = n;
   return ABR_OK;
 }
 

@@ -27,7 +27,7 @@ namespace abr {
 // particle; the position / alive flag are written back only when they changed
 // (same memory image as the reference's unconditional store, fewer bytes).
 // ---------------------------------------------------------------------------
-template <int D>
+template <int D, bool WINDOWED>
 __global__ void __launch_bounds__(256)
 k_enforce_key(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t n, Grid g,
               uint32_t *__restrict__ keys, DevScalars *sc) {
@@ -70,9 +70,19 @@ k_enforce_key(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t n,
       v[d] = (int)floor((r[d] - g.bmin[d]) * g.inv_side[d]);
       overflow |= (v[d] >= g.size[d]) | (v[d] < 0);
     }
-    key = (uint32_t)collapse_index<D>(g, v);
-    if (overflow) atomicAdd(&sc->n_aliased, 1u);
-    if (key >= g.key_bound) key = g.key_bound - 1; // cannot happen (v[d] <= size[d]); keeps the sort in range
+    if (WINDOWED) {
+      const int cl = overflow ? -1 : local_collapse<D>(g, v);
+      if (cl < 0) {
+        atomicAdd(&sc->n_outside, 1u); // not this rank's particle: reported as an error by the host
+        key = g.key_bound;
+      } else {
+        key = (uint32_t)cl;
+      }
+    } else {
+      key = (uint32_t)collapse_index<D>(g, v);
+      if (overflow) atomicAdd(&sc->n_aliased, 1u);
+      if (key >= g.key_bound) key = g.key_bound - 1; // cannot happen (v[d] <= size[d]); keeps the sort in range
+    }
   }
   keys[p] = key;
 }
@@ -81,8 +91,8 @@ k_enforce_key(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t n,
 // k2: radix sort.  Tile = 256 threads x 16 keys, warp-striped so that the
 // order (warp, slot, lane) equals the memory order -> stable ranks.
 // ---------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
-constexpr int RS_IPT = 16;
+constexpr int RS_THREADS = 512;
+constexpr int RS_IPT = 8;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RADIX = 256;
@@ -93,7 +103,7 @@ k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t 
              uint32_t *__restrict__ hist) {
   __shared__ uint32_t s_hist[RADIX];
   const uint32_t tile = blockIdx.x;
-  s_hist[threadIdx.x] = 0;
+  if (threadIdx.x < RADIX) s_hist[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t base = tile * RS_TILE;
 #pragma unroll
@@ -102,20 +112,31 @@ k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t 
     if (p < n) atomicAdd(&s_hist[(keys[p] >> shift) & (RADIX - 1)], 1u);
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * num_tiles + tile] = s_hist[threadIdx.x];
+  if (threadIdx.x < RADIX) hist[(size_t)threadIdx.x * num_tiles + tile] = s_hist[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+struct RadixScatterSmem {
+  uint32_t warp_hist[RS_WARPS][RADIX];
+  uint32_t digit_start[RADIX];
+  uint32_t glob_off[RADIX];
+  uint32_t s_keys[RS_TILE];
+  uint32_t s_idx[RS_TILE];
+  uint32_t s_scan[RADIX / 32];
+};
+
+__global__ void __launch_bounds__(RS_THREADS, 2)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ idx_out,
                 const uint32_t *__restrict__ tile_offsets, int shift, uint32_t n,
                 uint32_t num_tiles) {
-  __shared__ uint32_t warp_hist[RS_WARPS][RADIX];
-  __shared__ uint32_t digit_start[RADIX];
-  __shared__ uint32_t glob_off[RADIX];
-  __shared__ uint32_t s_keys[RS_TILE];
-  __shared__ uint32_t s_idx[RS_TILE];
-  __shared__ uint32_t s_scan[RS_WARPS];
+  extern __shared__ __align__(16) unsigned char rs_raw[];
+  RadixScatterSmem &S = *reinterpret_cast<RadixScatterSmem *>(rs_raw);
+  auto &warp_hist = S.warp_hist;
+  auto &digit_start = S.digit_start;
+  auto &glob_off = S.glob_off;
+  auto &s_keys = S.s_keys;
+  auto &s_idx = S.s_idx;
+  auto &s_scan = S.s_scan;
 
   const uint32_t tile = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -147,9 +168,8 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   }
   __syncthreads();
 
-  // per digit: exclusive prefix over warps, block total
-  uint32_t total;
-  {
+  // per digit: exclusive prefix over warps, block total (threads 0..255 own a digit)
+  if (tid < RADIX) {
     const int d = tid;
     uint32_t running = 0;
 #pragma unroll
@@ -158,23 +178,26 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
       warp_hist[w][d] = running;
       running += c;
     }
-    total = running;
+    const uint32_t total = running;
     glob_off[d] = tile_offsets[(size_t)d * num_tiles + tile];
-  }
-  // exclusive scan of the 256 digit totals
-  uint32_t incl = total;
+    // exclusive scan of the 256 digit totals
+    uint32_t incl = total;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += t;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    digit_start[d] = incl - total; // warp-local exclusive; completed below
   }
-  if (lane == 31) s_scan[warp] = incl;
   __syncthreads();
-  uint32_t woff = 0;
+  if (tid < RADIX) {
+    uint32_t woff = 0;
 #pragma unroll
-  for (int w = 0; w < RS_WARPS; ++w)
-    if (w < warp) woff += s_scan[w];
-  digit_start[tid] = woff + incl - total;
+    for (int w = 0; w < RADIX / 32; ++w)
+      if (w < warp) woff += s_scan[w];
+    digit_start[tid] += woff;
+  }
   __syncthreads();
 
 #pragma unroll
@@ -349,6 +372,7 @@ k_boundaries(const uint32_t *__restrict__ keys, uint32_t n, uint32_t ncells, uin
   const uint32_t k = keys[p];
   const uint32_t kprev = p > 0 ? keys[p - 1] : 0xFFFFFFFFu;
   const uint32_t knext = p + 1 < n ? keys[p + 1] : 0xFFFFFFFFu;
+  if (p > 0 && k < kprev) atomicAdd(&sc->n_unsorted, 1u);
   if (p == 0 || k != kprev) {
     if (k < ncells) bb[k] = p;
     if (k >= ncells && (p == 0 || kprev < ncells)) sc->n_incell = p;
@@ -379,7 +403,7 @@ k_gather_words(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
   const uint32_t cnt = (uint32_t)min((uint64_t)256, n_out - k0);
   if (threadIdx.x < cnt) {
     const uint64_t *e = src + (uint64_t)order[k0 + threadIdx.x] * words;
-    for (uint32_t w = 0; w < words; ++w) s_stage[threadIdx.x * words + w] = e[w];
+    for (uint32_t w = 0; w < words; ++w) s_stage[threadIdx.x * words + w] = __ldcs(e + w);
   }
   __syncthreads();
   const uint32_t total = cnt * words;
@@ -530,11 +554,25 @@ Grid Handle::grid() const {
   for (int d = 0; d < D; ++d) bound = bound * size[d] + size[d];
   g.ncells = (uint32_t)prod;
   g.key_bound = (uint32_t)(bound + 1);
+  g.win_lo = 0;
+  g.win_n = g.size[0];
+  g.own_lo = 0;
+  g.own_n = g.size[0];
+  if (windowed) {
+    g.win_lo = win_lo;
+    g.win_n = win_n;
+    g.own_lo = own_lo;
+    g.own_n = own_n;
+    uint64_t per_layer = 1;
+    for (int d = 1; d < D; ++d) per_layer *= size[d];
+    g.ncells = (uint32_t)(per_layer * (uint64_t)win_n);
+    g.key_bound = g.ncells; // windowed keys are local bucket numbers; overflow keys are rejected
+  }
   return g;
 }
 
 int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *order_out,
-                   size_t *n_alive_host, const ReorderSpec *reorder) {
+                   size_t *n_alive_host, const ReorderSpec *reorder, bool presorted) {
   if (!h->domain_set) return set_error(h, ABR_ERR_STATE, "build: domain has not been set");
   if (n >= 0x7FFFFFFFull) return set_error(h, ABR_ERR_UNSUPPORTED, "build: n must fit in int32");
   const int D = h->D;
@@ -542,8 +580,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
   if (n == 0) { // update_n == 0 -> return false (src/NeighbourSearchBase.h:375-376)
     // the reference keeps whatever bucket arrays it had (all ranges empty after
     // set_domain_impl's resize); give the query the same: empty buckets
-    uint64_t prod = 1;
-    for (int d = 0; d < D; ++d) prod *= h->size[d];
+    const uint64_t prod = h->grid().ncells;
     ABR_CUDA(h, h->bucket_begin.reserve(prod * sizeof(uint32_t)));
     ABR_CUDA(h, h->bucket_end.reserve(prod * sizeof(uint32_t)));
     ABR_CUDA(h, cudaMemsetAsync(h->bucket_begin.p, 0, prod * sizeof(uint32_t), h->stream));
@@ -580,6 +617,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     for (int d = 0; d < D; ++d) prod *= h->size[d];
     if (prod >= 0x7FFFFFF0ull || (uint64_t)g.key_bound >= 0xFFFFFFF0ull)
       return set_error(h, ABR_ERR_UNSUPPORTED, "build: too many buckets for 32-bit keys");
+    prod = g.ncells; // buckets stored locally (the slab window when there is one)
     h->ncells = prod;
 
     const uint32_t n32 = (uint32_t)n;
@@ -602,17 +640,25 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
 
     uint32_t *keys0 = h->keys[0].as<uint32_t>();
     const unsigned gb = grid_for(n, 256);
-    switch (D) {
-    case 1: k_enforce_key<1><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
-    case 2: k_enforce_key<2><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
-    default: k_enforce_key<3><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+    if (h->windowed) {
+      switch (D) {
+      case 2: k_enforce_key<2, true><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+      default: k_enforce_key<3, true><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+      }
+    } else {
+      switch (D) {
+      case 1: k_enforce_key<1, false><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+      case 2: k_enforce_key<2, false><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+      default: k_enforce_key<3, false><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+      }
     }
     h->launches += 1;
 
     // LSD radix sort over the bits of key_bound
+    ABR_CUDA(h, cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixScatterSmem)));
     int bits = 1;
     while (bits < 32 && (g.key_bound >> bits) != 0) ++bits;
-    const int passes = (bits + 7) / 8;
+    const int passes = presorted ? 0 : (bits + 7) / 8; // adopt_sorted: keys only, no permutation
     int cur = 0;
     uint32_t *hist = h->tile_hist.as<uint32_t>();
     for (int pass = 0; pass < passes; ++pass) {
@@ -625,7 +671,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
       k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, n32, shift, num_tiles, hist);
       cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
       if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
-      k_radix_scatter<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, iin, kout, iout, hist, shift, n32, num_tiles);
+      k_radix_scatter<<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(kin, iin, kout, iout, hist, shift, n32, num_tiles);
       h->launches += 2;
       cur ^= 1;
     }
@@ -652,6 +698,11 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     ABR_CUDA(h, cudaStreamSynchronize(h->stream));
     const size_t n_alive = h->h_scalars->n_alive;
     h->n_aliased = h->h_scalars->n_aliased;
+    if (h->h_scalars->n_outside != 0)
+      return set_error(h, ABR_ERR_INVALID, "build: " + std::to_string(h->h_scalars->n_outside) +
+                                               " particle(s) lie outside this rank's slab window");
+    if (presorted && h->h_scalars->n_unsorted != 0)
+      return set_error(h, ABR_ERR_INVALID, "adopt_sorted: positions are not sorted by bucket");
 
     if (attempt == 0 && n_alive != n && !h->grid_forced) {
       // would the reference (which sees n_alive) have chosen another grid?

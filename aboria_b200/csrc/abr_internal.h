@@ -41,7 +41,9 @@ struct DevScalars {
   uint32_t n_aliased;      // alive particles whose bucket index vector overflowed (v[d] >= size[d])
   uint32_t work_counter;   // dynamic tile scheduler of the tiled matvec
   uint32_t danger_count;   // rows handed to the exact per-row walk
-  uint32_t pad[3];
+  uint32_t n_outside;      // particles whose bucket layer is not in this rank's window
+  uint32_t n_unsorted;     // adopt_sorted: key inversions found
+  uint32_t pad[1];
   unsigned long long pair_count;
 };
 
@@ -62,6 +64,8 @@ struct Handle {
   size_t size_calculated_with_n = (size_t)-1;
   size_t n_alive_last = 0; // m_alive_indices.size()
   bool grid_forced = false;
+  bool windowed = false; // slab window along dim 0 (abr_domain_set_window)
+  int win_lo = 0, win_n = 0, own_lo = 0, own_n = 0;
 
   // --- device state ---------------------------------------------------------
   DevBuf keys[2], idx[2], tile_hist, scan_tmp;
@@ -95,7 +99,7 @@ struct ReorderSpec {
   const size_t *elem_bytes;
 };
 int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *order_out,
-                   size_t *n_alive_host, const ReorderSpec *reorder);
+                   size_t *n_alive_host, const ReorderSpec *reorder, bool presorted = false);
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
                    const size_t *elem_bytes, const int32_t *order, size_t n_out, const uint32_t *n_dev);
 

@@ -177,7 +177,9 @@ class Particles:
     def get_query(self):
         return Query(self)
 
-    def _bucket_view(self):
+    def _bucket_view(self, clone=True):
+        """(bucket_indices, bucket_begin, bucket_end) as int32 device tensors;
+        clone=False returns views borrowed from the handle (valid until the next build)"""
         ki, bb, be = C.c_void_p(), C.c_void_p(), C.c_void_p()
         nb = C.c_uint64()
         check(self._h, self._lib.abr_celllist_get(self._h, C.byref(ki), C.byref(bb), C.byref(be), C.byref(nb)))
@@ -188,7 +190,8 @@ class Particles:
         def view(ptr, count):
             if count == 0 or not ptr.value:
                 return torch.empty(0, dtype=torch.int32, device=self.device)
-            return torch.as_tensor(_DevArray(ptr.value, count, "<i4"), device=self.device).clone()
+            t = torch.as_tensor(_DevArray(ptr.value, count, "<i4"), device=self.device)
+            return t.clone() if clone else t
 
         return view(ki, n), view(bb, nb.value), view(be, nb.value)
 

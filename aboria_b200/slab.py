@@ -1,0 +1,342 @@
+"""Multi-GPU slab decomposition with halo exchange.
+
+The reference is single process; this is the one parallel strategy the build
+adds.  The domain is cut into slabs of bucket LAYERS along dimension 0 —
+`collapse_index_vector` makes dimension 0 the slowest index
+(src/detail/SpatialUtil.h:49-59), so a slab is a contiguous range of global
+bucket numbers AND of the globally sorted particle array: concatenating the
+owned ranges of all ranks reproduces the single-GPU cell list exactly.
+
+One process per GPU.  The only data-path communication is with the two slab
+neighbours (torch.distributed P2P: NCCL over NVLink on GPUs, gloo in the CPU
+tests): halo layers of the sorted columns once per build, halo entries of `b`
+once per product.  No global reduction: every row of y is owned by one rank.
+
+  SlabExchange   pure torch + torch.distributed plumbing (device agnostic;
+                 covered by the world_size-2 gloo tests)
+  SlabParticles  a rank's particles on its GPU: owned build -> halo exchange ->
+                 adopt the sorted [ghost_lo | owned | ghost_hi] set (libabr.so)
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def plan_layers(n_layers, world):
+    """balanced contiguous split of the bucket layers of dimension 0"""
+    base, rem = divmod(n_layers, world)
+    out, lo = [], 0
+    for g in range(world):
+        hi = lo + base + (1 if g < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def halo_width(radius, side0):
+    """bucket layers a row can reach: ceil(r / side) with the same rounding
+    guard as the tiled kernel (aboria_b200/csrc/abr_matvec.cu)"""
+    return max(1, int(math.ceil(radius / side0 - 1e-9)))
+
+
+class SlabExchange:
+    """Halo plumbing for one rank.
+
+    layer_offsets: (own_n + 1,) int64 CPU tensor — offsets of the owned bucket
+    layers inside the rank's SORTED owned arrays (layer l = rows
+    layer_offsets[l] .. layer_offsets[l+1])."""
+
+    def __init__(self, rank, world, periodic0, w, layer_offsets, group=None):
+        self.rank, self.world, self.w, self.group = rank, world, w, group
+        lo = layer_offsets.tolist()
+        own_n = len(lo) - 1
+        if own_n < w:
+            raise ValueError(f"rank {rank}: owns {own_n} bucket layers, fewer than the halo width {w}: replicas only (SURVEY §8e)")
+        self.n_own = lo[-1]
+        self.lower = (rank - 1) % world if (periodic0 or rank > 0) else None
+        self.upper = (rank + 1) % world if (periodic0 or rank < world - 1) else None
+        # rows of my first / last w owned layers (what the neighbours need)
+        self.send_lo = (0, lo[w])
+        self.send_hi = (lo[own_n - w], lo[own_n])
+        # sizes of the ghost ranges: exchanged once (tiny)
+        counts = torch.tensor([self.send_lo[1] - self.send_lo[0], self.send_hi[1] - self.send_hi[0]], dtype=torch.int64)
+        self.n_ghost_lo, self.n_ghost_hi = self._exchange_counts(counts)
+        self.own_begin = self.n_ghost_lo
+        self.own_end = self.n_ghost_lo + self.n_own
+        self.n_local = self.own_end + self.n_ghost_hi
+
+    def _dev(self):
+        return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+
+    def _exchange_counts(self, counts):
+        dev = self._dev()
+        mine = counts.to(dev)
+        from_lower = torch.zeros(1, dtype=torch.int64, device=dev)
+        from_upper = torch.zeros(1, dtype=torch.int64, device=dev)
+        ops = []
+        # order matters when lower == upper (world == 2): sends lo, hi; receives hi-ghost, lo-ghost
+        if self.lower is not None:
+            ops.append(dist.P2POp(dist.isend, mine[0:1], self.lower, self.group))
+        if self.upper is not None:
+            ops.append(dist.P2POp(dist.isend, mine[1:2], self.upper, self.group))
+        if self.upper is not None:
+            ops.append(dist.P2POp(dist.irecv, from_upper, self.upper, self.group))
+        if self.lower is not None:
+            ops.append(dist.P2POp(dist.irecv, from_lower, self.lower, self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return int(from_lower.item()), int(from_upper.item())
+
+    def _halo_ops(self, send_from, recv_into):
+        """send_from(which) -> contiguous tensor slice to send; recv_into(which) -> slice to fill"""
+        ops = []
+        if self.lower is not None and self.send_lo[1] > self.send_lo[0]:
+            ops.append(dist.P2POp(dist.isend, send_from("lo"), self.lower, self.group))
+        if self.upper is not None and self.send_hi[1] > self.send_hi[0]:
+            ops.append(dist.P2POp(dist.isend, send_from("hi"), self.upper, self.group))
+        if self.upper is not None and self.n_ghost_hi > 0:
+            ops.append(dist.P2POp(dist.irecv, recv_into("hi"), self.upper, self.group))
+        if self.lower is not None and self.n_ghost_lo > 0:
+            ops.append(dist.P2POp(dist.irecv, recv_into("lo"), self.lower, self.group))
+        return ops
+
+    def assemble(self, owned_sorted):
+        """[ghost_lo | owned | ghost_hi] for one sorted owned column (any dtype,
+        leading dimension = particles).  Ghost rows keep the sender's coordinates:
+        the periodic image is applied by the search (cur = r + image*L,
+        src/Search.h:188-190), never by moving a particle."""
+        out = torch.empty((self.n_local,) + tuple(owned_sorted.shape[1:]), dtype=owned_sorted.dtype, device=owned_sorted.device)
+        out[self.own_begin:self.own_end].copy_(owned_sorted)
+        self.fill_halo(out)
+        return out
+
+    def fill_halo(self, local):
+        """refresh the ghost ranges of a local column from the neighbours' owned
+        ranges (used for b before every product)"""
+        ob = self.own_begin
+
+        def send_from(which):
+            a, b = self.send_lo if which == "lo" else self.send_hi
+            return local[ob + a: ob + b]
+
+        def recv_into(which):
+            return local[: self.n_ghost_lo] if which == "lo" else local[self.own_end:]
+
+        ops = self._halo_ops(send_from, recv_into)
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return local
+
+    def halo_bytes(self, row_bytes):
+        return (self.n_ghost_lo + self.n_ghost_hi) * row_bytes
+
+
+class SlabParticles:
+    """One rank's share of a slab-decomposed particle set on its GPU."""
+
+    def __init__(self, D, low, high, periodic, n_total, n_leaf, radius, rank, world, device, group=None):
+        from . import _lib
+        from .particles import Particles
+
+        if D < 2:
+            raise ValueError("slabs need D >= 2")
+        self.D, self.rank, self.world, self.device, self.group = D, rank, world, device, group
+        self.low = np.ascontiguousarray(np.broadcast_to(np.asarray(low, dtype=np.float64), (D,)))
+        self.high = np.ascontiguousarray(np.broadcast_to(np.asarray(high, dtype=np.float64), (D,)))
+        self.periodic = np.ascontiguousarray(np.broadcast_to(np.asarray(periodic), (D,)).astype(np.uint8))
+        self.radius = float(radius)
+        L = _lib.lib()
+        size = np.zeros(D, dtype=np.uint32)
+        side = np.zeros(D, dtype=np.float64)
+        rc = L.abr_grid_for(D, self.low.ctypes.data, self.high.ctypes.data, float(n_leaf), int(n_total), size.ctypes.data, side.ctypes.data)
+        if rc:
+            raise RuntimeError("abr_grid_for failed")
+        self.size, self.side = size, side
+        self.layers = plan_layers(int(size[0]), world)
+        self.lo_layer, self.hi_layer = self.layers[rank]
+        self.own_n = self.hi_layer - self.lo_layer
+        self.w = halo_width(self.radius, float(side[0]))
+        if bool(self.periodic[0]) and self.own_n + 2 * self.w > int(size[0]):
+            raise ValueError("slab window would wrap onto itself: replicas only (SURVEY §8e)")
+        self.p = Particles(D, 0, device=device)
+        self.per_layer = int(np.prod(size[1:], dtype=np.int64))
+        self.ex = None
+
+    def slab_bounds(self):
+        """[x_lo, x_hi) of this rank's slab in dimension 0"""
+        s = float(self.side[0])
+        return float(self.low[0]) + self.lo_layer * s, float(self.low[0]) + self.hi_layer * s
+
+    def _force(self, win_lo, win_n, own_lo, own_n):
+        from ._lib import check
+
+        p = self.p
+        check(p._h, p._lib.abr_domain_force_grid(p._h, self.D, self.low.ctypes.data, self.high.ctypes.data, self.periodic.ctypes.data, self.size.ctypes.data))
+        check(p._h, p._lib.abr_domain_set_window(p._h, win_lo, win_n, own_lo, own_n))
+
+    def build(self, pos_owned_unsorted, extra_columns=None):
+        """owned build (window = owned layers) -> halo exchange of the sorted
+        columns -> adopt the sorted local set (window = owned + 2w ghost layers)."""
+        from ._lib import check
+
+        p = self.p
+        p.resize_from_positions(pos_owned_unsorted)
+        for k, v in (extra_columns or {}).items():
+            p.columns[k] = v
+        p.low, p.high, p.periodic = self.low, self.high, self.periodic
+        # stage A: sort the owned particles into their (global-grid) buckets
+        self._force(self.lo_layer, self.own_n, 0, self.own_n)
+        n_own = p.update_positions()
+        if n_own != pos_owned_unsorted.shape[0]:
+            raise RuntimeError("slab build: particles died during the owned build")
+        bb = p._bucket_view(clone=False)[1]
+        layer_first = bb[:: self.per_layer].long().cpu()
+        layer_offsets = torch.cat([layer_first, torch.tensor([n_own], dtype=torch.int64)])
+        # stage B: halo layers of every sorted column
+        self.ex = SlabExchange(self.rank, self.world, bool(self.periodic[0]), self.w, layer_offsets, self.group)
+        ex = self.ex
+        self.order_owned = p.get_alive_indicies()
+        cols = {k: ex.assemble(v) for k, v in p.columns.items()}
+        p.columns = cols
+        # stage C: bucket ranges of the sorted local set
+        has_lo = ex.lower is not None
+        has_hi = ex.upper is not None
+        win_lo = self.lo_layer - (self.w if has_lo else 0)
+        win_n = self.own_n + (self.w if has_lo else 0) + (self.w if has_hi else 0)
+        self._force(win_lo, win_n, self.w if has_lo else 0, self.own_n)
+        p._sync_stream()
+        pos = p.columns["position"]
+        alive = p.columns["alive"]
+        check(p._h, p._lib.abr_celllist_adopt_sorted(p._h, C.c_void_p(pos.data_ptr()), C.c_void_p(alive.data_ptr()), pos.shape[0]))
+        p.searchable = True
+        return ex.n_local
+
+    def owned(self, local):
+        return local[self.ex.own_begin: self.ex.own_end]
+
+    def local_vector(self, owned_values):
+        """place owned values into a local (ghost-padded) vector"""
+        v = torch.zeros((self.ex.n_local,) + tuple(owned_values.shape[1:]), dtype=owned_values.dtype, device=owned_values.device)
+        v[self.ex.own_begin: self.ex.own_end] = owned_values
+        return v
+
+    def matvec(self, op, b_local):
+        """y_owned = (K b)_owned: halo exchange of b, then the local product"""
+        self.ex.fill_halo(b_local)
+        y = op.matvec(b_local)
+        return y
+
+
+def run_bench(args, rank, world, dev, metric, unit):
+    """bench.py body for N > 1 (weak scaling: args.n_per_gpu particles per GPU
+    in the periodic unit cube, slabs along dimension 0)."""
+    import json
+    import os
+    import sys
+
+    import aboria_b200 as ab
+    from aboria_b200 import kernels as K
+    from aboria_b200 import synth
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import EPS, N_LEAF, ClockSampler
+
+    n_total = args.n_per_gpu * world
+    box_side = (N_LEAF / float(n_total)) ** (1.0 / 3.0)
+    size = int(np.floor(1.0 / box_side))
+    side = 1.0 / size
+    radius = side
+    sp = SlabParticles(3, 0.0, 1.0, True, n_total, N_LEAF, radius, rank, world, dev)
+    # this rank's particles: uniform in its slab, share proportional to its layer count
+    shares = [int(round(n_total * (hi - lo) / size)) for lo, hi in sp.layers]
+    shares[-1] = n_total - sum(shares[:-1])
+    n_mine, first_id = shares[rank], sum(shares[:rank])
+    x_lo, x_hi = sp.slab_bounds()
+    pos_unsorted = synth.torch_uniform_positions(n_mine, 3, [x_lo, 0.0, 0.0], [x_hi, 1.0, 1.0], synth.SEED, first_id, dev)
+    b_owned = torch.from_numpy(synth.vector(n_mine, first_id=first_id)).to(dev)
+    op = ab.create_sparse_operator(sp.p, sp.p, radius, K.inv_dist(EPS))
+
+    def step():
+        sp.build(pos_unsorted.clone())
+        # b follows the particles: gather by the owned sort order, pad with ghosts
+        b_local = sp.local_vector(b_owned[sp.order_owned.long()])
+        return sp.matvec(op, b_local)
+
+    step()
+    cnt, _ = sp.p.pair_stats(radius)
+    pairs_t = sp.owned(cnt).long().sum()
+    dist.all_reduce(pairs_t)
+    pairs = int(pairs_t.item())
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+    torch.cuda.synchronize()
+    launches0 = sp.p.last_counters()["total_launches"]
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_local = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.barrier()
+    dist.all_reduce(ms_local, op=dist.ReduceOp.MAX)  # max over ranks
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sp.p.last_counters()["total_launches"] - launches0
+    ms_per_step = float(ms_local.item()) / args.steps
+    value = pairs / (ms_per_step * 1e-3)
+
+    # end-to-end with host buffers: H2D of positions and b, D2H of y, every step
+    pos_host = torch.empty((n_mine, 3), dtype=torch.float64, pin_memory=True)
+    pos_host.copy_(pos_unsorted)
+    b_host = torch.empty(n_mine, dtype=torch.float64, pin_memory=True)
+    b_host.copy_(b_owned)
+    y_host = torch.empty(n_mine, dtype=torch.float64, pin_memory=True)
+
+    def e2e_step():
+        sp.build(pos_host.to(dev, non_blocking=True))
+        b_dev = b_host.to(dev, non_blocking=True)
+        b_local = sp.local_vector(b_dev[sp.order_owned.long()])
+        y = sp.matvec(op, b_local)
+        y_host.copy_(sp.owned(y))
+
+    import time
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_sec = float(t_e2e.item()) / e2e_steps
+    halo = torch.tensor([float(sp.ex.n_ghost_lo + sp.ex.n_ghost_hi)], dtype=torch.float64, device=dev)
+    dist.all_reduce(halo)
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c5-weak: 3-D periodic unit cube, uniform random, n_leaf=10, r=bucket side, kernel 1/(|dx|+0.1), fp64; slabs along dim 0, NCCL halo exchange",
+                       "n_particles_per_gpu": args.n_per_gpu, "n_particles": n_total, "buckets": size ** 3, "radius": radius, "pairs_per_matvec": pairs,
+                       "halo_particles_total": int(halo.item()), "parallelism": f"slab{world}",
+                       "l2": "inputs exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": pairs / e2e_sec, "unit": unit, "h2d_bytes_per_step": int(n_mine * 32 * world), "d2h_bytes_per_step": int(n_mine * 8 * world),
+                    "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps},
+            "gpu_launches": int(launches) * world, "clocks": clocks,
+            "roofline": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()

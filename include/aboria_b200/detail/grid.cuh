@@ -26,9 +26,33 @@ struct Grid {
   double side[MAXD];      // m_bucket_side_length
   double inv_side[MAXD];  // 1.0 / side (src/detail/SpatialUtil.h:116)
   double L[MAXD];         // bmax - bmin (one rounding, as in Search.h:188-190)
-  uint32_t ncells;        // m_size.prod()
+  uint32_t ncells;        // number of buckets stored locally (= m_size.prod() without a window)
   uint32_t key_bound;     // keys of alive particles are < key_bound; dead = key_bound
+  // Slab window along dimension 0 (multi-GPU).  The arithmetic above
+  // always uses the GLOBAL grid; a rank stores only the bucket layers
+  // win_lo .. win_lo+win_n-1 (unwrapped, may run past either end of a periodic
+  // dimension) and computes rows only for its own layers own_lo .. own_lo+own_n-1
+  // (local numbering).  Single GPU: win_lo = 0, win_n = size[0], own everything.
+  int win_lo, win_n, own_lo, own_n;
 };
+
+// global layer index (dimension 0) -> local layer, or -1 when not stored here
+__host__ __device__ inline int local_layer(const Grid &g, int v0) {
+  int l = v0 - g.win_lo;
+  if (l < 0) l += g.size[0];
+  if (l >= g.size[0]) l -= g.size[0];
+  return (l >= 0 && l < g.win_n) ? l : -1;
+}
+
+// collapse a GLOBAL bucket index vector to the LOCAL bucket number (-1: not stored)
+template <int D> __host__ __device__ inline int local_collapse(const Grid &g, const int *v) {
+  const int l = local_layer(g, v[0]);
+  if (l < 0) return -1;
+  int index = l;
+#pragma unroll
+  for (int i = 1; i < D; ++i) index = index * g.size[i] + v[i];
+  return index;
+}
 
 struct Query {
   Grid g;
@@ -194,7 +218,9 @@ __device__ inline void search_walk(const Query &q, const double *r, double R, Vi
 #pragma unroll
     for (int i = 0; i < D; ++i) cur[i] = r[i] + (double)img[i] * g.L[i];
     for (BucketWalk<D> b(g, cur, R2); b.valid; b.increment()) {
-      const unsigned c = (unsigned)collapse_index<D>(g, b.index);
+      const int cl = local_collapse<D>(g, b.index);
+      if (cl < 0) continue; // bucket layer held by another rank (never within reach of an owned row)
+      const unsigned c = (unsigned)cl;
       const unsigned jb = q.bucket_begin[c], je = q.bucket_end[c];
       for (unsigned j = jb; j < je; ++j) {
         double dx[D];

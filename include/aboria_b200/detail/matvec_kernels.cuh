@@ -280,6 +280,12 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
 #pragma unroll
   for (int d = 0; d < D; ++d) img0[d] = 0;
   const uint32_t image_id0 = STATS ? (uint32_t)image_linear_index<D>(g, img0) : 0u;
+  // buckets of the bucket layers this rank owns (all of them on a single GPU)
+  uint32_t per_layer = 1;
+#pragma unroll
+  for (int d = 1; d < D; ++d) per_layer *= (uint32_t)g.size[d];
+  const uint32_t first_cell = (D > 1 ? (uint32_t)g.own_lo * per_layer : 0u);
+  const uint32_t own_cells = (D > 1 ? (uint32_t)g.own_n * per_layer : g.ncells);
   const DrainCtx dc{p.q.pos, p.b, p.r2lo};
   const double R2 = p.r2;
 
@@ -288,10 +294,10 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
     uint32_t grab = 0;
     if (lane == 0) grab = atomicAdd(p.work_counter, TILED_GRAB);
     grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
-    if (grab >= g.ncells) break;
-    const uint32_t grab_end = min(grab + TILED_GRAB, g.ncells);
+    if (grab >= own_cells) break;
+    const uint32_t grab_end = min(grab + TILED_GRAB, own_cells);
 
-    for (uint32_t cell = grab; cell < grab_end; ++cell) {
+    for (uint32_t cell = first_cell + grab; cell < first_cell + grab_end; ++cell) {
       const uint32_t rb = bbeg[cell], re = bend[cell];
       if (rb == re) continue;
       // bucket coordinates of the target (inverse of collapse_index)
@@ -302,6 +308,12 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
         for (int d = D - 1; d >= 0; --d) {
           tc[d] = (int)(rem % (uint32_t)g.size[d]);
           rem /= (uint32_t)g.size[d];
+        }
+        if (D > 1) { // local layer -> global layer (slab window; identity on a single GPU)
+          int gl = g.win_lo + (int)(cell / per_layer);
+          if (gl < 0) gl += g.size[0];
+          if (gl >= g.size[0]) gl -= g.size[0];
+          tc[0] = gl;
         }
       }
       const int zlo = tc[L] - p.w[L], zhi = tc[L] + p.w[L];
@@ -355,9 +367,11 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
             const int a = max(zlo, 0), bnd = min(zhi, S - 1);
             if (ok && a <= bnd) {
               nc[L] = a;
-              const uint32_t c_lo = (uint32_t)collapse_index<D>(g, nc);
-              jb = bbeg[c_lo];
-              len = bend[c_lo + (uint32_t)(bnd - a)] - jb;
+              const int c_lo = local_collapse<D>(g, nc);
+              if (c_lo >= 0) {
+                jb = bbeg[c_lo];
+                len = bend[c_lo + (bnd - a)] - jb;
+              }
             }
           }
           uint32_t pin = len;
@@ -431,8 +445,9 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
                 if (a > bnd) continue;
                 img[L] = -m;
                 nc[L] = a - m * S;
-                const uint32_t c_lo = (uint32_t)collapse_index<D>(g, nc);
-                const uint32_t jb = bbeg[c_lo], je = bend[c_lo + (uint32_t)(bnd - a)];
+                const int c_lo = local_collapse<D>(g, nc);
+                if (c_lo < 0) continue;
+                const uint32_t jb = bbeg[c_lo], je = bend[c_lo + (bnd - a)];
                 if (jb >= je) continue;
                 __syncwarp();
                 if (lane < nr) {

@@ -95,6 +95,27 @@ int abr_domain_get(abr_handle h, uint32_t *size_host, double *side_host, uint64_
 int abr_domain_force_grid(abr_handle h, int D, const double *bmin_host, const double *bmax_host,
                           const uint8_t *periodic_host, const uint32_t *size_host);
 
+/* The grid CellListOrdered::set_domain_impl would choose for n particles
+ * (src/CellListOrdered.h:140-157), as a pure host function. */
+int abr_grid_for(int D, const double *bmin_host, const double *bmax_host, double n_particles_in_leaf,
+                 size_t n, uint32_t *size_host, double *side_host);
+
+/* Multi-GPU slabs (no counterpart in the single-process
+ * reference).  After abr_domain_force_grid with the GLOBAL grid, restrict this
+ * handle to the bucket layers win_lo .. win_lo+win_n-1 of dimension 0
+ * (unwrapped numbering: a window of a periodic dimension may start below 0 or
+ * end past size[0]); rows are computed for the local layers own_lo ..
+ * own_lo+own_n-1 only (the others are ghost layers received from neighbours).
+ * All bucket/key arithmetic stays that of the global grid, so concatenating
+ * the owned ranges of all ranks reproduces the single-GPU cell list exactly. */
+int abr_domain_set_window(abr_handle h, int win_lo, int win_n, int own_lo, int own_n);
+
+/* Adopt a particle set that is ALREADY sorted by (local) bucket — a rank's
+ * [ghost_lo | owned | ghost_hi] concatenation after the halo exchange:
+ * computes keys and the bucket ranges, checks sortedness, binds the query.
+ * No permutation, no reorder. */
+int abr_celllist_adopt_sorted(abr_handle h, double *pos_sorted, uint8_t *alive, size_t n);
+
 /* neighbour_search_base::update_positions (src/NeighbourSearchBase.h:350-495)
  * for the ordered case + CellListOrdered::update_positions_impl
  * (src/CellListOrdered.h:190-259):
