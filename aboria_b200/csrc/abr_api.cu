@@ -55,10 +55,6 @@ int abr_create(abr_handle *out, int device, void *stream) {
     return ABR_ERR_CUDA;
   }
   cudaMemset(h->d_scalars, 0, sizeof(abr::DevScalars));
-  // the reorder is a random gather of 1..104-byte elements: ask L2 to fetch 32-byte
-  // sectors from HBM instead of the default 64 (a hint; measured in profiles/)
-  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-  cudaGetLastError();
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
   for (int d = 0; d < abr::MAXD; ++d) {

@@ -403,7 +403,7 @@ k_gather_words(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
   const uint32_t cnt = (uint32_t)min((uint64_t)256, n_out - k0);
   if (threadIdx.x < cnt) {
     const uint64_t *e = src + (uint64_t)order[k0 + threadIdx.x] * words;
-    for (uint32_t w = 0; w < words; ++w) s_stage[threadIdx.x * words + w] = __ldcs(e + w);
+    for (uint32_t w = 0; w < words; ++w) s_stage[threadIdx.x * words + w] = __ldg(e + w); // plain nc load: .cs/.no_allocate fetch MORE from HBM (tools/gather_probe.cu)
   }
   __syncthreads();
   const uint32_t total = cnt * words;
