@@ -69,6 +69,21 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p)
       stencil *= (2.0 * p->w[d] + 1.0);
     }
     if (stencil > 8192.0) tiled = false; // radius >> bucket side: the walk is the better kernel
+    if (tiled) {
+      // fp32 pre-filter: coordinates relative to the stencil origin have magnitude
+      // M <= (2w+2) side (+ slack); |dx| is known to ~2 ulp32(M) per component, so the
+      // relative error of the fp32 |dx|^2 near the cut-off is <= 2 D * 2^-22 * M / R plus a
+      // few ulp32 of arithmetic.  An 8x safety factor on top; tests compare pair-set
+      // hashes with the oracle.
+      double M = 0;
+      for (int d = 0; d < D; ++d) M = std::fmax(M, (2.0 * p->w[d] + 2.0) * h->side[d]);
+      const double tol = 8.0 * (2.0 * D * std::ldexp(1.0, -22) * M / R + std::ldexp(1.0, -20));
+      double pr = p->r2 * (1.0 + tol);
+      float prf = (float)pr;
+      if ((double)prf < pr) prf = std::nextafterf(prf, INFINITY);
+      if (!(prf < 1.0e30f) || !(p->r2 > 1e-30)) tiled = false; // out of comfortable fp32 range
+      p->pre_r2 = prf;
+    }
     if (!tiled && c.force_path == 0)
       return set_error(h, ABR_ERR_INVALID, "tiled path not applicable for this radius / grid");
   }

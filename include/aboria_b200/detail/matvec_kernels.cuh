@@ -47,6 +47,7 @@ struct abr_matvec_plan {
   int use_tiled;
   int w[abr::MAXD];        // stencil half width per dimension
   double r2, r2lo;         // cut-off^2 and the "rounding sensitive" lower edge
+  float pre_r2;            // fp32 pre-filter threshold: r2 * (1 + tol), never rejects a pair the exact test accepts
   double tolf[abr::MAXD];  // fractional bucket coordinate tolerance
   uint32_t *work_counter;
   uint32_t *danger_count;
@@ -149,6 +150,7 @@ template <int D, class F, bool STATS> struct WarpSmem {
   static constexpr int RB = TiledCfg<D, F, STATS>::RB;
   double rows0[RB][4];                    // rows of the batch (x,y,z,pad)
   double rowsS[RB][4];                    // rows shifted by a periodic image
+  float rowsf[RB + 2][4];                 // rows relative to the bucket-stencil origin, fp32 (pre-filter); padded with far-away dummies
   unsigned long long part[NACC][RB][32];  // partial sums [row][lane]
   uint32_t lq[32][QSTRIDE];               // lane-private accepted-pair queues: (j << ROW_BITS) | row
   uint32_t run_pref[32];                  // candidate-run directory: inclusive prefix of run lengths
@@ -169,6 +171,7 @@ struct DrainCtx {
   const double *pos;
   const double *b;
   double r2lo;
+  double r2;
 };
 
 template <int D, class F, bool STATS, class SM>
@@ -187,7 +190,8 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
   __syncwarp();
   for (uint32_t base = 0; base < total; base += 32) {
     const uint32_t k = base + lane;
-    if (k < total) {
+    if (k >= total) continue;
+    {
       uint32_t o = 0;
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1)
@@ -202,6 +206,9 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
         dx[d] = p.pos[(size_t)j * D + d] - rowp[i][d];
         d2 = d2 + dx[d] * dx[d];
       }
+      // the queue holds the survivors of the conservative fp32 pre-filter; this is
+      // the reference's exact predicate (src/Search.h:438-446)
+      if (d2 > p.r2) continue;
       if (d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
       if (STATS) {
         sm.part[0][i][lane] += 1ull;
@@ -224,33 +231,45 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
 }
 
 // One step of the hot loop: this lane's TWO candidates (jA, jB) against the nr
-// rows of the batch, two rows at a time (one shared-memory row fetch feeds two
-// tests).  Exact un-fused predicate; an accepted pair costs one predicated
-// store into the lane's own queue.
+// rows of the batch, two rows at a time.  This is a conservative fp32
+// PRE-FILTER on coordinates relative to the stencil origin: a pair survives if
+// |dx|^2 <= r^2 (1 + tol) in fp32, tol chosen on the host so that no pair the
+// exact fp64 test accepts is ever dropped.  Survivors cost one predicated
+// 4-byte store into the lane's own queue; the exact un-fused fp64 predicate is
+// applied to them in drain_queues.  (The fp64 pipe is the scarce resource:
+// 6.45 candidates are tested per accepted pair.)
 template <int D, class F, bool STATS, class SM>
-__device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, double R2, const F &f, int lane, const double *pA,
-                                          const double *pB, uint32_t jA, uint32_t jB, bool vA, bool vB, int nr,
-                                          const double (*rowp)[4], uint32_t image_id, uint32_t r0, uint32_t &cnt) {
+__device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_r2, const F &f, int lane,
+                                          const float *pA, const float *pB, uint32_t jA, uint32_t jB, bool vA, bool vB,
+                                          int nr, const double (*rowp)[4], uint32_t image_id, uint32_t r0,
+                                          uint32_t &cnt) {
   uint32_t *myq = sm.lq[lane];
-  const uint32_t eA = jA << ROW_BITS, eB = jB << ROW_BITS;
-  for (int i = 0; i < nr; i += 2) {
-    const bool second = i + 1 < nr; // odd tail: the second row of the pair is masked
-    const int i1 = second ? i + 1 : i;
-    double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+  // invalid candidates are parked far away instead of being predicated out
+  float a[D], b[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    a[d] = vA ? pA[d] : -3.0e18f;
+    b[d] = vB ? pB[d] : -3.0e18f;
+  }
+  uint32_t eA = jA << ROW_BITS, eB = jB << ROW_BITS;
+  for (int i = 0; i < nr; i += 2) { // rowsf is padded with a dummy row: an odd tail needs no special case
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      const double r0d = rowp[i][d], r1d = rowp[i1][d];
-      const double ta0 = pA[d] - r0d, ta1 = pA[d] - r1d;
-      const double tb0 = pB[d] - r0d, tb1 = pB[d] - r1d;
-      a0 = a0 + ta0 * ta0;
-      a1 = a1 + ta1 * ta1;
-      b0 = b0 + tb0 * tb0;
-      b1 = b1 + tb1 * tb1;
+      const float r0d = sm.rowsf[i][d], r1d = sm.rowsf[i + 1][d];
+      const float ta0 = a[d] - r0d, ta1 = a[d] - r1d;
+      const float tb0 = b[d] - r0d, tb1 = b[d] - r1d;
+      a0 = fmaf(ta0, ta0, a0);
+      a1 = fmaf(ta1, ta1, a1);
+      b0 = fmaf(tb0, tb0, b0);
+      b1 = fmaf(tb1, tb1, b1);
     }
-    if (vA && !(a0 > R2)) myq[cnt++] = eA | (uint32_t)i;
-    if (vA && second && !(a1 > R2)) myq[cnt++] = eA | (uint32_t)i1;
-    if (vB && !(b0 > R2)) myq[cnt++] = eB | (uint32_t)i;
-    if (vB && second && !(b1 > R2)) myq[cnt++] = eB | (uint32_t)i1;
+    if (a0 <= pre_r2) myq[cnt++] = eA;
+    if (a1 <= pre_r2) myq[cnt++] = eA + 1u;
+    if (b0 <= pre_r2) myq[cnt++] = eB;
+    if (b1 <= pre_r2) myq[cnt++] = eB + 1u;
+    eA += 2u;
+    eB += 2u;
     if (__any_sync(0xFFFFFFFFu, cnt >= (uint32_t)QDRAIN)) {
       drain_queues<D, F, STATS>(sm, dc, f, lane, cnt, r0, rowp, image_id);
       cnt = 0;
@@ -286,8 +305,8 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
   for (int d = 1; d < D; ++d) per_layer *= (uint32_t)g.size[d];
   const uint32_t first_cell = (D > 1 ? (uint32_t)g.own_lo * per_layer : 0u);
   const uint32_t own_cells = (D > 1 ? (uint32_t)g.own_n * per_layer : g.ncells);
-  const DrainCtx dc{p.q.pos, p.b, p.r2lo};
-  const double R2 = p.r2;
+  const DrainCtx dc{p.q.pos, p.b, p.r2lo, p.r2};
+  const float pre_r2 = p.pre_r2;
 
   while (true) {
     // warp-level dynamic scheduler: no block barrier anywhere in this kernel
@@ -323,6 +342,11 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
 #pragma unroll
       for (int d = 0; d < D - 1; ++d) boundary |= (tc[d] - p.w[d] < 0) | (tc[d] + p.w[d] >= g.size[d]);
 
+      // origin of the fp32 pre-filter coordinates: lower corner of the stencil
+      double origin[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) origin[d] = g.bmin[d] + (double)(tc[d] - p.w[d]) * g.side[d];
+
       for (uint32_t r0 = rb; r0 < re; r0 += RB) {
         const int nr = (int)min((uint32_t)RB, re - r0);
         // ---- load the rows of this batch, flag rounding-sensitive ones ----
@@ -340,6 +364,13 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
           }
         }
         if (lane == 0) sm.danger = 0;
+        if (lane < RB + 2) {
+          // fp32 copy relative to the stencil origin (lower corner of the first neighbour
+          // bucket); rows >= nr are dummies far away from everything
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+            sm.rowsf[lane][d] = lane < nr ? (float)(sm.rows0[lane][d] - origin[d]) : 3.0e18f;
+        }
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
           for (int i = 0; i < nr; ++i) sm.part[a][i][lane] = 0ull;
@@ -389,7 +420,7 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
             // two candidates per lane: k and k + 32
             uint32_t jj[2];
             bool vv[2];
-            double pj[2][D];
+            float pj[2][D];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint32_t k = kb + 32 * h + lane;
@@ -401,9 +432,9 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
                 if (sm.run_pref[rho + step - 1] <= ks) rho += step;
               jj[h] = ks + sm.run_delta[rho];
 #pragma unroll
-              for (int d = 0; d < D; ++d) pj[h][d] = pos[(size_t)jj[h] * D + d];
+              for (int d = 0; d < D; ++d) pj[h][d] = (float)(pos[(size_t)jj[h] * D + d] - origin[d]);
             }
-            test_rows<D, F, STATS>(sm, dc, R2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
+            test_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
                                    image_id0, r0, cnt);
           }
         }
@@ -459,15 +490,17 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
                 for (uint32_t cb = jb; cb < je; cb += 64) {
                   uint32_t jj[2];
                   bool vv[2];
-                  double pj[2][D];
+                  float pj[2][D];
 #pragma unroll
                   for (int h = 0; h < 2; ++h) {
                     jj[h] = min(cb + 32 * h + lane, je - 1);
                     vv[h] = cb + 32 * h + lane < je;
+                    // pre-filter only: move the candidate by -image*L instead of the row by +image*L
 #pragma unroll
-                    for (int d = 0; d < D; ++d) pj[h][d] = pos[(size_t)jj[h] * D + d];
+                    for (int d = 0; d < D; ++d)
+                      pj[h][d] = (float)((pos[(size_t)jj[h] * D + d] - (double)img[d] * g.L[d]) - origin[d]);
                   }
-                  test_rows<D, F, STATS>(sm, dc, R2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
+                  test_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
                                          image_id, r0, cnt);
                 }
                 // leave no pair of this image in the queues (rowsS is reused)
