@@ -178,6 +178,7 @@ template <int D, class F, bool STATS, class SM>
 __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, int lane, uint32_t cnt, uint32_t r0,
                                           const double (*rowp)[4], uint32_t image_id) {
   constexpr int BR = F::BR, BC = F::BC;
+  constexpr int U = 1; // pairs per lane per round (U = 2 was measured: no gain, costs a CTA of occupancy)
   uint32_t pin = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -188,41 +189,69 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
   __syncwarp();
   sm.dq_pref[lane] = pin;
   __syncwarp();
-  for (uint32_t base = 0; base < total; base += 32) {
-    const uint32_t k = base + lane;
-    if (k >= total) continue;
-    {
+  for (uint32_t base = 0; base < total; base += 32 * U) {
+    bool live[U];
+    uint32_t j[U], i[U];
+    // deal the queued pairs out evenly: pair k belongs to the lane `o` with
+    // dq_pref[o-1] <= k < dq_pref[o]
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t k = base + 32 * u + lane;
+      live[u] = k < total;
+      const uint32_t ks = live[u] ? k : total - 1;
       uint32_t o = 0;
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1)
-        if (sm.dq_pref[o + step - 1] <= k) o += step;
-      const uint32_t local = k - (o ? sm.dq_pref[o - 1] : 0u);
+        if (sm.dq_pref[o + step - 1] <= ks) o += step;
+      const uint32_t local = ks - (o ? sm.dq_pref[o - 1] : 0u);
       const uint32_t ent = sm.lq[o][local];
-      const uint32_t j = ent >> ROW_BITS, i = ent & ((1u << ROW_BITS) - 1u);
+      j[u] = ent >> ROW_BITS;
+      i[u] = ent & ((1u << ROW_BITS) - 1u);
+    }
+    // all global loads first
+    double pj[U][D], bj[U][BC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) pj[u][d] = p.pos[(size_t)j[u] * D + d];
+      if (!STATS) {
+#pragma unroll
+        for (int c = 0; c < BC; ++c) bj[u][c] = p.b[(size_t)j[u] * BC + c];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       double dx[D];
       double d2 = 0;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        dx[d] = p.pos[(size_t)j * D + d] - rowp[i][d];
+        dx[d] = pj[u][d] - rowp[i[u]][d];
         d2 = d2 + dx[d] * dx[d];
       }
       // the queue holds the survivors of the conservative fp32 pre-filter; this is
       // the reference's exact predicate (src/Search.h:438-446)
-      if (d2 > p.r2) continue;
-      if (d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
+      const bool ok = live[u] && !(d2 > p.r2);
+      if (ok && d2 > p.r2lo) atomicOr(&sm.danger, 1u << i[u]);
       if (STATS) {
-        sm.part[0][i][lane] += 1ull;
-        sm.part[1][i][lane] += mix64((uint64_t)j * 81u + (uint64_t)image_id);
+        if (ok) {
+          sm.part[0][i[u]][lane] += 1ull;
+          sm.part[1][i[u]][lane] += mix64((uint64_t)j[u] * 81u + (uint64_t)image_id);
+        }
       } else {
+        // F is evaluated unconditionally (it is pure; j, i are valid indices even for
+        // a pair that fails the test) so the two chains interleave; only the
+        // accumulation is predicated
         double blk[BR * BC];
-        f(dx, d2, r0 + i, j, blk);
+        f(dx, d2, r0 + i[u], j[u], blk);
 #pragma unroll
         for (int a2 = 0; a2 < BR; ++a2) {
           double s = 0;
 #pragma unroll
-          for (int c = 0; c < BC; ++c) s += blk[a2 * BC + c] * p.b[(size_t)j * BC + c];
-          double *slot = reinterpret_cast<double *>(&sm.part[a2][i][lane]);
-          *slot += s;
+          for (int c = 0; c < BC; ++c) s += blk[a2 * BC + c] * bj[u][c];
+          if (ok) {
+            double *slot = reinterpret_cast<double *>(&sm.part[a2][i[u]][lane]);
+            *slot += s;
+          }
         }
       }
     }
