@@ -1,5 +1,6 @@
 // C-ABI entry points of libabr.so (declared in include/abr.h).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -55,6 +56,7 @@ int abr_create(abr_handle *out, int device, void *stream) {
     return ABR_ERR_CUDA;
   }
   cudaMemset(h->d_scalars, 0, sizeof(abr::DevScalars));
+  if (const char *e = getenv("ABR_PHASED_GATHER")) h->phased_gather = (e[0] != '0');
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
   for (int d = 0; d < abr::MAXD; ++d) {

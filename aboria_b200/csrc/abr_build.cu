@@ -477,12 +477,78 @@ int probe_fp64_peak(Handle *h, double *tflops) {
 
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
+// Phased gather for column sets larger than L2.  A random gather from an array
+// that does not fit in L2 pulls ~91 B from HBM per element whatever its size
+// (tools/gather_probe.cu).  Here the SOURCE index range is cut into windows
+// whose rows (all columns together) fit in L2; one launch per window streams the
+// whole permutation (coalesced, evict-first) and moves only the elements whose
+// source lies in the window — every source sector is fetched from HBM once and
+// reused from L2 by the other elements of its line.
+constexpr int GP_MAXC = 8;
+struct GatherCols {
+  int ncols;
+  const uint8_t *src[GP_MAXC];
+  uint8_t *dst[GP_MAXC];
+  uint32_t eb[GP_MAXC];
+};
+
+__global__ void __launch_bounds__(256)
+k_gather_phased(const GatherCols cols, const int32_t *__restrict__ order, uint64_t n_out,
+                const uint32_t *__restrict__ n_dev, uint32_t lo, uint32_t hi) {
+  if (n_dev) n_out = min(n_out, (uint64_t)*n_dev);
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_out) return;
+  const uint32_t o = (uint32_t)__ldcs(order + k);
+  if (o < lo || o >= hi) return;
+  for (int c = 0; c < cols.ncols; ++c) {
+    const uint32_t eb = cols.eb[c];
+    const uint8_t *s = cols.src[c] + (uint64_t)o * eb;
+    uint8_t *d = cols.dst[c] + k * eb;
+    if ((eb & 7u) == 0 && (((uintptr_t)s | (uintptr_t)d) & 7u) == 0) {
+      for (uint32_t w = 0; w < eb / 8; ++w) __stcs(reinterpret_cast<uint64_t *>(d) + w, __ldg(reinterpret_cast<const uint64_t *>(s) + w));
+    } else if ((eb & 3u) == 0 && (((uintptr_t)s | (uintptr_t)d) & 3u) == 0) {
+      for (uint32_t w = 0; w < eb / 4; ++w) reinterpret_cast<uint32_t *>(d)[w] = __ldg(reinterpret_cast<const uint32_t *>(s) + w);
+    } else {
+      for (uint32_t w = 0; w < eb; ++w) d[w] = __ldg(s + w);
+    }
+  }
+}
+
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
                    const size_t *elem_bytes, const int32_t *order, size_t n_out, const uint32_t *n_dev) {
   if (n_out == 0) return ABR_OK;
+  size_t row_bytes = 0;
+  for (int c = 0; c < ncols; ++c) {
+    if (elem_bytes[c] == 0 || !src[c] || !dst[c]) return set_error(h, ABR_ERR_INVALID, "gather: null column");
+    row_bytes += elem_bytes[c];
+  }
+  // source larger than L2 -> phased gather (window = rows worth ~80 MB of source)
+  const size_t kWindowBytes = (size_t)80 << 20;
+  if (h->phased_gather && row_bytes * n_out > 2 * kWindowBytes && n_out < 0xFFFFFFFFull) {
+    const uint32_t win = (uint32_t)std::max<size_t>(1, kWindowBytes / row_bytes);
+    // the source index space is [0, n_src); n_out <= n_src and order[] < n_src.  n_src is
+    // not known here, but order holds a permutation prefix of it: windows up to 2^32 cover it
+    const uint64_t n_src = h->gather_src_n ? h->gather_src_n : n_out;
+    for (int c0 = 0; c0 < ncols; c0 += GP_MAXC) {
+      GatherCols gc;
+      gc.ncols = std::min(GP_MAXC, ncols - c0);
+      for (int c = 0; c < gc.ncols; ++c) {
+        gc.src[c] = static_cast<const uint8_t *>(src[c0 + c]);
+        gc.dst[c] = static_cast<uint8_t *>(dst[c0 + c]);
+        gc.eb[c] = (uint32_t)elem_bytes[c0 + c];
+      }
+      for (uint64_t lo = 0; lo < n_src; lo += win) {
+        // the last window is open-ended: order[] may hold indices >= n_out when dead particles were dropped
+        const uint64_t hi = (lo + win >= n_src) ? 0xFFFFFFFFull : lo + win;
+        k_gather_phased<<<grid_for(n_out, 256), 256, 0, h->stream>>>(gc, order, n_out, n_dev, (uint32_t)lo, (uint32_t)hi);
+        h->launches += 1;
+      }
+    }
+    ABR_CUDA(h, cudaGetLastError());
+    return ABR_OK;
+  }
   for (int c = 0; c < ncols; ++c) {
     const size_t eb = elem_bytes[c];
-    if (eb == 0 || !src[c] || !dst[c]) return set_error(h, ABR_ERR_INVALID, "gather: null column");
     const bool aligned8 = (eb % 8 == 0) && ((uintptr_t)src[c] % 8 == 0) && ((uintptr_t)dst[c] % 8 == 0);
     if (aligned8 && eb <= 128) { // staged path: 256 * eb bytes of shared memory (<= 32 KB)
       const uint32_t words = (uint32_t)(eb / 8);
@@ -691,8 +757,10 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     if (reorder) {
       // Particles::reorder enqueued behind the build, bounded by the device-side
       // alive count: the only host round trip of update_positions is the final one
+      h->gather_src_n = n;
       int rc = gather_columns(h, reorder->ncols, reorder->src, reorder->dst, reorder->elem_bytes, order_out, n,
                               &h->d_scalars->n_alive);
+      h->gather_src_n = 0;
       if (rc) return rc;
     }
     ABR_CUDA(h, cudaStreamSynchronize(h->stream));

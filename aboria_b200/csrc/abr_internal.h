@@ -84,6 +84,8 @@ struct Handle {
 
   uint64_t counters[4] = {0, 0, 0, 0};
   uint64_t launches = 0; // kernels launched since abr_create
+  bool phased_gather = false; // L2-windowed reorder for column sets larger than L2 (measured SLOWER on B200: 5.8 vs 3.0 ms build; ABR_PHASED_GATHER=1 enables)
+  uint64_t gather_src_n = 0; // source length of the gather in flight (0: unknown, use n_out)
 
   Grid grid() const;
 };

@@ -150,7 +150,10 @@ template <int D, class F, bool STATS> struct WarpSmem {
   static constexpr int RB = TiledCfg<D, F, STATS>::RB;
   double rows0[RB][4];                    // rows of the batch (x,y,z,pad)
   double rowsS[RB][4];                    // rows shifted by a periodic image
-  float rowsf[RB + 2][4];                 // rows relative to the bucket-stencil origin, fp32 (pre-filter); padded with far-away dummies
+  // rows relative to the bucket-stencil origin, fp32, for the pre-filter: row PAIRS packed
+  // per dimension (x_2p, x_2p+1), (y..), (z..), pad — the operands of f32x2 instructions;
+  // padded with far-away dummy rows
+  unsigned long long rowsf2[RB / 2 + 1][4];
   unsigned long long part[NACC][RB][32];  // partial sums [row][lane]
   uint32_t lq[32][QSTRIDE];               // lane-private accepted-pair queues: (j << ROW_BITS) | row
   uint32_t run_pref[32];                  // candidate-run directory: inclusive prefix of run lengths
@@ -259,14 +262,41 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
   __syncwarp();
 }
 
+// packed fp32 pairs (Blackwell FADD2 / FFMA2): one instruction, two rows
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // One step of the hot loop: this lane's TWO candidates (jA, jB) against the nr
 // rows of the batch, two rows at a time.  This is a conservative fp32
 // PRE-FILTER on coordinates relative to the stencil origin: a pair survives if
 // |dx|^2 <= r^2 (1 + tol) in fp32, tol chosen on the host so that no pair the
-// exact fp64 test accepts is ever dropped.  Survivors cost one predicated
-// 4-byte store into the lane's own queue; the exact un-fused fp64 predicate is
-// applied to them in drain_queues.  (The fp64 pipe is the scarce resource:
-// 6.45 candidates are tested per accepted pair.)
+// exact fp64 test accepts is ever dropped.  The two rows of a step are the two
+// halves of packed f32x2 operands (FADD2 / FFMA2): 4 tests cost 4 D packed
+// instructions.  Survivors cost one predicated 4-byte store into the lane's own
+// queue; the exact un-fused fp64 predicate is applied to them in drain_queues.
+// (6.45 candidates are tested per accepted pair, so this loop is kept off the
+// fp64 pipe altogether.)
 template <int D, class F, bool STATS, class SM>
 __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_r2, const F &f, int lane,
                                           const float *pA, const float *pB, uint32_t jA, uint32_t jB, bool vA, bool vB,
@@ -274,25 +304,33 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
                                           uint32_t &cnt) {
   uint32_t *myq = sm.lq[lane];
   // invalid candidates are parked far away instead of being predicated out
-  float a[D], b[D];
+  unsigned long long a[D], b[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    a[d] = vA ? pA[d] : -3.0e18f;
-    b[d] = vB ? pB[d] : -3.0e18f;
+    const float av = vA ? pA[d] : -3.0e18f, bv = vB ? pB[d] : -3.0e18f;
+    a[d] = pack2(av, av);
+    b[d] = pack2(bv, bv);
   }
   uint32_t eA = jA << ROW_BITS, eB = jB << ROW_BITS;
-  for (int i = 0; i < nr; i += 2) { // rowsf is padded with a dummy row: an odd tail needs no special case
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const float r0d = sm.rowsf[i][d], r1d = sm.rowsf[i + 1][d];
-      const float ta0 = a[d] - r0d, ta1 = a[d] - r1d;
-      const float tb0 = b[d] - r0d, tb1 = b[d] - r1d;
-      a0 = fmaf(ta0, ta0, a0);
-      a1 = fmaf(ta1, ta1, a1);
-      b0 = fmaf(tb0, tb0, b0);
-      b1 = fmaf(tb1, tb1, b1);
+  const int npairs = (nr + 1) >> 1; // an odd tail pairs with a dummy row
+  for (int pr = 0; pr < npairs; ++pr) {
+    unsigned long long accA, accB;
+    {
+      const unsigned long long r = sm.rowsf2[pr][0];
+      const unsigned long long ta = sub2(a[0], r), tb = sub2(b[0], r);
+      accA = mul2(ta, ta);
+      accB = mul2(tb, tb);
     }
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      const unsigned long long r = sm.rowsf2[pr][d];
+      const unsigned long long ta = sub2(a[d], r), tb = sub2(b[d], r);
+      accA = fma2(ta, ta, accA);
+      accB = fma2(tb, tb, accB);
+    }
+    float a0, a1, b0, b1;
+    unpack2(accA, a0, a1);
+    unpack2(accB, b0, b1);
     if (a0 <= pre_r2) myq[cnt++] = eA;
     if (a1 <= pre_r2) myq[cnt++] = eA + 1u;
     if (b0 <= pre_r2) myq[cnt++] = eB;
@@ -395,10 +433,11 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
         if (lane == 0) sm.danger = 0;
         if (lane < RB + 2) {
           // fp32 copy relative to the stencil origin (lower corner of the first neighbour
-          // bucket); rows >= nr are dummies far away from everything
+          // bucket), packed in row pairs; rows >= nr are dummies far away from everything
+          float *rf = reinterpret_cast<float *>(&sm.rowsf2[0][0]);
 #pragma unroll
           for (int d = 0; d < D; ++d)
-            sm.rowsf[lane][d] = lane < nr ? (float)(sm.rows0[lane][d] - origin[d]) : 3.0e18f;
+            rf[(((lane >> 1) * 4) + d) * 2 + (lane & 1)] = lane < nr ? (float)(sm.rows0[lane][d] - origin[d]) : 3.0e18f;
         }
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
