@@ -281,8 +281,8 @@ def run_ours(args):
     mv_tflops = flops_per_pair * pairs / (ms_mv * 1e-3) / 1e12
     roofline = {"bound": "hbm", "kernel": "abr::tiled_kernel<3, InvDist> (sparse matvec, dominant kernel of the step)",
                 "achieved": mv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": mv_gbs / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=32M (profiles/r1e_ncu_tiled_kernel_v5_summary.txt)
-                "traffic": 1.576e9 if n == 32_000_000 else None, "algorithmic_bytes": mv_bytes, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=32M (profiles/r1m_ncu_tiled_kernel_v7_summary.txt)
+                "traffic": 1.590e9 if n == 32_000_000 else None, "algorithmic_bytes": mv_bytes, "peak_source": peak_src,
                 "note": "the matvec is fp64-pipe bound, not HBM bound (SURVEY §8d); see roofline_fp64. algorithmic bytes = N(8D+8BR)+N(8D+8BC)+8C"}
     roofline_fp64 = {"bound": "fp64", "achieved": mv_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": mv_tflops / fp64_peak,
                      "peak_source": "measured here (abr_probe_fp64_peak, DFMA loop)", "flops_per_pair": flops_per_pair,
