@@ -289,3 +289,90 @@ def test_large_properties():
     assert bool(((op * (2 * x)) == 2 * Kx).all())
     lhs, rhs = float(torch.dot(x, Ky)), float(torch.dot(yv, Kx))
     assert abs(lhs - rhs) / abs(lhs) < 1e-12
+
+
+# ----------------------------------------------------------------------------
+# BASELINE.json configs at full size
+# ----------------------------------------------------------------------------
+def test_c2_rbf_2d_full_size_vs_oracle():
+    # configs[1]: 2-D RBF interpolation, Wendland C2 compact kernel, N=1e6, ~30 neighbours/point
+    N = 1_000_000
+    pos = synth.uniform_positions(N, 2)
+    h = 0.5 * np.sqrt(30.0 / (np.pi * N))
+    o, out, p = build_both(pos, 0.0, 1.0, False)
+    assert_build_equal(o, out, p)
+    y, y_o, npairs, op, bt = _matvec_both(o, out, p, K.wendland_c2(h), orc.K_WENDLAND_C2, [h], 2 * h)
+    assert rel_l2(y, y_o) <= TOL
+    assert 28 < npairs / N < 32
+    cnt_o, hs_o = o.pair_stats(out["pos"], 2 * h)
+    cnt, hs = p.pair_stats(2 * h, path=0)
+    assert np.array_equal(cnt.cpu().numpy().view(np.uint32), cnt_o)
+    assert np.array_equal(hs.cpu().numpy().view(np.uint64), hs_o)
+
+
+def test_c3_lj_4m_newton_third_law_and_sampled_oracle():
+    # configs[2]: 3-D Lennard-Jones force evaluation, N=4M, periodic, cutoff 2.5 sigma.
+    # Property (size independent): the force kernel is antisymmetric, so with b = 1 the
+    # total force vanishes.  Parity: rows sampled from the cloud against the oracle.
+    N = 4_000_000
+    L = (N / 0.8442) ** (1.0 / 3.0)
+    dev = torch.device("cuda:0")
+    pos = synth.torch_uniform_positions(N, 3, 0.0, L, synth.SEED, 0, dev)
+    p = ab.Particles(3, 0)
+    p.resize_from_positions(pos)
+    p.init_neighbour_search(0.0, L, True)
+    op = ab.create_sparse_operator(p, p, 2.5, K.lj_force(3, 1.0, 1.0))
+    ones = torch.ones(N, dtype=torch.float64, device=dev)
+    f = (op * ones).view(N, 3)
+    # uniform random clouds have arbitrarily close pairs -> huge forces; compare sums relative to sum |f|
+    tot = f.sum(dim=0).abs().max().item()
+    scale = f.abs().sum().item()
+    assert tot / scale < 1e-12
+    # oracle on the same sorted positions, sampled rows (rows != cols path on the oracle side)
+    ps = p.get("position").cpu().numpy()
+    o = orc.Oracle(3)
+    o.set_domain(0.0, L, True, 10.0)
+    out = o.update_positions(ps.copy())
+    assert np.array_equal(out["order"], np.arange(N))  # already sorted: the stable build is idempotent
+    o.update_iterators(ps)
+    sub = np.arange(0, N, 401)
+    y_o, _ = o.sparse_matvec(ps[sub], orc.K_LJ_FORCE, [1.0, 1.0], 2.5, np.ones(N), BR=3, BC=1)
+    y_g = f.cpu().numpy()[sub].reshape(-1)
+    assert rel_l2(y_g, y_o) <= TOL
+
+
+def test_c4_sph_clustered_16m_properties():
+    # configs[3]: SPH density sum, N=16M clustered cloud (64 Gaussian blobs + 10 % background),
+    # periodic (1,1,0).  Oracle too slow at this size: tiled == exact walk on sampled rows,
+    # symmetric kernel => x.(K y) == y.(K x), and the oracle on sampled rows.
+    N = 16_000_000
+    dev = torch.device("cuda:0")
+    pos = torch.from_numpy(synth.clustered_positions(N)).to(dev)
+    p = ab.Particles(3, 0)
+    p.resize_from_positions(pos)
+    p.init_neighbour_search(0.0, 1.0, [True, True, False])
+    q = p.get_query()
+    assert int((q.bucket_end.long() - q.bucket_begin.long()).sum()) == N
+    h = 1.5 * N ** (-1.0 / 3.0)
+    r = 2 * h
+    kern = K.sph_density(h, 1.0 / N, 21.0 / (256.0 * np.pi))
+    op = ab.create_sparse_operator(p, p, r, kern)
+    cnt0, hs0 = p.pair_stats(r, path=0)
+    sub = torch.arange(0, N, 1601, device=dev)
+    cnt1, hs1 = p.pair_stats(r, rows=p.get("position")[sub].contiguous(), path=1)
+    assert bool((cnt0[sub] == cnt1).all()) and bool((hs0[sub] == hs1).all())
+    assert int(cnt0.max()) > 500  # heavy buckets are exercised
+    x = torch.from_numpy(synth.vector(N, seed=7)).to(dev)
+    yv = torch.from_numpy(synth.vector(N, seed=8)).to(dev)
+    Kx, Ky = op * x, op * yv
+    lhs, rhs = float(torch.dot(x, Ky)), float(torch.dot(yv, Kx))
+    assert abs(lhs - rhs) / abs(lhs) < 1e-12
+    ps = p.get("position").cpu().numpy()
+    o = orc.Oracle(3)
+    o.set_domain(0.0, 1.0, [True, True, False], 10.0)
+    out = o.update_positions(ps.copy())
+    assert np.array_equal(out["order"], np.arange(N))
+    o.update_iterators(ps)
+    subn = sub.cpu().numpy()[::4]
+    y_o, _ = o.sparse_matvec(ps[subn], orc.K_SPH_DENSITY, [h, 1.0 / N, 21.0 / (256.0 * np.pi)], r, x.cpu().numpy())
+    assert rel_l2(Kx.cpu().numpy()[subn], y_o) <= TOL
