@@ -165,6 +165,19 @@ template <int D, class F, bool STATS> struct WarpSmem {
 
 constexpr uint32_t TILED_GRAB = 8; // consecutive buckets a warp claims per scheduler step
 
+// Stencil trimming.  A neighbour bucket at offset o (in buckets) from the target
+// bucket is at least max(|o|-1, 0) * side away from every point of the target
+// in that dimension.  Given the squared gap already spent in the slow dimensions,
+// returns how many buckets the last dimension can still reach (-1: none), with a
+// 1e-6 relative safety margin — far above rounding, far below anything that
+// changes which buckets are needed.  (r/side = 1.09, w = 2: 81 of 125 buckets.)
+__device__ __forceinline__ int reach_last_dim(double r2, double gap2, double side_last, int w_last) {
+  const double rem2 = r2 * (1.0 + 1e-6) - gap2;
+  if (rem2 < 0.0) return -1;
+  const int m = (int)(sqrt(rem2) / side_last * (1.0 + 1e-6) + 1e-6) + 1;
+  return m < w_last ? m : w_last;
+}
+
 // Drain the lane-private queues: the queued (j, row) pairs of all lanes are
 // dealt out evenly, 32 per round, so the expensive part of the product (sqrt,
 // divide, the user's math) runs at full lane utilisation instead of on the ~15 %
@@ -455,16 +468,21 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
             int nc[D];
             bool ok = true;
             int rem = rid;
+            double gap2 = 0.0;
 #pragma unroll
             for (int d = D - 2; d >= 0; --d) {
               const int span = 2 * p.w[d] + 1;
-              const int u = tc[d] + (rem % span) - p.w[d];
+              const int od = (rem % span) - p.w[d];
+              const int u = tc[d] + od;
               rem /= span;
               ok &= (u >= 0) & (u < g.size[d]);
               nc[d] = u;
+              const double gap = (double)max(abs(od) - 1, 0) * g.side[d];
+              gap2 += gap * gap;
             }
-            const int a = max(zlo, 0), bnd = min(zhi, S - 1);
-            if (ok && a <= bnd) {
+            const int wz = reach_last_dim(p.r2, gap2, g.side[L], p.w[L]); // trimmed stencil
+            const int a = max(tc[L] - wz, 0), bnd = min(tc[L] + wz, S - 1);
+            if (ok && wz >= 0 && a <= bnd) {
               nc[L] = a;
               const int c_lo = local_collapse<D>(g, nc);
               if (c_lo >= 0) {
@@ -521,8 +539,11 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
           while (more) {
             int nc[D], img[D];
             bool ok_slow = true, slow_shifted = false;
+            double gap2 = 0.0;
 #pragma unroll
             for (int d = 0; d < D - 1; ++d) {
+              const double gap = (double)max(abs(o[d]) - 1, 0) * g.side[d];
+              gap2 += gap * gap;
               int u = tc[d] + o[d];
               img[d] = 0;
               if (u < 0) {
@@ -536,11 +557,12 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
               slow_shifted |= (img[d] != 0);
               nc[d] = u;
             }
-            if (ok_slow) {
+            const int wz = reach_last_dim(p.r2, gap2, g.side[L], p.w[L]); // trimmed stencil
+            if (ok_slow && wz >= 0) {
               for (int m = (g.periodic[L] ? -1 : 0); m <= (g.periodic[L] ? 1 : 0); ++m) {
                 if (m == 0 && !slow_shifted) continue; // primary image: done in phase 1
                 // unwrapped indices [m*S, m*S + S - 1] map to buckets [0,S-1] with image -m
-                const int a = max(zlo, m * S), bnd = min(zhi, m * S + S - 1);
+                const int a = max(tc[L] - wz, m * S), bnd = min(tc[L] + wz, m * S + S - 1);
                 if (a > bnd) continue;
                 img[L] = -m;
                 nc[L] = a - m * S;
