@@ -67,6 +67,7 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p)
       p->tolf[d] = std::fmax(4e-9, 8.0 * delta * h->inv_side[d]);
       if (p->tolf[d] > 0.125) tiled = false;
       stencil *= (2.0 * p->w[d] + 1.0);
+      if (p->w[d] >= 2) p->trim = 1;
     }
     if (stencil > 8192.0) tiled = false; // radius >> bucket side: the walk is the better kernel
     if (tiled) {

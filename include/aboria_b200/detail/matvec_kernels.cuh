@@ -46,6 +46,7 @@ struct abr_matvec_plan {
   // tiled path
   int use_tiled;
   int w[abr::MAXD];        // stencil half width per dimension
+  int trim;                // some w >= 2: trim the stencil by distance (nothing to trim when all w == 1)
   double r2, r2lo;         // cut-off^2 and the "rounding sensitive" lower edge
   float pre_r2;            // fp32 pre-filter threshold: r2 * (1 + tol), never rejects a pair the exact test accepts
   double tolf[abr::MAXD];  // fractional bucket coordinate tolerance
@@ -357,8 +358,11 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
   }
 }
 
+// occupancy target: the shared-memory footprint allows 7 CTAs/SM for scalar kernels
+// (needs <= 73 registers), 3 for D x 1 block kernels
 template <int D, class F, bool STATS>
-__global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_plan p, const F f) {
+__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::NACC == 1 ? 7 : 3))
+tiled_kernel(const abr_matvec_plan p, const F f) {
   constexpr int BR = F::BR;
   constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
   constexpr int RB = TiledCfg<D, F, STATS>::RB;
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
               const double gap = (double)max(abs(od) - 1, 0) * g.side[d];
               gap2 += gap * gap;
             }
-            const int wz = reach_last_dim(p.r2, gap2, g.side[L], p.w[L]); // trimmed stencil
+            const int wz = p.trim ? reach_last_dim(p.r2, gap2, g.side[L], p.w[L]) : p.w[L]; // trimmed stencil
             const int a = max(tc[L] - wz, 0), bnd = min(tc[L] + wz, S - 1);
             if (ok && wz >= 0 && a <= bnd) {
               nc[L] = a;
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(TILED_THREADS) tiled_kernel(const abr_matvec_p
               slow_shifted |= (img[d] != 0);
               nc[d] = u;
             }
-            const int wz = reach_last_dim(p.r2, gap2, g.side[L], p.w[L]); // trimmed stencil
+            const int wz = p.trim ? reach_last_dim(p.r2, gap2, g.side[L], p.w[L]) : p.w[L]; // trimmed stencil
             if (ok_slow && wz >= 0) {
               for (int m = (g.periodic[L] ? -1 : 0); m <= (g.periodic[L] ? 1 : 0); ++m) {
                 if (m == 0 && !slow_shifted) continue; // primary image: done in phase 1
