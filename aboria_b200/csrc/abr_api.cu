@@ -81,6 +81,10 @@ int abr_destroy(abr_handle hh) {
   }
   h->tile_hist.release();
   h->scan_tmp.release();
+  h->idx2.release();
+  h->tmp_cols.release();
+  h->tile_tab.release();
+  h->seg_hist.release();
   h->bucket_begin.release();
   h->bucket_end.release();
   h->danger_list.release();
@@ -94,6 +98,20 @@ int abr_set_stream(abr_handle hh, void *stream) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return ABR_ERR_INVALID;
   h->stream = static_cast<cudaStream_t>(stream);
+  return ABR_OK;
+}
+
+int abr_set_option(abr_handle hh, const char *name, double value) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !name) return ABR_ERR_INVALID;
+  const std::string k(name);
+  if (k == "two_level_min_n") {
+    h->two_level_min_n = value < 0 ? 0 : (size_t)value;
+  } else if (k == "phased_gather") {
+    h->phased_gather = value != 0;
+  } else {
+    return abr::set_error(h, ABR_ERR_INVALID, "set_option: unknown option " + k);
+  }
   return ABR_OK;
 }
 

@@ -97,22 +97,56 @@ constexpr int RS_TILE = RS_THREADS * RS_IPT;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RADIX = 256;
 
-// per-tile digit histogram, digit-major: hist[d * num_tiles + tile]
+// Tile table of a SEGMENTED pass (two-level build): tiles never straddle the bins
+// of the first-level partition, and the histogram is laid out [bin][digit][tile in
+// bin] so that one flat exclusive scan yields bin-local destinations.  Null table
+// = dense pass: tile t covers [t*RS_TILE, ...), histogram digit-major [digit][tile].
+struct TileTab {
+  const uint32_t *start;   // first element of the tile
+  const uint32_t *count;   // elements in the tile
+  const uint32_t *hbase;   // histogram index of (digit 0, this tile)
+  const uint32_t *hstride; // histogram stride between digits
+  const uint32_t *total;   // number of tiles in use (device)
+};
+
+struct TileInfo {
+  uint32_t start, count, hbase, hstride;
+  bool live;
+};
+__device__ __forceinline__ TileInfo tile_info(const TileTab &tt, uint32_t tile, uint32_t n, uint32_t num_tiles) {
+  TileInfo t;
+  if (tt.start) {
+    t.live = tile < *tt.total;
+    t.start = t.live ? tt.start[tile] : 0;
+    t.count = t.live ? tt.count[tile] : 0;
+    t.hbase = t.live ? tt.hbase[tile] : 0;
+    t.hstride = t.live ? tt.hstride[tile] : 0;
+  } else {
+    t.live = true;
+    t.start = tile * RS_TILE;
+    t.count = min((uint32_t)RS_TILE, n - t.start);
+    t.hbase = tile;
+    t.hstride = num_tiles;
+  }
+  return t;
+}
+
+// per-tile digit histogram
 __global__ void __launch_bounds__(RS_THREADS)
 k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t num_tiles,
-             uint32_t *__restrict__ hist) {
+             uint32_t *__restrict__ hist, const TileTab tt) {
   __shared__ uint32_t s_hist[RADIX];
-  const uint32_t tile = blockIdx.x;
+  const TileInfo ti = tile_info(tt, blockIdx.x, n, num_tiles);
+  if (!ti.live) return;
   if (threadIdx.x < RADIX) s_hist[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t base = tile * RS_TILE;
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
-    const uint32_t p = base + j * RS_THREADS + threadIdx.x;
-    if (p < n) atomicAdd(&s_hist[(keys[p] >> shift) & (RADIX - 1)], 1u);
+    const uint32_t q = j * RS_THREADS + threadIdx.x;
+    if (q < ti.count) atomicAdd(&s_hist[(keys[ti.start + q] >> shift) & (RADIX - 1)], 1u);
   }
   __syncthreads();
-  if (threadIdx.x < RADIX) hist[(size_t)threadIdx.x * num_tiles + tile] = s_hist[threadIdx.x];
+  if (threadIdx.x < RADIX) hist[(size_t)threadIdx.x * ti.hstride + ti.hbase] = s_hist[threadIdx.x];
 }
 
 struct RadixScatterSmem {
@@ -124,11 +158,15 @@ struct RadixScatterSmem {
   uint32_t s_scan[RADIX / 32];
 };
 
+// DEST_ONLY: instead of moving (key, index) pairs, write for every input element
+// its destination (dest[p], coalesced) — the first level of the two-level build
+// moves whole particle records with it.
+template <bool DEST_ONLY>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ idx_out,
                 const uint32_t *__restrict__ tile_offsets, int shift, uint32_t n,
-                uint32_t num_tiles) {
+                uint32_t num_tiles, const TileTab tt) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RadixScatterSmem &S = *reinterpret_cast<RadixScatterSmem *>(rs_raw);
   auto &warp_hist = S.warp_hist;
@@ -138,26 +176,27 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   auto &s_idx = S.s_idx;
   auto &s_scan = S.s_scan;
 
-  const uint32_t tile = blockIdx.x;
+  const TileInfo ti = tile_info(tt, blockIdx.x, n, num_tiles);
+  if (!ti.live) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t lane_lt = (1u << lane) - 1u;
   for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
   __syncthreads();
 
-  const uint32_t wbase = tile * RS_TILE + warp * (RS_IPT * 32);
+  const uint32_t qbase = warp * (RS_IPT * 32); // position inside the tile
+  const uint32_t wbase = ti.start + qbase;
   uint32_t key[RS_IPT], val[RS_IPT];
   uint16_t rank[RS_IPT];
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
     const uint32_t p = wbase + j * 32 + lane;
-    const bool valid = p < n;
+    const bool valid = qbase + j * 32 + lane < ti.count;
     key[j] = valid ? keys_in[p] : 0xFFFFFFFFu;
     val[j] = valid ? (idx_in ? idx_in[p] : p) : 0u;
   }
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
-    const uint32_t p = wbase + j * 32 + lane;
-    const bool valid = p < n;
+    const bool valid = qbase + j * 32 + lane < ti.count;
     const uint32_t d = (key[j] >> shift) & (RADIX - 1);
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : (RADIX + lane));
     const uint32_t prev = warp_hist[warp][d];
@@ -179,7 +218,7 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
       running += c;
     }
     const uint32_t total = running;
-    glob_off[d] = tile_offsets[(size_t)d * num_tiles + tile];
+    glob_off[d] = tile_offsets[(size_t)d * ti.hstride + ti.hbase];
     // exclusive scan of the 256 digit totals
     uint32_t incl = total;
 #pragma unroll
@@ -203,15 +242,20 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
     const uint32_t p = wbase + j * 32 + lane;
-    if (p < n) {
+    if (qbase + j * 32 + lane < ti.count) {
       const uint32_t d = (key[j] >> shift) & (RADIX - 1);
       const uint32_t slot = digit_start[d] + warp_hist[warp][d] + rank[j];
-      s_keys[slot] = key[j];
-      s_idx[slot] = val[j];
+      if (DEST_ONLY) {
+        idx_out[p] = glob_off[d] + (slot - digit_start[d]); // dest[p]
+      } else {
+        s_keys[slot] = key[j];
+        s_idx[slot] = val[j];
+      }
     }
   }
+  if (DEST_ONLY) return;
   __syncthreads();
-  const uint32_t tile_count = min((uint32_t)RS_TILE, n - tile * RS_TILE);
+  const uint32_t tile_count = ti.count;
   for (uint32_t s = tid; s < tile_count; s += RS_THREADS) {
     const uint32_t k = s_keys[s];
     const uint32_t d = (k >> shift) & (RADIX - 1);
@@ -514,6 +558,70 @@ k_gather_phased(const GatherCols cols, const int32_t *__restrict__ order, uint64
   }
 }
 
+// First level of the two-level build: every particle record (all columns, its
+// key and its original index) moves to the bin of its most significant key
+// digit.  Reads are coalesced (original order); the writes advance 256
+// sequential streams, which L2 turns into full-sector HBM writes.
+__global__ void __launch_bounds__(256)
+k_move_by_dest(const GatherCols cols, const uint32_t *__restrict__ dest, const uint32_t *__restrict__ keys_in,
+               uint32_t *__restrict__ keys_out, uint32_t *__restrict__ orig_out, uint32_t n) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t d = dest[p];
+  keys_out[d] = keys_in[p];
+  orig_out[d] = p;
+  for (int c = 0; c < cols.ncols; ++c) {
+    const uint32_t eb = cols.eb[c];
+    const uint8_t *s = cols.src[c] + (uint64_t)p * eb;
+    uint8_t *t = cols.dst[c] + (uint64_t)d * eb;
+    if ((eb & 7u) == 0 && (((uintptr_t)s | (uintptr_t)t) & 7u) == 0) {
+      for (uint32_t w = 0; w < eb / 8; ++w) reinterpret_cast<uint64_t *>(t)[w] = __ldg(reinterpret_cast<const uint64_t *>(s) + w);
+    } else if ((eb & 3u) == 0 && (((uintptr_t)s | (uintptr_t)t) & 3u) == 0) {
+      for (uint32_t w = 0; w < eb / 4; ++w) reinterpret_cast<uint32_t *>(t)[w] = __ldg(reinterpret_cast<const uint32_t *>(s) + w);
+    } else {
+      for (uint32_t w = 0; w < eb; ++w) t[w] = __ldg(s + w);
+    }
+  }
+}
+
+// Tile table of the segmented passes from the scanned first-level histogram:
+// bin b starts at scanned[b * num_tiles] (digit-major layout, tile 0).
+struct TileTabW {
+  uint32_t *start, *count, *hbase, *hstride, *total, *bin_tile0;
+};
+__global__ void __launch_bounds__(RADIX) k_tiletab_bins(const uint32_t *__restrict__ scanned, uint32_t num_tiles, uint32_t n, TileTabW w) {
+  __shared__ uint32_t s_nt[RADIX];
+  const int b = threadIdx.x;
+  const uint32_t lo = scanned[(size_t)b * num_tiles];
+  const uint32_t hi = b + 1 < RADIX ? scanned[(size_t)(b + 1) * num_tiles] : n;
+  const uint32_t nt = (hi - lo + RS_TILE - 1) / RS_TILE;
+  s_nt[b] = nt;
+  __syncthreads();
+  if (b == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < RADIX; ++i) {
+      const uint32_t c = s_nt[i];
+      s_nt[i] = run;
+      run += c;
+    }
+    *w.total = run;
+  }
+  __syncthreads();
+  w.bin_tile0[b] = s_nt[b];
+  const uint32_t t0 = s_nt[b];
+  for (uint32_t t = 0; t < nt; ++t) {
+    w.start[t0 + t] = lo + t * RS_TILE;
+    w.count[t0 + t] = min((uint32_t)RS_TILE, hi - (lo + t * RS_TILE));
+    w.hbase[t0 + t] = RADIX * t0 + t;
+    w.hstride[t0 + t] = nt;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_iota(uint32_t *out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
                    const size_t *elem_bytes, const int32_t *order, size_t n_out, const uint32_t *n_dev) {
   if (n_out == 0) return ABR_OK;
@@ -721,27 +829,100 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     h->launches += 1;
 
     // LSD radix sort over the bits of key_bound
-    ABR_CUDA(h, cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixScatterSmem)));
+    ABR_CUDA(h, cudaFuncSetAttribute(k_radix_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixScatterSmem)));
     int bits = 1;
     while (bits < 32 && (g.key_bound >> bits) != 0) ++bits;
     const int passes = presorted ? 0 : (bits + 7) / 8; // adopt_sorted: keys only, no permutation
     int cur = 0;
     uint32_t *hist = h->tile_hist.as<uint32_t>();
-    for (int pass = 0; pass < passes; ++pass) {
-      const int shift = pass * 8;
-      const uint32_t *kin = h->keys[cur].as<uint32_t>();
-      const uint32_t *iin = pass == 0 ? nullptr : h->idx[cur].as<uint32_t>();
-      uint32_t *kout = h->keys[cur ^ 1].as<uint32_t>();
-      uint32_t *iout = (pass == passes - 1) ? reinterpret_cast<uint32_t *>(order_out)
-                                            : h->idx[cur ^ 1].as<uint32_t>();
-      k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, n32, shift, num_tiles, hist);
+    const TileTab dense{nullptr, nullptr, nullptr, nullptr, nullptr};
+    const uint32_t *perm = nullptr;      // two-level: final position -> position in the binned copy
+    const uint32_t *orig_tmp = nullptr;  // two-level: binned position -> original index
+    GatherCols tmp_cols;                 // two-level: the binned copy of every column
+    tmp_cols.ncols = 0;
+    const bool two_level = reorder && !presorted && passes >= 2 && n >= h->two_level_min_n && reorder->ncols <= GP_MAXC;
+    if (two_level) {
+      // ---- level 1: stable partition of whole records by the most significant digit ----
+      const int top_shift = 8 * (passes - 1);
+      size_t tmp_bytes = 0;
+      for (int c = 0; c < reorder->ncols; ++c) tmp_bytes += ((reorder->elem_bytes[c] * n + 255) / 256) * 256;
+      ABR_CUDA(h, h->tmp_cols.reserve(tmp_bytes));
+      ABR_CUDA(h, h->idx2.reserve(n * sizeof(uint32_t)));
+      const uint32_t t_bound = num_tiles + RADIX;
+      ABR_CUDA(h, h->tile_tab.reserve((size_t)(4 * t_bound + RADIX + 8) * sizeof(uint32_t)));
+      ABR_CUDA(h, h->seg_hist.reserve((size_t)RADIX * t_bound * sizeof(uint32_t)));
+      GatherCols src_cols;
+      src_cols.ncols = tmp_cols.ncols = reorder->ncols;
+      {
+        uint8_t *base = h->tmp_cols.as<uint8_t>();
+        for (int c = 0; c < reorder->ncols; ++c) {
+          src_cols.src[c] = static_cast<const uint8_t *>(reorder->src[c]);
+          src_cols.dst[c] = base;
+          src_cols.eb[c] = (uint32_t)reorder->elem_bytes[c];
+          tmp_cols.src[c] = base;
+          tmp_cols.dst[c] = static_cast<uint8_t *>(reorder->dst[c]);
+          tmp_cols.eb[c] = (uint32_t)reorder->elem_bytes[c];
+          base += ((reorder->elem_bytes[c] * n + 255) / 256) * 256;
+        }
+      }
+      uint32_t *dest = h->idx[0].as<uint32_t>();
+      uint32_t *keys1 = h->keys[1].as<uint32_t>();
+      uint32_t *orig = h->idx[1].as<uint32_t>();
+      k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(keys0, n32, top_shift, num_tiles, hist, dense);
       cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
       if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
-      k_radix_scatter<<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(kin, iin, kout, iout, hist, shift, n32, num_tiles);
-      h->launches += 2;
-      cur ^= 1;
+      ABR_CUDA(h, cudaFuncSetAttribute(k_radix_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixScatterSmem)));
+      k_radix_scatter<true><<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(keys0, nullptr, nullptr, dest, hist, top_shift, n32,
+                                                                                             num_tiles, dense);
+      k_move_by_dest<<<gb, 256, 0, h->stream>>>(src_cols, dest, keys0, keys1, orig, n32);
+      // tile table of the segmented passes
+      uint32_t *tb = h->tile_tab.as<uint32_t>();
+      TileTabW tw{tb, tb + t_bound, tb + 2 * t_bound, tb + 3 * t_bound, tb + 4 * t_bound, tb + 4 * t_bound + 8};
+      k_tiletab_bins<<<1, RADIX, 0, h->stream>>>(hist, num_tiles, n32, tw);
+      const TileTab seg{tw.start, tw.count, tw.hbase, tw.hstride, tw.total};
+      h->launches += 4;
+      // ---- level 2: LSD passes over the remaining digits, segmented by bin; they
+      //      permute (key, binned position) pairs inside 1/256th of the array ----
+      uint32_t *shist = h->seg_hist.as<uint32_t>();
+      const uint32_t *kin = keys1;
+      const uint32_t *iin = nullptr; // iota
+      uint32_t *kbuf[2] = {h->keys[0].as<uint32_t>(), h->keys[1].as<uint32_t>()};
+      uint32_t *ibuf[2] = {h->idx[0].as<uint32_t>(), h->idx2.as<uint32_t>()};
+      int out = 0;
+      for (int pass = 0; pass < passes - 1; ++pass) {
+        const int shift = pass * 8;
+        ABR_CUDA(h, cudaMemsetAsync(shist, 0, (size_t)RADIX * t_bound * sizeof(uint32_t), h->stream));
+        k_radix_hist<<<t_bound, RS_THREADS, 0, h->stream>>>(kin, n32, shift, num_tiles, shist, seg);
+        e = device_scan<OpSum, false, 0>(h, shist, (uint64_t)RADIX * t_bound, shist, nullptr);
+        if (e != cudaSuccess) return check_cuda(h, e, "segmented radix scan");
+        k_radix_scatter<false><<<t_bound, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(kin, iin, kbuf[out], ibuf[out], shist, shift, n32,
+                                                                                              num_tiles, seg);
+        h->launches += 2;
+        kin = kbuf[out];
+        iin = ibuf[out];
+        out ^= 1;
+      }
+      h->sorted_keys = kin;
+      perm = iin;
+      orig_tmp = orig;
+    } else {
+      for (int pass = 0; pass < passes; ++pass) {
+        const int shift = pass * 8;
+        const uint32_t *kin = h->keys[cur].as<uint32_t>();
+        const uint32_t *iin = pass == 0 ? nullptr : h->idx[cur].as<uint32_t>();
+        uint32_t *kout = h->keys[cur ^ 1].as<uint32_t>();
+        uint32_t *iout = (pass == passes - 1) ? reinterpret_cast<uint32_t *>(order_out)
+                                              : h->idx[cur ^ 1].as<uint32_t>();
+        k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, n32, shift, num_tiles, hist, dense);
+        cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
+        if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
+        k_radix_scatter<false><<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(kin, iin, kout, iout, hist, shift, n32, num_tiles,
+                                                                                                dense);
+        h->launches += 2;
+        cur ^= 1;
+      }
+      h->sorted_keys = h->keys[cur].as<uint32_t>();
     }
-    h->sorted_keys = h->keys[cur].as<uint32_t>();
 
     // bucket ranges
     uint32_t *bb = h->bucket_begin.as<uint32_t>();
@@ -757,10 +938,27 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     if (reorder) {
       // Particles::reorder enqueued behind the build, bounded by the device-side
       // alive count: the only host round trip of update_positions is the final one
-      h->gather_src_n = n;
-      int rc = gather_columns(h, reorder->ncols, reorder->src, reorder->dst, reorder->elem_bytes, order_out, n,
-                              &h->d_scalars->n_alive);
-      h->gather_src_n = 0;
+      int rc;
+      if (two_level) {
+        // the source of every output element lies in the same 1/256th of the binned
+        // copy as the element itself: the random side of this gather is served by L2
+        const void *srcs[GP_MAXC + 1];
+        void *dsts[GP_MAXC + 1];
+        size_t ebs[GP_MAXC + 1];
+        for (int c = 0; c < tmp_cols.ncols; ++c) {
+          srcs[c] = tmp_cols.src[c];
+          dsts[c] = tmp_cols.dst[c];
+          ebs[c] = tmp_cols.eb[c];
+        }
+        srcs[tmp_cols.ncols] = orig_tmp; // m_alive_indices: original index of every sorted particle
+        dsts[tmp_cols.ncols] = order_out;
+        ebs[tmp_cols.ncols] = sizeof(uint32_t);
+        rc = gather_columns(h, tmp_cols.ncols + 1, srcs, dsts, ebs, reinterpret_cast<const int32_t *>(perm), n, &h->d_scalars->n_alive);
+      } else {
+        h->gather_src_n = n;
+        rc = gather_columns(h, reorder->ncols, reorder->src, reorder->dst, reorder->elem_bytes, order_out, n, &h->d_scalars->n_alive);
+        h->gather_src_n = 0;
+      }
       if (rc) return rc;
     }
     ABR_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -69,6 +69,8 @@ struct Handle {
 
   // --- device state ---------------------------------------------------------
   DevBuf keys[2], idx[2], tile_hist, scan_tmp;
+  DevBuf idx2, tmp_cols, tile_tab, seg_hist; // two-level build
+  size_t two_level_min_n = (size_t)1 << 20;  // use the two-level build from this many particles (abr_set_option)
   DevBuf bucket_begin, bucket_end;
   DevBuf danger_list;
   DevScalars *d_scalars = nullptr;

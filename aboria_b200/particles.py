@@ -200,6 +200,10 @@ class Particles:
         check(self._h, self._lib.abr_last_counters(self._h, C.byref(c)))
         return dict(walk_rows=int(c[0]), aliased=int(c[1]), launches=int(c[2]), total_launches=int(c[3]))
 
+    def set_option(self, name, value):
+        """tuning knobs of the library (no effect on results), see abr_set_option"""
+        check(self._h, self._lib.abr_set_option(self._h, name.encode(), float(value)))
+
     def probe_fp64_peak(self):
         """measured DFMA throughput of this device in TFLOP/s"""
         self._sync_stream()

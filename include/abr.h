@@ -78,6 +78,10 @@ int abr_create(abr_handle *out, int device, void *stream);
 int abr_destroy(abr_handle h);
 int abr_set_stream(abr_handle h, void *stream);
 int abr_synchronize(abr_handle h);
+/* Tuning knobs (no effect on results): "two_level_min_n" — particle count from which
+ * abr_update_positions uses the two-level (partition + bin-local sort) build;
+ * "phased_gather" — 0/1. */
+int abr_set_option(abr_handle h, const char *name, double value);
 const char *abr_last_error_string(abr_handle h);
 const char *abr_version(void);
 

@@ -20,10 +20,13 @@ TOL = 1e-12
     (2, 1000, 10, True), (2, 1000, 10, False), (2, 1000, 1, True),
     (3, 1, 10, True), (3, 3, 10, False), (3, 1000, 100, True), (3, 1000, 10, False), (3, 1000, 1, True),
     (3, 5000, 10, True), (3, 100000, 10, True), (2, 100000, 10, False)])
-def test_build_parity(D, N, nn, periodic):
+@pytest.mark.parametrize("two_level", [False, True])
+def test_build_parity(D, N, nn, periodic, two_level):
+    # both build strategies: LSD sort + random gather, and the two-level build
+    # (records partitioned by the top key digit, bin-local passes, L2-local gather)
     rng = np.random.default_rng(100 * D + N + nn)
     pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
-    o, out, p = build_both(pos, -1.0, 1.0, periodic, nn)
+    o, out, p = build_both(pos, -1.0, 1.0, periodic, nn, two_level=two_level)
     assert_build_equal(o, out, p)
 
 
@@ -42,8 +45,9 @@ def test_build_dead_wrap_and_columns():
     o, out, p = build_both(pos, 0.0, 1.0, periodic, 10.0, alive=alive, variables=None)
     assert_build_equal(o, out, p)
     assert 0 < out["n_alive"] < N
-    # now with user columns: every column is gathered by the same order
+    # now with user columns: every column is gathered by the same order (two-level build)
     p2 = ab.Particles(3, N, variables=vars_)
+    p2.set_option("two_level_min_n", 0)
     p2.set("position", torch.from_numpy(pos0.copy()))
     p2.set("alive", torch.from_numpy(alive.copy()))
     cols = {"a": rng.random(N), "v": rng.random((N, 3)), "flag": rng.integers(0, 255, N).astype(np.uint8),
@@ -243,11 +247,12 @@ def test_matvec_rows_not_cols_and_row_radius():
     assert np.array_equal(hs.cpu().numpy().view(np.uint64), hs_o)
 
 
-def test_clustered_cloud():
-    # c4-style clustered cloud at reduced N: heavy buckets, periodic (1,1,0)
+@pytest.mark.parametrize("two_level", [False, True])
+def test_clustered_cloud(two_level):
+    # c4-style clustered cloud at reduced N: heavy buckets (very uneven first-level bins), periodic (1,1,0)
     N = 200000
     pos = synth.clustered_positions(N)
-    o, out, p = build_both(pos, 0.0, 1.0, [True, True, False])
+    o, out, p = build_both(pos, 0.0, 1.0, [True, True, False], two_level=two_level)
     assert_build_equal(o, out, p)
     h = 1.5 * N ** (-1.0 / 3.0)
     _stats_equal(o, out, p, 2 * h)

@@ -6,7 +6,7 @@ import aboria_b200 as ab
 from oracle import oracle as orc
 
 
-def build_both(pos, low, high, periodic, n_leaf=10.0, alive=None, variables=None):
+def build_both(pos, low, high, periodic, n_leaf=10.0, alive=None, variables=None, two_level=None):
     """Runs init_neighbour_search on the oracle (stable sort) and on the GPU
     for the same input; returns (oracle, oracle_out, particles)."""
     pos = np.ascontiguousarray(pos, dtype=np.float64)
@@ -15,6 +15,8 @@ def build_both(pos, low, high, periodic, n_leaf=10.0, alive=None, variables=None
     al = None if alive is None else np.ascontiguousarray(alive, dtype=np.uint8).copy()
     out = o.init_neighbour_search(pos, low, high, periodic, n_leaf, alive=al, sort_mode=orc.SORT_STABLE)
     p = ab.Particles(D, n, variables=variables)
+    if two_level is not None:
+        p.set_option("two_level_min_n", 0 if two_level else 1e18)
     p.set("position", torch.from_numpy(pos.copy()))
     if alive is not None:
         p.set("alive", torch.from_numpy(np.ascontiguousarray(alive, dtype=np.uint8)))
