@@ -97,6 +97,15 @@ constexpr int RS_TILE = RS_THREADS * RS_IPT;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RADIX = 256;
 
+// a set of columns (device pointers + element sizes) passed to kernels by value
+constexpr int GP_MAXC = 8;
+struct GatherCols {
+  int ncols;
+  const uint8_t *src[GP_MAXC];
+  uint8_t *dst[GP_MAXC];
+  uint32_t eb[GP_MAXC];
+};
+
 // Tile table of a SEGMENTED pass (two-level build): tiles never straddle the bins
 // of the first-level partition, and the histogram is laid out [bin][digit][tile in
 // bin] so that one flat exclusive scan yields bin-local destinations.  Null table
@@ -108,6 +117,16 @@ struct TileTab {
   const uint32_t *hstride; // histogram stride between digits
   const uint32_t *total;   // number of tiles in use (device)
 };
+
+__device__ __forceinline__ void copy_element(const uint8_t *__restrict__ s, uint8_t *__restrict__ t, uint32_t eb) {
+  if ((eb & 7u) == 0 && (((uintptr_t)s | (uintptr_t)t) & 7u) == 0) {
+    for (uint32_t w = 0; w < eb / 8; ++w) reinterpret_cast<uint64_t *>(t)[w] = __ldg(reinterpret_cast<const uint64_t *>(s) + w);
+  } else if ((eb & 3u) == 0 && (((uintptr_t)s | (uintptr_t)t) & 3u) == 0) {
+    for (uint32_t w = 0; w < eb / 4; ++w) reinterpret_cast<uint32_t *>(t)[w] = __ldg(reinterpret_cast<const uint32_t *>(s) + w);
+  } else {
+    for (uint32_t w = 0; w < eb; ++w) t[w] = __ldg(s + w);
+  }
+}
 
 struct TileInfo {
   uint32_t start, count, hbase, hstride;
@@ -158,15 +177,16 @@ struct RadixScatterSmem {
   uint32_t s_scan[RADIX / 32];
 };
 
-// DEST_ONLY: instead of moving (key, index) pairs, write for every input element
-// its destination (dest[p], coalesced) — the first level of the two-level build
-// moves whole particle records with it.
-template <bool DEST_ONLY>
+// MOVE_RECORDS (first level of the two-level build): besides (key, index) the
+// whole particle record — every column in `cols` — moves to its bin.  The tile's
+// records are read from a 4096-element window (L1/L2 resident) and written in the
+// sorted order of the tile, i.e. in contiguous runs per bin.
+template <bool MOVE_RECORDS>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ idx_out,
                 const uint32_t *__restrict__ tile_offsets, int shift, uint32_t n,
-                uint32_t num_tiles, const TileTab tt) {
+                uint32_t num_tiles, const TileTab tt, const GatherCols cols) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RadixScatterSmem &S = *reinterpret_cast<RadixScatterSmem *>(rs_raw);
   auto &warp_hist = S.warp_hist;
@@ -198,7 +218,15 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   for (int j = 0; j < RS_IPT; ++j) {
     const bool valid = qbase + j * 32 + lane < ti.count;
     const uint32_t d = (key[j] >> shift) & (RADIX - 1);
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : (RADIX + lane));
+    // lanes holding the same digit: eight independent ballots (pipelined) instead
+    // of MATCH.ANY, whose latency dominated this kernel (profiles/)
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+    if (!valid) peers = 0;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+      const uint32_t vote = __ballot_sync(0xFFFFFFFFu, (d >> bit) & 1u);
+      peers &= ((d >> bit) & 1u) ? vote : ~vote;
+    }
     const uint32_t prev = warp_hist[warp][d];
     __syncwarp();
     if (valid && (peers & lane_lt) == 0) warp_hist[warp][d] = prev + __popc(peers);
@@ -241,19 +269,13 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 
 #pragma unroll
   for (int j = 0; j < RS_IPT; ++j) {
-    const uint32_t p = wbase + j * 32 + lane;
     if (qbase + j * 32 + lane < ti.count) {
       const uint32_t d = (key[j] >> shift) & (RADIX - 1);
       const uint32_t slot = digit_start[d] + warp_hist[warp][d] + rank[j];
-      if (DEST_ONLY) {
-        idx_out[p] = glob_off[d] + (slot - digit_start[d]); // dest[p]
-      } else {
-        s_keys[slot] = key[j];
-        s_idx[slot] = val[j];
-      }
+      s_keys[slot] = key[j];
+      s_idx[slot] = val[j];
     }
   }
-  if (DEST_ONLY) return;
   __syncthreads();
   const uint32_t tile_count = ti.count;
   for (uint32_t s = tid; s < tile_count; s += RS_THREADS) {
@@ -261,7 +283,14 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     const uint32_t d = (k >> shift) & (RADIX - 1);
     const uint32_t out = glob_off[d] + (s - digit_start[d]);
     keys_out[out] = k;
-    idx_out[out] = s_idx[s];
+    const uint32_t src = s_idx[s];
+    idx_out[out] = src;
+    if (MOVE_RECORDS) {
+      for (int c = 0; c < cols.ncols; ++c) {
+        const uint32_t eb = cols.eb[c];
+        copy_element(cols.src[c] + (uint64_t)src * eb, cols.dst[c] + (uint64_t)out * eb, eb);
+      }
+    }
   }
 }
 
@@ -528,13 +557,6 @@ static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)(
 // whole permutation (coalesced, evict-first) and moves only the elements whose
 // source lies in the window — every source sector is fetched from HBM once and
 // reused from L2 by the other elements of its line.
-constexpr int GP_MAXC = 8;
-struct GatherCols {
-  int ncols;
-  const uint8_t *src[GP_MAXC];
-  uint8_t *dst[GP_MAXC];
-  uint32_t eb[GP_MAXC];
-};
 
 __global__ void __launch_bounds__(256)
 k_gather_phased(const GatherCols cols, const int32_t *__restrict__ order, uint64_t n_out,
@@ -554,32 +576,6 @@ k_gather_phased(const GatherCols cols, const int32_t *__restrict__ order, uint64
       for (uint32_t w = 0; w < eb / 4; ++w) reinterpret_cast<uint32_t *>(d)[w] = __ldg(reinterpret_cast<const uint32_t *>(s) + w);
     } else {
       for (uint32_t w = 0; w < eb; ++w) d[w] = __ldg(s + w);
-    }
-  }
-}
-
-// First level of the two-level build: every particle record (all columns, its
-// key and its original index) moves to the bin of its most significant key
-// digit.  Reads are coalesced (original order); the writes advance 256
-// sequential streams, which L2 turns into full-sector HBM writes.
-__global__ void __launch_bounds__(256)
-k_move_by_dest(const GatherCols cols, const uint32_t *__restrict__ dest, const uint32_t *__restrict__ keys_in,
-               uint32_t *__restrict__ keys_out, uint32_t *__restrict__ orig_out, uint32_t n) {
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const uint32_t d = dest[p];
-  keys_out[d] = keys_in[p];
-  orig_out[d] = p;
-  for (int c = 0; c < cols.ncols; ++c) {
-    const uint32_t eb = cols.eb[c];
-    const uint8_t *s = cols.src[c] + (uint64_t)p * eb;
-    uint8_t *t = cols.dst[c] + (uint64_t)d * eb;
-    if ((eb & 7u) == 0 && (((uintptr_t)s | (uintptr_t)t) & 7u) == 0) {
-      for (uint32_t w = 0; w < eb / 8; ++w) reinterpret_cast<uint64_t *>(t)[w] = __ldg(reinterpret_cast<const uint64_t *>(s) + w);
-    } else if ((eb & 3u) == 0 && (((uintptr_t)s | (uintptr_t)t) & 3u) == 0) {
-      for (uint32_t w = 0; w < eb / 4; ++w) reinterpret_cast<uint32_t *>(t)[w] = __ldg(reinterpret_cast<const uint32_t *>(s) + w);
-    } else {
-      for (uint32_t w = 0; w < eb; ++w) t[w] = __ldg(s + w);
     }
   }
 }
@@ -836,6 +832,8 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     int cur = 0;
     uint32_t *hist = h->tile_hist.as<uint32_t>();
     const TileTab dense{nullptr, nullptr, nullptr, nullptr, nullptr};
+    GatherCols no_cols;
+    no_cols.ncols = 0;
     const uint32_t *perm = nullptr;      // two-level: final position -> position in the binned copy
     const uint32_t *orig_tmp = nullptr;  // two-level: binned position -> original index
     GatherCols tmp_cols;                 // two-level: the binned copy of every column
@@ -865,22 +863,20 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
           base += ((reorder->elem_bytes[c] * n + 255) / 256) * 256;
         }
       }
-      uint32_t *dest = h->idx[0].as<uint32_t>();
       uint32_t *keys1 = h->keys[1].as<uint32_t>();
       uint32_t *orig = h->idx[1].as<uint32_t>();
       k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(keys0, n32, top_shift, num_tiles, hist, dense);
       cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
       if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
       ABR_CUDA(h, cudaFuncSetAttribute(k_radix_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixScatterSmem)));
-      k_radix_scatter<true><<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(keys0, nullptr, nullptr, dest, hist, top_shift, n32,
-                                                                                             num_tiles, dense);
-      k_move_by_dest<<<gb, 256, 0, h->stream>>>(src_cols, dest, keys0, keys1, orig, n32);
+      k_radix_scatter<true><<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(keys0, nullptr, keys1, orig, hist, top_shift, n32,
+                                                                                             num_tiles, dense, src_cols);
       // tile table of the segmented passes
       uint32_t *tb = h->tile_tab.as<uint32_t>();
       TileTabW tw{tb, tb + t_bound, tb + 2 * t_bound, tb + 3 * t_bound, tb + 4 * t_bound, tb + 4 * t_bound + 8};
       k_tiletab_bins<<<1, RADIX, 0, h->stream>>>(hist, num_tiles, n32, tw);
       const TileTab seg{tw.start, tw.count, tw.hbase, tw.hstride, tw.total};
-      h->launches += 4;
+      h->launches += 3;
       // ---- level 2: LSD passes over the remaining digits, segmented by bin; they
       //      permute (key, binned position) pairs inside 1/256th of the array ----
       uint32_t *shist = h->seg_hist.as<uint32_t>();
@@ -896,7 +892,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
         e = device_scan<OpSum, false, 0>(h, shist, (uint64_t)RADIX * t_bound, shist, nullptr);
         if (e != cudaSuccess) return check_cuda(h, e, "segmented radix scan");
         k_radix_scatter<false><<<t_bound, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(kin, iin, kbuf[out], ibuf[out], shist, shift, n32,
-                                                                                              num_tiles, seg);
+                                                                                              num_tiles, seg, no_cols);
         h->launches += 2;
         kin = kbuf[out];
         iin = ibuf[out];
@@ -917,7 +913,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
         cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
         if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
         k_radix_scatter<false><<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(kin, iin, kout, iout, hist, shift, n32, num_tiles,
-                                                                                                dense);
+                                                                                                dense, no_cols);
         h->launches += 2;
         cur ^= 1;
       }
