@@ -347,6 +347,17 @@ int abr_pair_stats(abr_handle hh, const double *row_pos, size_t n_rows, int rows
   return abr::run_pair_stats(h, c);
 }
 
+int abr_sparse_assemble(abr_handle hh, const double *row_pos, size_t n_rows, int rows_are_cols, const abr_kernel_desc *k, double radius,
+                        const double *radius_per_row, uint32_t *row_ptr, int32_t *col_idx, double *values, size_t capacity,
+                        uint64_t *nnz_host) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (n_rows > 0 && !row_pos) return abr::set_error(h, ABR_ERR_INVALID, "assemble: null row positions");
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::MatvecCall c{row_pos, n_rows, rows_are_cols, radius, radius_per_row, nullptr, nullptr, nullptr, nullptr, -1};
+  return abr::run_assemble(h, c, k, row_ptr, col_idx, values, capacity, nnz_host);
+}
+
 int abr_last_counters(abr_handle hh, uint64_t counters[4]) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !counters) return ABR_ERR_INVALID;

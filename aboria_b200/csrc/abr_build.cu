@@ -431,6 +431,12 @@ static cudaError_t device_scan(Handle *h, const uint32_t *in, uint64_t m, uint32
   return cudaGetLastError();
 }
 
+int scan_exclusive_u32(Handle *h, uint32_t *data, uint64_t m) {
+  cudaError_t e = device_scan<OpSum, false, 0>(h, data, m, data, nullptr);
+  if (e != cudaSuccess) return check_cuda(h, e, "exclusive scan");
+  return ABR_OK;
+}
+
 // ---------------------------------------------------------------------------
 // k3: run boundaries of the sorted keys.  Equivalent to lower_bound /
 // upper_bound of every bucket id in the sorted key array

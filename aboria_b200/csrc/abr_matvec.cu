@@ -142,6 +142,70 @@ template <int D> static int dispatch_builtin(Handle *h, const abr_matvec_plan &p
   return set_error(h, ABR_ERR_INVALID, "matvec: block_rows/block_cols do not match the kernel");
 }
 
+// ---- assemble (CSR) --------------------------------------------------------
+template <int D> static int dispatch_assemble(Handle *h, const abr_matvec_plan &p, const abr_kernel_desc *k, const uint32_t *row_ptr,
+                                             int32_t *col_idx, double *values) {
+  using namespace functors;
+  int e = -1;
+  switch (k->kernel_id) {
+  case ABR_K_CONST_SUM: e = launch_assemble<D>(p, ConstSum{k->row_vars[0], k->col_vars[0]}, row_ptr, col_idx, values); break;
+  case ABR_K_CONST_SUM_DIFF: e = launch_assemble<D>(p, ConstSumDiff{k->row_vars[0], k->col_vars[0]}, row_ptr, col_idx, values); break;
+  case ABR_K_INV_DIST: e = launch_assemble<D>(p, InvDist{k->params[0]}, row_ptr, col_idx, values); break;
+  case ABR_K_INV_DIST_AA: e = launch_assemble<D>(p, InvDistAA{k->params[0], k->row_vars[0], k->col_vars[0]}, row_ptr, col_idx, values); break;
+  case ABR_K_WENDLAND_C2: e = launch_assemble<D>(p, WendlandC2{k->params[0]}, row_ptr, col_idx, values); break;
+  case ABR_K_LJ_FORCE: e = launch_assemble<D>(p, LJForce<D>{k->params[0], k->params[1]}, row_ptr, col_idx, values); break;
+  case ABR_K_SPH_DENSITY: e = launch_assemble<D>(p, SphDensity<D>{k->params[0], k->params[1], k->params[2]}, row_ptr, col_idx, values); break;
+  case ABR_K_SPH_PRESSURE:
+    e = launch_assemble<D>(p, SphPressure<D>{k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]}, row_ptr, col_idx, values);
+    break;
+  default: return set_error(h, ABR_ERR_INVALID, "assemble: unknown kernel_id");
+  }
+  if (e != 0) return check_cuda(h, (cudaError_t)e, "assemble launch");
+  h->launches += 1;
+  return ABR_OK;
+}
+
+int scan_exclusive_u32(Handle *h, uint32_t *data, uint64_t m); // abr_build.cu
+
+int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint32_t *row_ptr, int32_t *col_idx, double *values,
+                 size_t capacity, uint64_t *nnz_host) {
+  if (!k || !row_ptr) return set_error(h, ABR_ERR_INVALID, "assemble: null pointer");
+  if (c.n_rows >= 0xFFFFFFF0ull) return set_error(h, ABR_ERR_UNSUPPORTED, "assemble: too many rows");
+  ABR_CUDA(h, cudaMemsetAsync(row_ptr, 0, (c.n_rows + 1) * sizeof(uint32_t), h->stream));
+  uint64_t nnz = 0;
+  if (c.n_rows > 0) {
+    // 1. entries per row (pair_stats), 2. exclusive scan -> row_ptr, 3. exact walk fills the rows
+    MatvecCall s = c;
+    s.count = row_ptr;
+    s.hash = nullptr;
+    s.b = nullptr;
+    s.y = nullptr;
+    int rc = run_pair_stats(h, s);
+    if (rc) return rc;
+    // guard against 32-bit overflow of the running sum: total in 64 bits on the host side
+    rc = scan_exclusive_u32(h, row_ptr, c.n_rows + 1);
+    if (rc) return rc;
+    uint32_t last = 0;
+    ABR_CUDA(h, cudaMemcpyAsync(&last, row_ptr + c.n_rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+    nnz = last;
+  }
+  if (nnz_host) *nnz_host = nnz;
+  if (!col_idx || c.n_rows == 0) return ABR_OK; // count only
+  if (capacity < nnz) return set_error(h, ABR_ERR_INVALID, "assemble: capacity smaller than the number of entries");
+  abr_matvec_plan p;
+  MatvecCall w = c;
+  w.force_path = 1;
+  w.count = nullptr;
+  int rc = make_plan(h, w, k->block_rows, &p);
+  if (rc) return rc;
+  switch (h->D) {
+  case 1: return dispatch_assemble<1>(h, p, k, row_ptr, col_idx, values);
+  case 2: return dispatch_assemble<2>(h, p, k, row_ptr, col_idx, values);
+  default: return dispatch_assemble<3>(h, p, k, row_ptr, col_idx, values);
+  }
+}
+
 int run_builtin_matvec(Handle *h, const MatvecCall &c, const abr_kernel_desc *k) {
   if (!k) return set_error(h, ABR_ERR_INVALID, "matvec: null kernel descriptor");
   if (c.n_rows == 0) return ABR_OK;

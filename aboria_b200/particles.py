@@ -290,6 +290,31 @@ class SparseOperator:
         del keep
         return npairs.value if count_pairs else None
 
+    def assemble(self, values=True):
+        """K.assemble(triplets) (src/Kernels.h:653-685) as CSR on the device:
+        returns (row_ptr int32[n_rows+1], col_idx int32[nnz], values float64[nnz, BR, BC] | None)."""
+        cols, rows = self.col_particles, self.row_particles
+        if not cols.searchable:
+            raise AbrError("column particle set has no neighbour search (call init_neighbour_search)")
+        cols._sync_stream()
+        d, keep = self._desc()
+        rpr = None
+        if self.radius_per_row is not None:
+            rpr = torch.as_tensor(self.radius_per_row, dtype=torch.float64, device=cols.device).contiguous()
+        n_rows = rows.size()
+        rp = rows.get("position")
+        row_ptr = torch.zeros(n_rows + 1, dtype=torch.int32, device=cols.device)
+        nnz = C.c_uint64(0)
+        args = (cols._h, _ptr(rp), n_rows, int(rows is cols), C.byref(d), self.radius, _ptr(rpr), _ptr(row_ptr))
+        check(cols._h, cols._lib.abr_sparse_assemble(*args, None, None, 0, C.byref(nnz)))
+        n = nnz.value
+        col_idx = torch.empty(max(n, 1), dtype=torch.int32, device=cols.device)
+        k = self.kernel
+        vals = torch.empty((max(n, 1), k.block_rows, k.block_cols), dtype=torch.float64, device=cols.device) if values else None
+        check(cols._h, cols._lib.abr_sparse_assemble(*args, _ptr(col_idx), _ptr(vals), n, C.byref(nnz)))
+        del keep
+        return row_ptr, col_idx[:n], (vals[:n] if values else None)
+
     def matvec(self, b):
         """y = K * b  (Eigen zeroes y first, src/detail/Operators.h:219-232)."""
         y = torch.zeros(self.rows(), dtype=torch.float64, device=self.col_particles.device)

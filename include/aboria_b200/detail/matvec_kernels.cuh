@@ -127,6 +127,44 @@ __global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, cons
 }
 
 // ---------------------------------------------------------------------------
+// assemble_kernel: KernelSparse::assemble to triplets (src/Kernels.h:653-685) as
+// CSR.  One thread per row walks the reference iterator, so the entries of a row
+// appear in exactly the order the reference pushes its triplets.
+// ---------------------------------------------------------------------------
+template <int D, class F>
+__global__ void __launch_bounds__(128) assemble_kernel(const abr_matvec_plan p, const F f, const uint32_t *__restrict__ row_ptr,
+                                                      int32_t *__restrict__ col_idx, double *__restrict__ values) {
+  constexpr int BR = F::BR, BC = F::BC;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n_rows; i += gridDim.x * blockDim.x) {
+    double r[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) r[d] = p.row_pos[(size_t)i * D + d];
+    const double R = p.radius_per_row ? p.radius_per_row[i] : p.radius;
+    uint32_t k = row_ptr[i];
+    const uint32_t kend = row_ptr[i + 1];
+    search_walk<D>(p.q, r, R, [&](unsigned j, const double *dx, double d2, int) {
+      if (k < kend) {
+        col_idx[k] = (int32_t)j;
+        if (values) {
+          double blk[BR * BC];
+          f(dx, d2, i, j, blk);
+#pragma unroll
+          for (int e = 0; e < BR * BC; ++e) values[(size_t)k * (BR * BC) + e] = blk[e];
+        }
+      }
+      ++k;
+    });
+  }
+}
+
+template <int D, class F> inline int launch_assemble(const abr_matvec_plan &p, const F &f, const uint32_t *row_ptr, int32_t *col_idx,
+                                                     double *values) {
+  const unsigned grid = (unsigned)((p.n_rows + 127) / 128);
+  if (grid > 0) assemble_kernel<D, F><<<grid, 128, 0, p.stream>>>(p, f, row_ptr, col_idx, values);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // tiled_kernel
 // ---------------------------------------------------------------------------
 // does the functor read dx?  (default yes; functors that only need |dx|^2 set

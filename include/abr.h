@@ -174,6 +174,20 @@ int abr_sparse_matvec(abr_handle h, const double *row_pos, size_t n_rows, int ro
                       const double *radius_per_row, const double *b, double *y,
                       uint64_t *n_pairs_host);
 
+/* KernelSparse::assemble to triplets (src/Kernels.h:653-685), as CSR:
+ * row i owns entries row_ptr[i] .. row_ptr[i+1]-1, col_idx[k] is the column
+ * PARTICLE j and values[k*BR*BC ..] its BR x BC block (row major) — i.e. the
+ * triplets (i*BR+ii, j*BC+jj, block(ii,jj)) of the reference, in the reference's
+ * own order within a row (the exact iterator walk).  Two-call protocol:
+ *   col_idx == NULL : count only — fills row_ptr (n_rows+1, device), returns nnz;
+ *   col_idx != NULL : also fills col_idx (capacity >= nnz) and, if non-NULL, values.
+ * Block entries, not scalars: nnz * BR * BC scalar non-zeros (7 / 14 in
+ * tests/operators.h:871, :938).  nnz must be < 2^32. */
+int abr_sparse_assemble(abr_handle h, const double *row_pos, size_t n_rows, int rows_are_cols,
+                        const abr_kernel_desc *kernel_host, double radius, const double *radius_per_row,
+                        uint32_t *row_ptr, int32_t *col_idx, double *values, size_t capacity,
+                        uint64_t *nnz_host);
+
 /* Neighbour-set diagnostics used by the parity tests: per row the number of
  * accepted (j,image) pairs of euclidean_search (src/Search.h:839-845) and an
  * order-independent 64-bit hash of that set.  path 0 = cell-tiled kernel (needs

@@ -676,6 +676,33 @@ uint64_t orc_sparse_matvec(void *h, const double *row_pos, size_t n_rows,
   return total;
 }
 
+// src/Kernels.h:653-685 KernelSparse::assemble(std::vector<Triplet>&): for every
+// row i (serial loop), for every search hit j: one BRxBC block.  Emitted as CSR
+// (row_ptr over block entries, col = particle index j, values row-major blocks),
+// entries of a row in the iterator's own order.  Pass col_idx == NULL to count.
+uint64_t orc_sparse_assemble(void *h, const double *row_pos, size_t n_rows, int kernel_id, const double *params,
+                             const double *const *row_vars, const double *const *col_vars, double radius,
+                             const double *radius_per_row, int BR, int BC, uint32_t *row_ptr, int32_t *col_idx,
+                             double *values) {
+  Oracle *o = static_cast<Oracle *>(h);
+  const int D = o->D;
+  KernelCtx k{kernel_id, D, params, row_vars, col_vars};
+  uint64_t nnz = 0;
+  for (size_t i = 0; i < n_rows; ++i) {
+    row_ptr[i] = (uint32_t)nnz;
+    const double R = radius_per_row ? radius_per_row[i] : radius;
+    euclidean_search(*o, row_pos + i * D, R, [&](unsigned j, const double *dx, int) {
+      if (col_idx) {
+        col_idx[nnz] = (int32_t)j;
+        if (values) eval_kernel(k, dx, i, j, values + nnz * (size_t)(BR * BC));
+      }
+      ++nnz;
+    });
+  }
+  row_ptr[n_rows] = (uint32_t)nnz;
+  return nnz;
+}
+
 // brute force of tests/neighbours.h:739-764: counts j with
 // squaredNorm(pj - pi - image*(max-min)) <= r2 over 3^D images (periodic) or
 // the single image (non periodic).  NOTE the operation order differs from the

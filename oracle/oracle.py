@@ -56,6 +56,8 @@ def lib():
         L.orc_pair_stats.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_sparse_matvec.restype = C.c_uint64
         L.orc_sparse_matvec.argtypes = [vp, dp, C.c_size_t, C.c_int, dp, C.POINTER(dp), C.POINTER(dp), C.c_double, dp, C.c_int, C.c_int, dp, dp, C.c_int]
+        L.orc_sparse_assemble.restype = C.c_uint64
+        L.orc_sparse_assemble.argtypes = [vp, dp, C.c_size_t, C.c_int, dp, C.POINTER(dp), C.POINTER(dp), C.c_double, dp, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), dp]
         L.orc_brute_force_counts.argtypes = [C.c_int, dp, C.c_size_t, dp, dp, C.c_int, C.c_double, C.POINTER(C.c_uint32)]
         L.orc_max_threads.restype = C.c_int
         _LIB = L
@@ -213,6 +215,30 @@ class Oracle:
         rpr = _f64(radius_per_row) if radius_per_row is not None else None
         npairs = lib().orc_sparse_matvec(self.h, _dp(row_pos), n_rows, int(kernel_id), _dp(params), RV, CV, float(radius), _dp(rpr), BR, BC, _dp(b), _dp(y), int(nthreads))
         return y, int(npairs)
+
+
+def _assemble(self, row_pos, kernel_id, params, radius, BR=1, BC=1, row_vars=(), col_vars=(), radius_per_row=None):
+    """K.assemble(triplets) (src/Kernels.h:653-685) as CSR: (row_ptr, col_idx, values[nnz,BR,BC])"""
+    row_pos = _f64(row_pos)
+    n_rows = row_pos.shape[0]
+    params = _f64(params if len(params) else [0.0])
+    rv = [_f64(v) for v in row_vars]
+    cv = [_f64(v) for v in col_vars]
+    dpp = C.POINTER(C.c_double)
+    RV = (dpp * max(1, len(rv)))(*[_dp(v) for v in rv])
+    CV = (dpp * max(1, len(cv)))(*[_dp(v) for v in cv])
+    rpr = _f64(radius_per_row) if radius_per_row is not None else None
+    row_ptr = np.zeros(n_rows + 1, dtype=np.uint32)
+    u32p, i32p = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    args = (self.h, _dp(row_pos), n_rows, int(kernel_id), _dp(params), RV, CV, float(radius), _dp(rpr), BR, BC, row_ptr.ctypes.data_as(u32p))
+    nnz = lib().orc_sparse_assemble(*args, None, None)
+    col = np.zeros(max(nnz, 1), dtype=np.int32)
+    vals = np.zeros((max(nnz, 1), BR, BC), dtype=np.float64)
+    lib().orc_sparse_assemble(*args, col.ctypes.data_as(i32p), _dp(vals))
+    return row_ptr, col[:nnz], vals[:nnz]
+
+
+Oracle.assemble = _assemble
 
 
 def max_threads():

@@ -381,3 +381,38 @@ def test_c4_sph_clustered_16m_properties():
     subn = sub.cpu().numpy()[::4]
     y_o, _ = o.sparse_matvec(ps[subn], orc.K_SPH_DENSITY, [h, 1.0 / N, 21.0 / (256.0 * np.pi)], r, x.cpu().numpy())
     assert rel_l2(Kx.cpu().numpy()[subn], y_o) <= TOL
+
+
+def test_assemble_csr_vs_oracle():
+    # KernelSparse::assemble (src/Kernels.h:653-685): identical
+    # sparsity structure and entry order, values to 1e-14
+    rng = np.random.default_rng(21)
+    for D, periodic, N in ((3, True, 6000), (2, False, 8000)):
+        pos = rng.random((N, D))
+        o, out, p = build_both(pos, 0.0, 1.0, periodic)
+        side = o.grid()[1][0]
+        r = 1.2 * side
+        op = ab.create_sparse_operator(p, p, r, K.inv_dist(0.1))
+        rp, col, val = op.assemble()
+        rp_o, col_o, val_o = o.assemble(out["pos"], orc.K_INV_DIST, [0.1], r)
+        assert np.array_equal(rp.cpu().numpy().view(np.uint32), rp_o)
+        assert np.array_equal(col.cpu().numpy(), col_o)
+        assert np.allclose(val.cpu().numpy(), val_o, rtol=1e-14, atol=0)
+        # the assembled matrix reproduces the matrix-free product
+        b = synth.vector(N)
+        y = (op * torch.from_numpy(b).to(p.device)).cpu().numpy()
+        rows = np.repeat(np.arange(N), np.diff(rp_o.astype(np.int64)))
+        y_csr = np.zeros(N)
+        np.add.at(y_csr, rows, val.cpu().numpy()[:, 0, 0] * b[col_o])
+        assert rel_l2(y, y_csr) <= TOL
+    # golden: tests/operators.h:871 (7 block entries), :938 (14 scalars for the 2x1 operator)
+    diameter = 0.1
+    p = ab.Particles(3, 3, variables={"scalar1": torch.float64, "scalar2": torch.float64})
+    p.set("position", torch.tensor([[0, 0, 0], [diameter * 0.9, 0, 0], [diameter * 1.8, 0, 0]], dtype=torch.float64))
+    p.set("scalar1", torch.full((3,), 1.0, dtype=torch.float64))
+    p.set("scalar2", torch.full((3,), 2.0, dtype=torch.float64))
+    p.init_neighbour_search(-1.0, 1.0, False)
+    rp, col, val = ab.create_sparse_operator(p, p, diameter, K.const_sum("scalar1", "scalar2")).assemble()
+    assert col.numel() == 7 and bool((val == 3.0).all())
+    rp2, col2, val2 = ab.create_sparse_operator(p, p, diameter, K.const_sum_diff("scalar1", "scalar2")).assemble()
+    assert col2.numel() * 2 == 14 and bool((val2[:, 0, 0] == 3.0).all()) and bool((val2[:, 1, 0] == -1.0).all())

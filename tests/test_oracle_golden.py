@@ -182,3 +182,26 @@ def test_enforce_domain_and_dead():
     assert p[0, 0] == 0.25 and p[1, 0] == 0.75 and p[5, 0] == 0.75
     assert sorted(out["order"].tolist()) == [0, 1, 4, 5]
     assert out["n_alive"] == 4
+
+
+def test_sparse_operator_assemble_golden():
+    # tests/operators.h:852-873: C.assemble(dense / sparse): 7 block entries, all equal to 3;
+    # the 2x1 operator has 14 scalar non-zeros (tests/operators.h:934-938)
+    diameter = 0.1
+    pos = np.array([[0, 0, 0], [diameter * 0.9, 0, 0], [diameter * 1.8, 0, 0]], dtype=np.float64)
+    o = orc.Oracle(3)
+    out = o.init_neighbour_search(pos, -1.0, 1.0, False)
+    s1, s2 = np.full(3, 1.0), np.full(3, 2.0)
+    rp, col, val = o.assemble(out["pos"], orc.K_CONST_SUM, [], diameter, row_vars=[s1], col_vars=[s2])
+    assert len(col) == 7 and np.all(val == 3.0)
+    dense = np.zeros((3, 3))
+    for i in range(3):
+        for k in range(rp[i], rp[i + 1]):
+            dense[i, col[k]] = val[k, 0, 0]
+    assert np.array_equal(dense, np.array([[3, 3, 0], [3, 3, 3], [0, 3, 3.0]]))
+    rp2, col2, val2 = o.assemble(out["pos"], orc.K_CONST_SUM_DIFF, [], diameter, BR=2, BC=1, row_vars=[s1], col_vars=[s2])
+    assert len(col2) * 2 == 14 and np.all(val2[:, 0, 0] == 3.0) and np.all(val2[:, 1, 0] == -1.0)
+    # assembled matrix times vector equals the matrix-free product (tests/operators.h:866-869)
+    v = np.array([1.0, 2.0, 3.0])
+    y, _ = o.sparse_matvec(out["pos"], orc.K_CONST_SUM, [], diameter, v, row_vars=[s1], col_vars=[s2])
+    assert np.array_equal(dense @ v, y)
