@@ -88,6 +88,7 @@ int abr_destroy(abr_handle hh) {
   h->bucket_begin.release();
   h->bucket_end.release();
   h->danger_list.release();
+  h->posb.release();
   if (h->d_scalars) cudaFree(h->d_scalars);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   delete h;

@@ -73,6 +73,7 @@ struct Handle {
   size_t two_level_min_n = (size_t)1 << 20;  // use the two-level build from this many particles (abr_set_option)
   DevBuf bucket_begin, bucket_end;
   DevBuf danger_list;
+  DevBuf posb; // packed (x, y, z, b) records of the column particles for the tiled product
   DevScalars *d_scalars = nullptr;
   DevScalars *h_scalars = nullptr; // pinned mirror
   const uint32_t *sorted_keys = nullptr;

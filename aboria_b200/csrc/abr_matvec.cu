@@ -8,9 +8,24 @@
 
 namespace abr {
 
+// (x, y, z, b) records for the tiled kernel: the drain gathers position and b of a
+// column particle with ONE 256-bit load instead of four scattered 8-byte loads
+// (the LSU data pipe was the binding limit, profiles/r1m_*).  Costs one streaming
+// pass (64 B/particle) per product.
+template <int D> __global__ void __launch_bounds__(256) k_pack_posb(const double *__restrict__ pos, const double *__restrict__ b, double *__restrict__ posb, uint32_t n) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double r[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int d = 0; d < D; ++d) r[d] = pos[(size_t)j * D + d];
+  if (b) r[3] = b[j];
+  double4 v = make_double4(r[0], r[1], r[2], r[3]);
+  reinterpret_cast<double4 *>(posb)[j] = v;
+}
+
 // Fills the plan: picks the tiled kernel when its preconditions hold, and the
 // rounding-safety margins that decide which rows go to the exact walk.
-static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p) {
+static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p, int BC = 1) {
   if (!h->built) return set_error(h, ABR_ERR_STATE, "matvec: cell list has not been built");
   if (!h->pos_sorted && h->n_sorted > 0) return set_error(h, ABR_ERR_STATE, "matvec: abr_query_set_particles not called");
   if (c.n_rows >= 0xFFFFFFFFull) return set_error(h, ABR_ERR_UNSUPPORTED, "matvec: too many rows");
@@ -94,6 +109,19 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p)
     p->danger_list = h->danger_list.as<uint32_t>();
     p->danger_capacity = (uint32_t)c.n_rows;
     ABR_CUDA(h, cudaMemsetAsync(&h->d_scalars->work_counter, 0, 2 * sizeof(uint32_t), h->stream));
+    // packed column records; b rides along when the block has one column
+    ABR_CUDA(h, h->posb.reserve((size_t)h->n_sorted * 4 * sizeof(double) + 32));
+    double *posb = h->posb.as<double>();
+    const uint32_t n32 = (uint32_t)h->n_sorted;
+    const double *bpack = (BC == 1 && c.b) ? c.b : nullptr;
+    const unsigned gb = (n32 + 255) / 256;
+    switch (D) {
+    case 1: k_pack_posb<1><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32); break;
+    case 2: k_pack_posb<2><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32); break;
+    default: k_pack_posb<3><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32); break;
+    }
+    h->launches += 1;
+    p->posb = posb;
   }
   (void)BR;
   return ABR_OK;
@@ -211,7 +239,7 @@ int run_builtin_matvec(Handle *h, const MatvecCall &c, const abr_kernel_desc *k)
   if (c.n_rows == 0) return ABR_OK;
   if (!c.row_pos || !c.b || !c.y) return set_error(h, ABR_ERR_INVALID, "matvec: null pointer");
   abr_matvec_plan p;
-  int rc = make_plan(h, c, k->block_rows, &p);
+  int rc = make_plan(h, c, k->block_rows, &p, k->block_cols);
   if (rc) return rc;
   switch (h->D) {
   case 1: return dispatch_builtin<1>(h, p, k);
@@ -239,9 +267,8 @@ int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, cons
   if (!launch || !functor) return set_error(h, ABR_ERR_INVALID, "custom matvec: null launcher/functor");
   if (c.n_rows == 0) return ABR_OK;
   if (!c.row_pos || !c.b || !c.y) return set_error(h, ABR_ERR_INVALID, "matvec: null pointer");
-  (void)BC;
   abr_matvec_plan p;
-  int rc = make_plan(h, c, BR, &p);
+  int rc = make_plan(h, c, BR, &p, BC);
   if (rc) return rc;
   const int e = launch(&p, functor);
   if (e != 0) return check_cuda(h, (cudaError_t)e, "custom matvec launch");

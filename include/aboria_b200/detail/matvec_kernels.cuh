@@ -44,6 +44,7 @@ struct abr_matvec_plan {
   const double *b;
   double *y;
   // tiled path
+  const double *posb;      // packed (x, y, z, b) per column particle, 32-byte records (b only when BC == 1)
   int use_tiled;
   int w[abr::MAXD];        // stencil half width per dimension
   int trim;                // some w >= 2: trim the stencil by distance (nothing to trim when all w == 1)
@@ -222,8 +223,18 @@ __device__ __forceinline__ int reach_last_dim(double r2, double gap2, double sid
 // divide, the user's math) runs at full lane utilisation instead of on the ~15 %
 // of lanes that pass the cut-off test.  dx and |dx|^2 are recomputed here with
 // the same operations in the same order as in the test.
+// one 32-byte record (x, y, z, b) per lane: a single 256-bit load (LDG.E.256, sm_100)
+__device__ __forceinline__ void ld_rec(const double *rec, double &x, double &y, double &z, double &w) {
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(rec));
+  x = __longlong_as_double((long long)a);
+  y = __longlong_as_double((long long)b);
+  z = __longlong_as_double((long long)c);
+  w = __longlong_as_double((long long)d);
+}
+
 struct DrainCtx {
-  const double *pos;
+  const double *pos; // packed records (plan.posb)
   const double *b;
   double r2lo;
   double r2;
@@ -263,15 +274,21 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
       j[u] = ent >> ROW_BITS;
       i[u] = ent & ((1u << ROW_BITS) - 1u);
     }
-    // all global loads first
+    // all global loads first: one 256-bit load brings the candidate's position and b
     double pj[U][D], bj[U][BC];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      double rec[4];
+      ld_rec(p.pos + (size_t)j[u] * 4, rec[0], rec[1], rec[2], rec[3]);
 #pragma unroll
-      for (int d = 0; d < D; ++d) pj[u][d] = p.pos[(size_t)j[u] * D + d];
+      for (int d = 0; d < D; ++d) pj[u][d] = rec[d];
       if (!STATS) {
+        if (BC == 1) {
+          bj[u][0] = rec[3];
+        } else {
 #pragma unroll
-        for (int c = 0; c < BC; ++c) bj[u][c] = p.b[(size_t)j[u] * BC + c];
+          for (int c = 0; c < BC; ++c) bj[u][c] = p.b[(size_t)j[u] * BC + c];
+        }
       }
     }
 #pragma unroll
@@ -427,7 +444,8 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
   for (int d = 1; d < D; ++d) per_layer *= (uint32_t)g.size[d];
   const uint32_t first_cell = (D > 1 ? (uint32_t)g.own_lo * per_layer : 0u);
   const uint32_t own_cells = (D > 1 ? (uint32_t)g.own_n * per_layer : g.ncells);
-  const DrainCtx dc{p.q.pos, p.b, p.r2lo, p.r2};
+  const DrainCtx dc{p.posb, p.b, p.r2lo, p.r2};
+  const double *__restrict__ posb = p.posb;
   const float pre_r2 = p.pre_r2;
 
   while (true) {
@@ -559,8 +577,10 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
               for (int step = 16; step > 0; step >>= 1)
                 if (sm.run_pref[rho + step - 1] <= ks) rho += step;
               jj[h] = ks + sm.run_delta[rho];
+              double rec[4];
+              ld_rec(posb + (size_t)jj[h] * 4, rec[0], rec[1], rec[2], rec[3]);
 #pragma unroll
-              for (int d = 0; d < D; ++d) pj[h][d] = (float)(pos[(size_t)jj[h] * D + d] - origin[d]);
+              for (int d = 0; d < D; ++d) pj[h][d] = (float)(rec[d] - origin[d]);
             }
             test_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
                                    image_id0, r0, cnt);
@@ -628,9 +648,10 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
                     jj[h] = min(cb + 32 * h + lane, je - 1);
                     vv[h] = cb + 32 * h + lane < je;
                     // pre-filter only: move the candidate by -image*L instead of the row by +image*L
+                    double rec[4];
+                    ld_rec(posb + (size_t)jj[h] * 4, rec[0], rec[1], rec[2], rec[3]);
 #pragma unroll
-                    for (int d = 0; d < D; ++d)
-                      pj[h][d] = (float)((pos[(size_t)jj[h] * D + d] - (double)img[d] * g.L[d]) - origin[d]);
+                    for (int d = 0; d < D; ++d) pj[h][d] = (float)((rec[d] - (double)img[d] * g.L[d]) - origin[d]);
                   }
                   test_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
                                          image_id, r0, cnt);
