@@ -32,6 +32,7 @@ SIGNATURES = {
     "abr_destroy": (C.c_int, [C.c_void_p]),
     "abr_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "abr_synchronize": (C.c_int, [C.c_void_p]),
+    "abr_check_async": (C.c_int, [C.c_void_p]),
     "abr_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "abr_last_error_string": (C.c_char_p, [C.c_void_p]),
     "abr_version": (C.c_char_p, []),

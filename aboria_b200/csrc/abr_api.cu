@@ -116,6 +116,20 @@ int abr_set_option(abr_handle hh, const char *name, double value) {
   return ABR_OK;
 }
 
+int abr_check_async(abr_handle hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->async_pending_n == 0) return ABR_OK;
+  const size_t n = h->async_pending_n;
+  h->async_pending_n = 0;
+  if (h->h_scalars->n_alive != n)
+    return abr::set_error(h, ABR_ERR_STATE, "asynchronous update_positions: particles died; results of this update are invalid, redo it synchronously");
+  if (h->h_scalars->n_aliased != 0 || h->h_scalars->n_outside != 0)
+    return abr::set_error(h, ABR_ERR_STATE, "asynchronous update_positions: a bucket index overflowed; redo the update synchronously");
+  return ABR_OK;
+}
+
 int abr_synchronize(abr_handle hh) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return ABR_ERR_INVALID;
@@ -288,8 +302,8 @@ int abr_update_positions(abr_handle hh, double *pos, uint8_t *alive, size_t n, i
   if (pos_col < 0 && n > 0) return abr::set_error(h, ABR_ERR_INVALID, "update_positions: the position column must be among the columns");
   ABR_CUDA(h, cudaSetDevice(h->device));
   abr::ReorderSpec spec{ncols, src, dst, elem_bytes};
-  size_t n_alive = 0;
-  int rc = abr::build_celllist(h, pos, alive, n, order_out, &n_alive, n > 0 ? &spec : nullptr);
+  size_t n_alive = n;
+  int rc = abr::build_celllist(h, pos, alive, n, order_out, n_alive_host ? &n_alive : nullptr, n > 0 ? &spec : nullptr);
   if (rc) return rc;
   if (n_alive_host) *n_alive_host = n_alive;
   // update_iterators: the query now reads the reordered position column

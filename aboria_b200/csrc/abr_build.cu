@@ -963,7 +963,17 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
       }
       if (rc) return rc;
     }
+    if (!n_alive_host && reorder && !presorted) {
+      // ASYNCHRONOUS update (caller passed no n_alive_host): nothing is read back now.
+      // The caller asserts that no particle dies; abr_check_async verifies it later.
+      h->n_aliased = 0;
+      h->n_alive_last = n;
+      h->async_pending_n = n;
+      h->built = true;
+      return ABR_OK;
+    }
     ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->async_pending_n = 0;
     const size_t n_alive = h->h_scalars->n_alive;
     h->n_aliased = h->h_scalars->n_aliased;
     if (h->h_scalars->n_outside != 0)

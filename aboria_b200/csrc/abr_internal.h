@@ -79,6 +79,7 @@ struct Handle {
   const uint32_t *sorted_keys = nullptr;
   uint64_t ncells = 0;
   bool built = false;
+  size_t async_pending_n = 0; // particle count of an unverified asynchronous update (0: none)
   uint32_t n_aliased = 0;
 
   // query binding

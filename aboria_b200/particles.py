@@ -118,14 +118,14 @@ class Particles:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(self._h, self._lib.abr_set_stream(self._h, C.c_void_p(stream)))
 
-    def init_neighbour_search(self, low, high, periodic, n_particles_in_leaf=10.0):
+    def init_neighbour_search(self, low, high, periodic, n_particles_in_leaf=10.0, assume_all_alive=False):
         D = self.D
         low = np.ascontiguousarray(np.broadcast_to(np.asarray(low, dtype=np.float64), (D,)))
         high = np.ascontiguousarray(np.broadcast_to(np.asarray(high, dtype=np.float64), (D,)))
         per = np.ascontiguousarray(np.broadcast_to(np.asarray(periodic), (D,)).astype(np.uint8))
         check(self._h, self._lib.abr_domain_set(self._h, D, low.ctypes.data, high.ctypes.data, per.ctypes.data, float(n_particles_in_leaf)))
         self.low, self.high, self.periodic = low, high, per
-        self.update_positions()
+        self.update_positions(assume_all_alive=assume_all_alive)
         self.searchable = True
 
     def force_grid(self, low, high, periodic, size):
@@ -146,8 +146,14 @@ class Particles:
         check(self._h, self._lib.abr_domain_get(self._h, size.ctypes.data, side.ctypes.data, C.byref(nb)))
         return size, side, nb.value
 
-    def update_positions(self):
-        """wrap / kill, build the ordered cell list, reorder every column."""
+    def check_async(self):
+        """verify the last asynchronous update (raises if a particle died)"""
+        check(self._h, self._lib.abr_check_async(self._h))
+
+    def update_positions(self, assume_all_alive=False):
+        """wrap / kill, build the ordered cell list, reorder every column.
+        assume_all_alive=True: asynchronous form (no host round trip); the caller
+        asserts no particle leaves the domain and calls check_async() later."""
         self._sync_stream()
         n = self.size()
         pos = self.columns["position"]
@@ -162,8 +168,9 @@ class Particles:
         SP = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
         DP = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
         EB = (C.c_size_t * nc)(*[t.element_size() * int(np.prod(t.shape[1:], dtype=np.int64)) for t in src])
-        check(self._h, self._lib.abr_update_positions(self._h, _ptr(pos), _ptr(alive), n, nc, SP, DP, EB, _ptr(order), C.byref(n_alive)))
-        na = n_alive.value
+        check(self._h, self._lib.abr_update_positions(self._h, _ptr(pos), _ptr(alive), n, nc, SP, DP, EB, _ptr(order),
+                                                      None if assume_all_alive else C.byref(n_alive)))
+        na = n if assume_all_alive else n_alive.value
         self._order = order[:na]
         self._other = dict(zip(names, src))
         self.columns = {k: t[:na] for k, t in zip(names, dst)}

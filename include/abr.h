@@ -78,6 +78,10 @@ int abr_create(abr_handle *out, int device, void *stream);
 int abr_destroy(abr_handle h);
 int abr_set_stream(abr_handle h, void *stream);
 int abr_synchronize(abr_handle h);
+/* Synchronises and verifies the last asynchronous abr_update_positions: error if
+ * a particle died or a bucket index overflowed (then the update must be redone
+ * with n_alive_host != NULL). */
+int abr_check_async(abr_handle h);
 /* Tuning knobs (no effect on results): "two_level_min_n" — particle count from which
  * abr_update_positions uses the two-level (partition + bin-local sort) build;
  * "phased_gather" — 0/1. */
@@ -151,7 +155,11 @@ int abr_gather_columns(abr_handle h, int ncols, const void *const *src_host, voi
  * the gathered position column.  The reorder is enqueued behind the build on
  * the device (bounded by the device-side alive count), so the whole update
  * costs ONE host synchronisation — the one that returns n_alive_host.
- * dst columns must have room for n elements; their first n_alive are valid. */
+ * dst columns must have room for n elements; their first n_alive are valid.
+ * n_alive_host == NULL selects the ASYNCHRONOUS form: nothing is read back, the
+ * call returns after enqueueing and the handle assumes every particle stays
+ * alive (n_alive == n).  The caller must confirm that with abr_check_async
+ * before trusting anything computed from this update. */
 int abr_update_positions(abr_handle h, double *pos, uint8_t *alive, size_t n, int ncols,
                          const void *const *src_host, void *const *dst_host,
                          const size_t *elem_bytes_host, int32_t *order_out, size_t *n_alive_host);
