@@ -50,7 +50,7 @@ int abr_create(abr_handle *out, int device, void *stream) {
   h->device = device;
   h->stream = static_cast<cudaStream_t>(stream);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaMalloc(&h->d_scalars, sizeof(abr::DevScalars))) != cudaSuccess ||
-      (e = cudaMallocHost(&h->h_scalars, sizeof(abr::DevScalars))) != cudaSuccess) {
+      (e = cudaMallocHost(&h->h_scalars, 3 * sizeof(abr::DevScalars))) != cudaSuccess) {
     g_create_error = std::string("abr_create: ") + cudaGetErrorString(e);
     delete h;
     return ABR_ERR_CUDA;

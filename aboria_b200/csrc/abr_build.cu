@@ -811,8 +811,12 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     memset(&init, 0, sizeof(init));
     init.n_alive = n32;
     init.n_incell = n32;
-    *h->h_scalars = init;
-    ABR_CUDA(h, cudaMemcpyAsync(h->d_scalars, h->h_scalars, sizeof(DevScalars), cudaMemcpyHostToDevice, h->stream));
+    // the initial values travel through their own pinned slots (h_scalars[1], [2],
+    // alternating): in the asynchronous mode the read-back of the previous build
+    // (into h_scalars[0]) and the previous upload may still be in flight
+    h->init_slot ^= 1;
+    h->h_scalars[1 + h->init_slot] = init;
+    ABR_CUDA(h, cudaMemcpyAsync(h->d_scalars, &h->h_scalars[1 + h->init_slot], sizeof(DevScalars), cudaMemcpyHostToDevice, h->stream));
 
     uint32_t *keys0 = h->keys[0].as<uint32_t>();
     const unsigned gb = grid_for(n, 256);

@@ -75,7 +75,8 @@ struct Handle {
   DevBuf danger_list;
   DevBuf posb; // packed (x, y, z, b) records of the column particles for the tiled product
   DevScalars *d_scalars = nullptr;
-  DevScalars *h_scalars = nullptr; // pinned mirror
+  DevScalars *h_scalars = nullptr; // pinned: [0] read-back mirror, [1], [2] alternating slots for initial values
+  int init_slot = 0;
   const uint32_t *sorted_keys = nullptr;
   uint64_t ncells = 0;
   bool built = false;
