@@ -104,6 +104,12 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
       return set_error(h, ABR_ERR_INVALID, "tiled path not applicable for this radius / grid");
   }
   p->use_tiled = tiled ? 1 : 0;
+  {
+    // small grids: hand out single buckets so that every resident warp gets work
+    const uint64_t warps = (uint64_t)h->sm_count * 28;
+    uint64_t gsz = p->q.g.ncells / (4 * warps);
+    p->grab = (uint32_t)(gsz < 1 ? 1 : (gsz > 8 ? 8 : gsz));
+  }
   if (tiled) {
     ABR_CUDA(h, h->danger_list.reserve((size_t)c.n_rows * sizeof(uint32_t)));
     p->danger_list = h->danger_list.as<uint32_t>();

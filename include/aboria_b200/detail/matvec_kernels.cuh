@@ -47,6 +47,7 @@ struct abr_matvec_plan {
   const double *posb;      // packed (x, y, z, b) per column particle, 32-byte records (b only when BC == 1)
   int use_tiled;
   int w[abr::MAXD];        // stencil half width per dimension
+  uint32_t grab;           // consecutive buckets a warp claims per scheduler step (1..8)
   int trim;                // some w >= 2: trim the stencil by distance (nothing to trim when all w == 1)
   double r2, r2lo;         // cut-off^2 and the "rounding sensitive" lower edge
   float pre_r2;            // fp32 pre-filter threshold: r2 * (1 + tol), never rejects a pair the exact test accepts
@@ -203,7 +204,7 @@ template <int D, class F, bool STATS> struct WarpSmem {
   uint32_t pad_[3];
 };
 
-constexpr uint32_t TILED_GRAB = 8; // consecutive buckets a warp claims per scheduler step
+constexpr uint32_t TILED_GRAB = 8; // most consecutive buckets a warp claims per scheduler step (plan.grab)
 
 // Stencil trimming.  A neighbour bucket at offset o (in buckets) from the target
 // bucket is at least max(|o|-1, 0) * side away from every point of the target
@@ -451,10 +452,10 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
   while (true) {
     // warp-level dynamic scheduler: no block barrier anywhere in this kernel
     uint32_t grab = 0;
-    if (lane == 0) grab = atomicAdd(p.work_counter, TILED_GRAB);
+    if (lane == 0) grab = atomicAdd(p.work_counter, p.grab);
     grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
     if (grab >= own_cells) break;
-    const uint32_t grab_end = min(grab + TILED_GRAB, own_cells);
+    const uint32_t grab_end = min(grab + p.grab, own_cells);
 
     for (uint32_t cell = first_cell + grab; cell < first_cell + grab_end; ++cell) {
       const uint32_t rb = bbeg[cell], re = bend[cell];
@@ -724,7 +725,7 @@ template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_pl
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILED_THREADS, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
-    const unsigned max_chunks = (p.q.g.ncells + TILED_GRAB * TILED_WARPS - 1) / (TILED_GRAB * TILED_WARPS);
+    const unsigned max_chunks = (p.q.g.ncells + p.grab * TILED_WARPS - 1) / (p.grab * TILED_WARPS);
     unsigned grid = (unsigned)(p.sm_count * per_sm);
     if (grid > max_chunks) grid = max_chunks;
     if (grid < 1) grid = 1;
