@@ -181,7 +181,9 @@ constexpr int ROW_BITS = 4;
 
 template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
-  static constexpr int RB = 1 << ROW_BITS; // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows)
+  // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows); block kernels keep
+  // BR partial-sum tables, so they take 8 rows at a time to stay at 5-6 CTAs/SM
+  static constexpr int RB = NACC == 1 ? (1 << ROW_BITS) : 8;
 };
 
 // per-warp shared memory (a warp works on one target bucket at a time and never
@@ -415,9 +417,9 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
 }
 
 // occupancy target: the shared-memory footprint allows 7 CTAs/SM for scalar kernels
-// (needs <= 73 registers), 3 for D x 1 block kernels
+// (needs <= 73 registers), 5 for D x 1 block kernels
 template <int D, class F, bool STATS>
-__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::NACC == 1 ? 7 : 3))
+__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::NACC == 1 ? 7 : 5))
 tiled_kernel(const abr_matvec_plan p, const F f) {
   constexpr int BR = F::BR;
   constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
