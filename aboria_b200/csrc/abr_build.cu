@@ -586,6 +586,22 @@ k_gather_phased(const GatherCols cols, const int32_t *__restrict__ order, uint64
   }
 }
 
+// Final reorder of the two-level build, all columns in one launch: the permutation
+// is read once per particle and every source element sits in the L2-resident bin of
+// its destination.
+__global__ void __launch_bounds__(256)
+k_gather_fused(const GatherCols cols, const uint32_t *__restrict__ perm, uint32_t n_out, const uint32_t *__restrict__ n_dev) {
+  if (n_dev) n_out = min(n_out, *n_dev);
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_out) return;
+  const uint32_t o = perm[k];
+#pragma unroll 1
+  for (int c = 0; c < cols.ncols; ++c) {
+    const uint32_t eb = cols.eb[c];
+    copy_element(cols.src[c] + (uint64_t)o * eb, cols.dst[c] + (uint64_t)k * eb, eb);
+  }
+}
+
 // Tile table of the segmented passes from the scanned first-level histogram:
 // bin b starts at scanned[b * num_tiles] (digit-major layout, tile 0).
 struct TileTabW {
@@ -848,7 +864,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     const uint32_t *orig_tmp = nullptr;  // two-level: binned position -> original index
     GatherCols tmp_cols;                 // two-level: the binned copy of every column
     tmp_cols.ncols = 0;
-    const bool two_level = reorder && !presorted && passes >= 2 && n >= h->two_level_min_n && reorder->ncols <= GP_MAXC;
+    const bool two_level = reorder && !presorted && passes >= 2 && n >= h->two_level_min_n && reorder->ncols <= GP_MAXC - 1;
     if (two_level) {
       // ---- level 1: stable partition of whole records by the most significant digit ----
       const int top_shift = 8 * (passes - 1);
@@ -948,18 +964,14 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
       if (two_level) {
         // the source of every output element lies in the same 1/256th of the binned
         // copy as the element itself: the random side of this gather is served by L2
-        const void *srcs[GP_MAXC + 1];
-        void *dsts[GP_MAXC + 1];
-        size_t ebs[GP_MAXC + 1];
-        for (int c = 0; c < tmp_cols.ncols; ++c) {
-          srcs[c] = tmp_cols.src[c];
-          dsts[c] = tmp_cols.dst[c];
-          ebs[c] = tmp_cols.eb[c];
-        }
-        srcs[tmp_cols.ncols] = orig_tmp; // m_alive_indices: original index of every sorted particle
-        dsts[tmp_cols.ncols] = order_out;
-        ebs[tmp_cols.ncols] = sizeof(uint32_t);
-        rc = gather_columns(h, tmp_cols.ncols + 1, srcs, dsts, ebs, reinterpret_cast<const int32_t *>(perm), n, &h->d_scalars->n_alive);
+        GatherCols fc = tmp_cols;
+        fc.src[fc.ncols] = reinterpret_cast<const uint8_t *>(orig_tmp); // m_alive_indices: original index of every sorted particle
+        fc.dst[fc.ncols] = reinterpret_cast<uint8_t *>(order_out);
+        fc.eb[fc.ncols] = sizeof(uint32_t);
+        fc.ncols += 1;
+        k_gather_fused<<<gb, 256, 0, h->stream>>>(fc, perm, n32, &h->d_scalars->n_alive);
+        h->launches += 1;
+        rc = ABR_OK;
       } else {
         h->gather_src_n = n;
         rc = gather_columns(h, reorder->ncols, reorder->src, reorder->dst, reorder->elem_bytes, order_out, n, &h->d_scalars->n_alive);

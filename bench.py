@@ -228,7 +228,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     e0.record()
     evs = []
+    host_t = []
     for _ in range(args.steps):
+        th0 = time.perf_counter()
         a, bb_, c = ev(), ev(), ev()
         p.resize_from_positions(pos_unsorted.clone())
         a.record()
@@ -237,6 +239,7 @@ def run_ours(args):
         y = op.matvec(b)
         c.record()
         evs.append((a, bb_, c))
+        host_t.append((time.perf_counter() - th0) * 1e3)
     e1.record()
     torch.cuda.synchronize()
     p.check_async()  # no particle died in the asynchronous updates
@@ -312,6 +315,7 @@ def run_ours(args):
                    "n_particles_per_gpu": n, "n_particles": n, "buckets": ncells, "radius": radius, "pairs_per_matvec": pairs,
                    "l2": "inputs (0.77 GB positions) exceed the 126 MB L2; no flush needed", "rows_recomputed_by_exact_walk": walk_rows},
         "ms_build": ms_build, "ms_matvec": ms_mv, "build_mparticles_per_s": n / (ms_build * 1e-3) / 1e6,
+        "ms_build_min_max": [float(np.min(t_build)), float(np.max(t_build))], "host_enqueue_ms_per_step": float(np.median(host_t)),
         "roofline": roofline, "roofline_fp64": roofline_fp64, "roofline_build": roofline_build,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
