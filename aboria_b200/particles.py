@@ -105,7 +105,17 @@ class Particles:
         """Replace the whole set by n new particles at `pos` (host or device)."""
         pos = torch.as_tensor(pos, dtype=torch.float64)
         n = pos.shape[0]
-        self.columns["position"] = pos.to(self.device, non_blocking=True).contiguous()
+        cur = self.columns.get("position")
+        if cur is not None and cur.shape == pos.shape and cur.is_contiguous():
+            # same size as before: refill the existing buffers (no allocation on the hot path)
+            cur.copy_(pos, non_blocking=True)
+            torch.arange(n, dtype=torch.int64, device=self.device, out=self.columns["id"])
+            self.columns["alive"].fill_(1)
+            for name in self.columns:
+                if name not in ("position", "id", "alive"):
+                    self.columns[name].zero_()
+            return
+        self.columns["position"] = pos.to(self.device, non_blocking=True).contiguous().clone() if pos.device == self.device else pos.to(self.device, non_blocking=True).contiguous()
         self.columns["id"] = torch.arange(n, dtype=torch.int64, device=self.device)
         self.columns["alive"] = torch.ones(n, dtype=torch.uint8, device=self.device)
         for name in list(self.columns):
@@ -158,12 +168,22 @@ class Particles:
         n = self.size()
         pos = self.columns["position"]
         alive = self.columns["alive"]
-        order = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        order = getattr(self, "_order_buf", None)
+        if order is None or order.shape[0] != max(n, 1):
+            order = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+            self._order_buf = order
         n_alive = C.c_size_t(0)
-        # reorder: every column is gathered into the other buffer (room for n), then swapped
+        # reorder: every column is gathered into the other buffer (room for n), then swapped;
+        # the other buffer is kept between calls like the reference's other_data
         names = list(self.columns)
         src = [self.columns[k] for k in names]
-        dst = [torch.empty_like(t) for t in src]
+        dst = []
+        for k, t in zip(names, src):
+            o = self._other.get(k)
+            if o is not None and o.shape == t.shape and o.dtype == t.dtype and o.is_contiguous() and o.data_ptr() != t.data_ptr():
+                dst.append(o)
+            else:
+                dst.append(torch.empty_like(t))
         nc = len(names)
         SP = (C.c_void_p * nc)(*[t.data_ptr() for t in src])
         DP = (C.c_void_p * nc)(*[t.data_ptr() for t in dst])
@@ -322,9 +342,14 @@ class SparseOperator:
         del keep
         return row_ptr, col_idx[:n], (vals[:n] if values else None)
 
-    def matvec(self, b):
-        """y = K * b  (Eigen zeroes y first, src/detail/Operators.h:219-232)."""
-        y = torch.zeros(self.rows(), dtype=torch.float64, device=self.col_particles.device)
+    def matvec(self, b, out=None):
+        """y = K * b  (Eigen zeroes y first, src/detail/Operators.h:219-232).
+        out: optional preallocated result vector (zeroed here)."""
+        if out is None:
+            y = torch.zeros(self.rows(), dtype=torch.float64, device=self.col_particles.device)
+        else:
+            y = out
+            y.zero_()
         self.evaluate(y, b)
         return y
 
