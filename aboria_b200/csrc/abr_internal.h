@@ -126,6 +126,7 @@ struct MatvecCall {
 };
 int run_builtin_matvec(Handle *h, const MatvecCall &c, const abr_kernel_desc *k);
 int run_pair_stats(Handle *h, const MatvecCall &c);
+int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm);
 int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint32_t *row_ptr, int32_t *col_idx, double *values,
                  size_t capacity, uint64_t *nnz_host);
 int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, const void *functor,

@@ -268,6 +268,34 @@ int run_pair_stats(Handle *h, const MatvecCall &c) {
   }
 }
 
+template <int D> static int launch_norm_stats(Handle *h, const abr_matvec_plan &p, int lnorm) {
+  const unsigned grid = (unsigned)((p.n_rows + 127) / 128);
+  switch (lnorm) {
+  case -1: norm_stats_kernel<D, -1><<<grid, 128, 0, p.stream>>>(p); break;
+  case 1: norm_stats_kernel<D, 1><<<grid, 128, 0, p.stream>>>(p); break;
+  case 2: norm_stats_kernel<D, 2><<<grid, 128, 0, p.stream>>>(p); break;
+  default: return set_error(h, ABR_ERR_UNSUPPORTED, "distance_search: norm must be -1 (Chebyshev), 1 (Manhattan) or 2 (Euclidean)");
+  }
+  h->launches += 1;
+  ABR_CUDA(h, cudaGetLastError());
+  return ABR_OK;
+}
+
+int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm) {
+  if (c.n_rows == 0) return ABR_OK;
+  if (!c.row_pos) return set_error(h, ABR_ERR_INVALID, "distance_search: null pointer");
+  abr_matvec_plan p;
+  MatvecCall w = c;
+  w.force_path = 1;
+  int rc = make_plan(h, w, 1, &p);
+  if (rc) return rc;
+  switch (h->D) {
+  case 1: return launch_norm_stats<1>(h, p, lnorm);
+  case 2: return launch_norm_stats<2>(h, p, lnorm);
+  default: return launch_norm_stats<3>(h, p, lnorm);
+  }
+}
+
 int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, const void *functor,
                       int BR, int BC) {
   if (!launch || !functor) return set_error(h, ABR_ERR_INVALID, "custom matvec: null launcher/functor");

@@ -231,6 +231,18 @@ class Particles:
         """tuning knobs of the library (no effect on results), see abr_set_option"""
         check(self._h, self._lib.abr_set_option(self._h, name.encode(), float(value)))
 
+    def distance_search_stats(self, radius, lnorm, queries=None):
+        """distance_search<lnorm> / chebyshev_search (-1) / manhatten_search (1) /
+        euclidean_search (2) from `queries` (default: the particles themselves):
+        per query the neighbour count and pair-set hash."""
+        self._sync_stream()
+        qp = self.columns["position"] if queries is None else torch.as_tensor(queries, dtype=torch.float64, device=self.device).contiguous()
+        n = qp.shape[0]
+        cnt = torch.zeros(n, dtype=torch.int32, device=self.device)
+        hs = torch.zeros(n, dtype=torch.int64, device=self.device)
+        check(self._h, self._lib.abr_distance_search_stats(self._h, _ptr(qp), n, float(radius), None, int(lnorm), _ptr(cnt), _ptr(hs)))
+        return cnt, hs
+
     def probe_fp64_peak(self):
         """measured DFMA throughput of this device in TFLOP/s"""
         self._sync_stream()

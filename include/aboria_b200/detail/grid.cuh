@@ -84,10 +84,24 @@ template <int D> __device__ inline int point_to_bucket(const Grid &g, const doub
 }
 
 // ---------------------------------------------------------------------------
-// lattice_iterator_within_distance<Query,2,IdentityTransform>
+// distance_helper<LNormNumber> (src/detail/Distance.h:46-139) for the norms that
+// round identically on host and device: -1 Chebyshev (max |x|), 1 Manhattan
+// (sum |x|), 2 Euclidean (sum x*x).  p >= 3 goes through std::pow in the
+// reference and is not offered on the device.
+// ---------------------------------------------------------------------------
+template <int LN> struct DistHelper {
+  __host__ __device__ static inline double value(double x) { return LN == 2 ? x * x : fabs(x); }
+  __host__ __device__ static inline double accumulate(double acc, double v) {
+    if (LN == -1) return v > acc ? v : acc;
+    return acc + v;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// lattice_iterator_within_distance<Query,LNormNumber,IdentityTransform>
 // (src/NeighbourSearchBase.h:1720-2009), restated for the device.
 // ---------------------------------------------------------------------------
-template <int D> struct BucketWalk {
+template <int D, int LN = 2> struct BucketWalk {
   const Grid &g;
   double qp[D];
   double half[D];
@@ -106,7 +120,7 @@ template <int D> struct BucketWalk {
     for (int i = 0; i < D; ++i) {
       const double centre = ((double)b[i] + 0.5) * g.side[i] + g.bmin[i];
       const double t = fmax(fabs(centre - qp[i]) - half[i], 0.0);
-      acc = acc + t * t;
+      acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(t));
     }
     return acc;
   }
@@ -118,7 +132,7 @@ template <int D> struct BucketWalk {
       const double dx = 0.5 * (g.bmin[i] + g.bmax[i]) - qp[i];
       const double hl = 0.5 * (g.bmax[i] - g.bmin[i]);
       const double t = fmax(fabs(dx) - hl, 0.0);
-      acc = acc + t * t;
+      acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(t));
     }
     return acc > r2;
   }
@@ -200,15 +214,17 @@ template <int D> struct BucketWalk {
 };
 
 // ---------------------------------------------------------------------------
-// search_iterator<Query,2> (src/Search.h:66-496) as a visitor: image lattice
-// (last dim fastest, :152-159) x buckets near cur = r + image*L (:188-190) x
-// particles of the bucket, accept iff !(sum dx^2 > R2) (:438-446).
-// visit(j, dx, image_linear_index)
+// search_iterator<Query,LNormNumber> (src/Search.h:66-496) as a visitor: image
+// lattice (last dim fastest, :152-159) x buckets near cur = r + image*L
+// (:188-190) x particles of the bucket, accept iff !(norm(dx) > R2) (:438-446),
+// R2 = get_value_to_accumulate(R).  LN = 2: euclidean_search, -1:
+// chebyshev_search, 1: manhatten_search (src/Search.h:794-845).
+// visit(j, dx, accumulated norm, image_linear_index)
 // ---------------------------------------------------------------------------
-template <int D, typename Visit>
+template <int D, int LN = 2, typename Visit>
 __device__ inline void search_walk(const Query &q, const double *r, double R, Visit &&visit) {
   const Grid &g = q.g;
-  const double R2 = R * R;
+  const double R2 = DistHelper<LN>::value(R);
   int img[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) img[i] = g.periodic[i] ? -1 : 0;
@@ -217,7 +233,7 @@ __device__ inline void search_walk(const Query &q, const double *r, double R, Vi
     double cur[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) cur[i] = r[i] + (double)img[i] * g.L[i];
-    for (BucketWalk<D> b(g, cur, R2); b.valid; b.increment()) {
+    for (BucketWalk<D, LN> b(g, cur, R2); b.valid; b.increment()) {
       const int cl = local_collapse<D>(g, b.index);
       if (cl < 0) continue; // bucket layer held by another rank (never within reach of an owned row)
       const unsigned c = (unsigned)cl;
@@ -228,7 +244,7 @@ __device__ inline void search_walk(const Query &q, const double *r, double R, Vi
 #pragma unroll
         for (int i = 0; i < D; ++i) dx[i] = q.pos[(size_t)j * D + i] - cur[i];
 #pragma unroll
-        for (int i = 0; i < D; ++i) acc = acc + dx[i] * dx[i];
+        for (int i = 0; i < D; ++i) acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(dx[i]));
         if (!(acc > R2)) visit(j, dx, acc, image_counter);
       }
     }

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, cons
     if (STATS) {
       uint32_t cnt = 0;
       uint64_t hs = 0;
-      search_walk<D>(p.q, r, R, [&](unsigned j, const double *, double, int image) {
+      search_walk<D, 2>(p.q, r, R, [&](unsigned j, const double *, double, int image) {
         ++cnt;
         hs += mix64((uint64_t)j * 81u + (uint64_t)image);
       });
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, cons
       double acc[BR];
 #pragma unroll
       for (int a = 0; a < BR; ++a) acc[a] = p.y[(size_t)i * BR + a];
-      search_walk<D>(p.q, r, R, [&](unsigned j, const double *dx, double d2, int) {
+      search_walk<D, 2>(p.q, r, R, [&](unsigned j, const double *dx, double d2, int) {
         double blk[BR * BC];
         f(dx, d2, i, j, blk);
 #pragma unroll
@@ -125,6 +125,28 @@ __global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, cons
 #pragma unroll
       for (int a = 0; a < BR; ++a) p.y[(size_t)i * BR + a] = acc[a];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// norm_stats_kernel: distance_search<LN> / chebyshev_search / manhatten_search
+// (src/Search.h:794-831) — per-row neighbour count and pair-set hash
+// ---------------------------------------------------------------------------
+template <int D, int LN>
+__global__ void __launch_bounds__(128) norm_stats_kernel(const abr_matvec_plan p) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n_rows; i += gridDim.x * blockDim.x) {
+    double r[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) r[d] = p.row_pos[(size_t)i * D + d];
+    const double R = p.radius_per_row ? p.radius_per_row[i] : p.radius;
+    uint32_t cnt = 0;
+    uint64_t hs = 0;
+    search_walk<D, LN>(p.q, r, R, [&](unsigned j, const double *, double, int image) {
+      ++cnt;
+      hs += mix64((uint64_t)j * 81u + (uint64_t)image);
+    });
+    if (p.stat_count) p.stat_count[i] = cnt;
+    if (p.stat_hash) p.stat_hash[i] = hs;
   }
 }
 
@@ -144,7 +166,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const abr_matvec_plan p, 
     const double R = p.radius_per_row ? p.radius_per_row[i] : p.radius;
     uint32_t k = row_ptr[i];
     const uint32_t kend = row_ptr[i + 1];
-    search_walk<D>(p.q, r, R, [&](unsigned j, const double *dx, double d2, int) {
+    search_walk<D, 2>(p.q, r, R, [&](unsigned j, const double *dx, double d2, int) {
       if (k < kend) {
         col_idx[k] = (int32_t)j;
         if (values) {

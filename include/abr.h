@@ -204,6 +204,17 @@ int abr_pair_stats(abr_handle h, const double *row_pos, size_t n_rows, int rows_
                    double radius, const double *radius_per_row, int path, uint32_t *count,
                    uint64_t *hash);
 
+/* The p-norm query iterator: distance_search<LNormNumber>, chebyshev_search
+ * (lnorm -1), manhatten_search (1), euclidean_search (2) (src/Search.h:794-845)
+ * from arbitrary query points: per point the number of (j, image) hits and the
+ * order-independent hash of that set.  The device-side iterator itself is
+ * abr::search_walk<D, LN> (include/aboria_b200/detail/grid.cuh) for custom kernels.
+ * p >= 3 is not offered: the reference evaluates it through std::pow, whose
+ * rounding a device pow() does not reproduce. */
+int abr_distance_search_stats(abr_handle h, const double *query_pos, size_t n_queries, double radius,
+                              const double *radius_per_query, int lnorm, uint32_t *count,
+                              uint64_t *hash);
+
 /* Counters of the last abr_sparse_matvec / abr_pair_stats on the tiled path:
  * [0] rows re-done by the exact per-row walk (rounding-sensitive rows),
  * [1] particles whose bucket index overflowed in the last build (forces the

@@ -124,11 +124,30 @@ struct Oracle {
 };
 
 // ---------------------------------------------------------------------------
-// src/NeighbourSearchBase.h:1720-2009 lattice_iterator_within_distance<Query,2,
-// IdentityTransform>; enumerates buckets near a point exactly as the reference
-// does (quadrant by quadrant, row-wise with early exit).
+// src/detail/Distance.h:46-139 distance_helper<LNormNumber>: -1 = Chebyshev
+// (max), 1 = Manhattan, 2 = Euclidean (pow(x,2) == x*x), p >= 3 via
+// std::pow as the reference does.
 // ---------------------------------------------------------------------------
-struct BucketIter {
+template <int LN> struct dist_helper {
+  static inline double value(double x) {
+    if (LN == -1 || LN == 1) return std::abs(x);
+    if (LN == 0) return x != 0;
+    if (LN == 2) return x * x;
+    if (LN == 4) return std::pow(x, LN);
+    return std::abs(std::pow(x, LN));
+  }
+  static inline double accumulate(double accum, double v) {
+    if (LN == -1) return v > accum ? v : accum;
+    return accum + v;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// src/NeighbourSearchBase.h:1720-2009 lattice_iterator_within_distance<Query,
+// LNormNumber,IdentityTransform>; enumerates buckets near a point exactly as the
+// reference does (quadrant by quadrant, row-wise with early exit).
+// ---------------------------------------------------------------------------
+template <int LN = 2> struct BucketIter {
   const Oracle *q;
   int D;
   double query_point[MAXD];
@@ -152,7 +171,7 @@ struct BucketIter {
     for (int i = 0; i < D; ++i)
       dx[i] = std::max(std::abs(dx[i]) - half_bucket_length[i], 0.0);
     double accum = 0; // src/detail/Distance.h:131-138
-    for (int i = 0; i < D; ++i) accum = accum + dx[i] * dx[i];
+    for (int i = 0; i < D; ++i) accum = dist_helper<LN>::accumulate(accum, dist_helper<LN>::value(dx[i]));
     return accum;
   }
 
@@ -165,7 +184,7 @@ struct BucketIter {
       dx[i] = std::max(std::abs(dx[i]) - half_domain_side_length, 0.0);
     }
     double accum = 0;
-    for (int i = 0; i < D; ++i) accum = accum + dx[i] * dx[i];
+    for (int i = 0; i < D; ++i) accum = dist_helper<LN>::accumulate(accum, dist_helper<LN>::value(dx[i]));
     return accum > max_distance2;
   }
 
@@ -209,7 +228,7 @@ struct BucketIter {
   BucketIter(const Oracle *query, const double *point, double max_distance)
       : q(query), D(query->D) {
     for (int i = 0; i < D; ++i) query_point[i] = point[i];
-    max_distance2 = max_distance * max_distance; // pow(x,2) -> x*x (§0.5)
+    max_distance2 = dist_helper<LN>::value(max_distance); // pow(x,2) -> x*x (§0.5)
     if (outside_domain(point)) {
       valid = false;
     } else {
@@ -254,11 +273,11 @@ struct BucketIter {
 // particle in the bucket range: dx = p_j - cur; accept iff !(sum dx^2 > r^2)
 // (src/Search.h:438-446).  Calls visit(j, dx, image_linear_index).
 // ---------------------------------------------------------------------------
-template <typename Visit>
-inline void euclidean_search(const Oracle &q, const double *r, double max_distance,
-                             Visit &&visit) {
+template <int LN, typename Visit>
+inline void distance_search(const Oracle &q, const double *r, double max_distance,
+                            Visit &&visit) {
   const int D = q.D;
-  const double max_distance2 = max_distance * max_distance;
+  const double max_distance2 = dist_helper<LN>::value(max_distance);
   int start[MAXD], end[MAXD], img[MAXD];
   for (int i = 0; i < D; ++i) {
     start[i] = q.periodic[i] ? -1 : 0;
@@ -271,14 +290,14 @@ inline void euclidean_search(const Oracle &q, const double *r, double max_distan
     double cur[MAXD];
     for (int i = 0; i < D; ++i)
       cur[i] = r[i] + img[i] * (q.bmax[i] - q.bmin[i]); // Search.h:188-190
-    for (BucketIter b(&q, cur, max_distance); b.valid; b.increment()) {
+    for (BucketIter<LN> b(&q, cur, max_distance); b.valid; b.increment()) {
       const unsigned c = (unsigned)collapse_index_vector(D, q.size, b.index);
       const unsigned jb = q.bucket_begin[c], je = q.bucket_end[c];
       for (unsigned j = jb; j < je; ++j) {
         double dx[MAXD];
         double accum = 0;
         for (int i = 0; i < D; ++i) dx[i] = q.pos[(size_t)j * D + i] - cur[i];
-        for (int i = 0; i < D; ++i) accum = accum + dx[i] * dx[i];
+        for (int i = 0; i < D; ++i) accum = dist_helper<LN>::accumulate(accum, dist_helper<LN>::value(dx[i]));
         if (!(accum > max_distance2)) visit(j, dx, image_counter);
       }
     }
@@ -291,6 +310,12 @@ inline void euclidean_search(const Oracle &q, const double *r, double max_distan
     }
     if (i < 0) images_left = false;
   }
+}
+
+// euclidean_search (src/Search.h:839-845) = distance_search<2>
+template <typename Visit>
+inline void euclidean_search(const Oracle &q, const double *r, double max_distance, Visit &&visit) {
+  distance_search<2>(q, r, max_distance, visit);
 }
 
 // ---------------------------------------------------------------------------
@@ -593,7 +618,7 @@ long orc_buckets_near_point(void *h, const double *point, double max_distance,
                             int *out, long max_out) {
   Oracle *o = static_cast<Oracle *>(h);
   long count = 0;
-  for (BucketIter b(o, point, max_distance); b.valid; b.increment()) {
+  for (BucketIter<2> b(o, point, max_distance); b.valid; b.increment()) {
     if (out && count < max_out)
       for (int d = 0; d < o->D; ++d) out[count * o->D + d] = b.index[d];
     ++count;
@@ -637,6 +662,35 @@ void orc_pair_stats(void *h, const double *row_pos, size_t n_rows, double radius
     if (count) count[i] = c;
     if (hash) hash[i] = hs;
   }
+}
+
+// distance_search<LNormNumber> / chebyshev_search / manhatten_search
+// (src/Search.h:794-831): per-row neighbour count and pair-set hash for the
+// norms -1 (Chebyshev), 1 (Manhattan), 2 (Euclidean), 3, 4
+int orc_pair_stats_norm(void *h, const double *row_pos, size_t n_rows, double radius, int lnorm, uint32_t *count,
+                        uint64_t *hash) {
+  Oracle *o = static_cast<Oracle *>(h);
+  const int D = o->D;
+  if (lnorm != -1 && lnorm != 1 && lnorm != 2 && lnorm != 3 && lnorm != 4) return 1;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (size_t i = 0; i < n_rows; ++i) {
+    uint32_t c = 0;
+    uint64_t hs = 0;
+    auto visit = [&](unsigned j, const double *, int image) {
+      ++c;
+      hs += mix64((uint64_t)j * 81u + (uint64_t)image);
+    };
+    switch (lnorm) {
+    case -1: distance_search<-1>(*o, row_pos + i * D, radius, visit); break;
+    case 1: distance_search<1>(*o, row_pos + i * D, radius, visit); break;
+    case 3: distance_search<3>(*o, row_pos + i * D, radius, visit); break;
+    case 4: distance_search<4>(*o, row_pos + i * D, radius, visit); break;
+    default: distance_search<2>(*o, row_pos + i * D, radius, visit); break;
+    }
+    if (count) count[i] = c;
+    if (hash) hash[i] = hs;
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------

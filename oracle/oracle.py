@@ -54,6 +54,8 @@ def lib():
         L.orc_search_point.restype = C.c_long
         L.orc_search_point.argtypes = [vp, dp, C.c_double, ip, ip, dp, C.c_long]
         L.orc_pair_stats.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_pair_stats_norm.restype = C.c_int
+        L.orc_pair_stats_norm.argtypes = [vp, dp, C.c_size_t, C.c_double, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_sparse_matvec.restype = C.c_uint64
         L.orc_sparse_matvec.argtypes = [vp, dp, C.c_size_t, C.c_int, dp, C.POINTER(dp), C.POINTER(dp), C.c_double, dp, C.c_int, C.c_int, dp, dp, C.c_int]
         L.orc_sparse_assemble.restype = C.c_uint64
@@ -197,6 +199,17 @@ class Oracle:
         hs = np.zeros(n, dtype=np.uint64)
         rpr = _f64(radius_per_row) if radius_per_row is not None else None
         lib().orc_pair_stats(self.h, _dp(row_pos), n, float(radius), _dp(rpr), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), hs.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return cnt, hs
+
+    def pair_stats_norm(self, row_pos, radius, lnorm):
+        """distance_search<lnorm> (src/Search.h:794-831): count and pair-set hash per row"""
+        row_pos = _f64(row_pos)
+        n = row_pos.shape[0]
+        cnt = np.zeros(n, dtype=np.uint32)
+        hs = np.zeros(n, dtype=np.uint64)
+        rc = lib().orc_pair_stats_norm(self.h, _dp(row_pos), n, float(radius), int(lnorm), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), hs.ctypes.data_as(C.POINTER(C.c_uint64)))
+        if rc:
+            raise ValueError("unsupported norm")
         return cnt, hs
 
     def sparse_matvec(self, row_pos, kernel_id, params, radius, b, BR=1, BC=1, row_vars=(), col_vars=(), radius_per_row=None, y=None, nthreads=0):

@@ -416,3 +416,29 @@ def test_assemble_csr_vs_oracle():
     assert col.numel() == 7 and bool((val == 3.0).all())
     rp2, col2, val2 = ab.create_sparse_operator(p, p, diameter, K.const_sum_diff("scalar1", "scalar2")).assemble()
     assert col2.numel() * 2 == 14 and bool((val2[:, 0, 0] == 3.0).all()) and bool((val2[:, 1, 0] == -1.0).all())
+
+
+@pytest.mark.parametrize("lnorm", [-1, 1, 2])
+def test_distance_search_norms(lnorm):
+    # chebyshev_search / manhatten_search / euclidean_search (src/Search.h:794-845):
+    # identical hit sets to the oracle; Linf on the regular lattice gives the box
+    # counts of tests/neighbours.h:675-684
+    rng = np.random.default_rng(5 + lnorm)
+    for D, periodic, N, r in ((3, True, 3000, 0.25), (2, False, 3000, 0.1), (1, True, 500, 0.05)):
+        pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+        o, out, p = build_both(pos, -1.0, 1.0, periodic)
+        cnt, hs = p.distance_search_stats(r, lnorm)
+        cnt_o, hs_o = o.pair_stats_norm(out["pos"], r, lnorm)
+        assert np.array_equal(cnt.cpu().numpy().view(np.uint32), cnt_o)
+        assert np.array_equal(hs.cpu().numpy().view(np.uint64), hs_o)
+        q = rng.uniform(-1.2, 1.2, size=(200, D))  # queries outside the domain too
+        cq, hq = p.distance_search_stats(r, lnorm, queries=q)
+        cq_o, hq_o = o.pair_stats_norm(q, r, lnorm)
+        assert np.array_equal(cq.cpu().numpy().view(np.uint32), cq_o)
+        assert np.array_equal(hq.cpu().numpy().view(np.uint64), hq_o)
+    if lnorm == -1:
+        n, rr = 20, 2.1
+        idx = np.indices((n,) * 2).reshape(2, -1).T[:, ::-1]
+        o, out, p = build_both(idx.astype(np.float64) + 0.5, 0.0, float(n), True)
+        cnt, _ = p.distance_search_stats(rr, -1)
+        assert bool((cnt == (2 * int(np.floor(rr)) + 1) ** 2).all())

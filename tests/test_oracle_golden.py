@@ -205,3 +205,37 @@ def test_sparse_operator_assemble_golden():
     v = np.array([1.0, 2.0, 3.0])
     y, _ = o.sparse_matvec(out["pos"], orc.K_CONST_SUM, [], diameter, v, row_vars=[s1], col_vars=[s2])
     assert np.array_equal(dense @ v, y)
+
+
+@pytest.mark.parametrize("D,n,r", [(1, 100, 1.5), (2, 50, 1.0001), (2, 50, 1.5), (2, 20, 2.1), (3, 10, 1.9), (3, 10, 1.0001)])
+def test_helper_d_regular_linf_box_counts(D, n, r):
+    # tests/neighbours.h:675-684: Linf (chebyshev) search on the regular lattice finds
+    # (2 floor(r) + 1)^D points
+    idx = np.indices((n,) * D).reshape(D, -1).T[:, ::-1]
+    pos = idx.astype(np.float64) + 0.5
+    o = orc.Oracle(D)
+    out = o.init_neighbour_search(pos, 0.0, float(n), True, 10)
+    cnt, _ = o.pair_stats_norm(out["pos"], r, -1)
+    assert np.all(cnt == (2 * int(np.floor(r)) + 1) ** D)
+    # L2 through the generic path equals the euclidean path
+    c2, h2 = o.pair_stats_norm(out["pos"], r, 2)
+    c2e, h2e = o.pair_stats(out["pos"], r)
+    assert np.array_equal(c2, c2e) and np.array_equal(h2, h2e)
+
+
+def test_manhattan_and_chebyshev_random_vs_brute_force():
+    rng = np.random.default_rng(99)
+    N, D, r = 800, 3, 0.3
+    pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+    for periodic in (True, False):
+        o = orc.Oracle(D)
+        out = o.init_neighbour_search(pos, -1.0, 1.0, periodic, 10)
+        ps = out["pos"]
+        shifts = np.array(np.meshgrid(*[[-2.0, 0.0, 2.0]] * D, indexing="ij")).reshape(D, -1).T if periodic else np.zeros((1, D))
+        for lnorm, fn in ((-1, lambda d: np.abs(d).max(-1)), (1, lambda d: np.abs(d).sum(-1))):
+            cnt, _ = o.pair_stats_norm(ps, r, lnorm)
+            brute = np.zeros(N, dtype=np.int64)
+            for sft in shifts:
+                d = ps[None, :, :] - (ps[:, None, :] + sft)
+                brute += (fn(d) <= r).sum(1)
+            assert np.array_equal(cnt, brute), (lnorm, periodic)
