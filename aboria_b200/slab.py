@@ -258,13 +258,17 @@ def run_bench(args, rank, world, dev, metric, unit):
     n_mine, first_id = shares[rank], sum(shares[:rank])
     x_lo, x_hi = sp.slab_bounds()
     pos_unsorted = synth.torch_uniform_positions(n_mine, 3, [x_lo, 0.0, 0.0], [x_hi, 1.0, 1.0], synth.SEED, first_id, dev)
+    # b is indexed by post-reorder position, as in the single-GPU bench (src/Kernels.h:745-748)
     b_owned = torch.from_numpy(synth.vector(n_mine, first_id=first_id)).to(dev)
     op = ab.create_sparse_operator(sp.p, sp.p, radius, K.inv_dist(EPS))
+    state = {}
 
     def step():
         sp.build(pos_unsorted.clone())
-        # b follows the particles: gather by the owned sort order, pad with ghosts
-        b_local = sp.local_vector(b_owned[sp.order_owned.long()])
+        b_local = state.get("b_local")
+        if b_local is None or b_local.shape[0] != sp.ex.n_local:
+            b_local = state["b_local"] = torch.zeros(sp.ex.n_local, dtype=torch.float64, device=dev)
+        b_local[sp.ex.own_begin: sp.ex.own_end].copy_(b_owned)  # owned entries; ghosts come from the neighbours
         return sp.matvec(op, b_local)
 
     step()
@@ -304,8 +308,8 @@ def run_bench(args, rank, world, dev, metric, unit):
 
     def e2e_step():
         sp.build(pos_host.to(dev, non_blocking=True))
-        b_dev = b_host.to(dev, non_blocking=True)
-        b_local = sp.local_vector(b_dev[sp.order_owned.long()])
+        b_local = torch.zeros(sp.ex.n_local, dtype=torch.float64, device=dev)
+        b_local[sp.ex.own_begin: sp.ex.own_end].copy_(b_host, non_blocking=True)  # H2D straight into the owned range
         y = sp.matvec(op, b_local)
         y_host.copy_(sp.owned(y))
 
