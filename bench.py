@@ -184,6 +184,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
         from aboria_b200 import slab
