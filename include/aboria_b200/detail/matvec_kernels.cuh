@@ -196,15 +196,15 @@ template <int D, class F> inline int launch_assemble(const abr_matvec_plan &p, c
 template <class F, class = void> struct needs_dx { static constexpr bool value = true; };
 template <class F> struct needs_dx<F, decltype((void)F::NEEDS_DX)> { static constexpr bool value = F::NEEDS_DX; };
 
-constexpr int QCAP = 16;      // accepted pairs a lane may hold
-constexpr int QDRAIN = 12;    // drain when any lane holds this many (a test step adds <= 4)
-constexpr int QSTRIDE = QCAP + 1; // odd stride: lane-private columns fall into distinct banks
+constexpr int QDRAIN = 12;            // drain when any lane holds this many (a test step adds <= 4)
+constexpr int QCAP = QDRAIN - 1 + 4;  // most accepted pairs a lane can hold
 constexpr int ROW_BITS = 4;
+constexpr int PCOL = 16;              // columns of the partial-sum table (lanes l and l+16 share one)
 
 template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
   // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows); block kernels keep
-  // BR partial-sum tables, so they take 8 rows at a time to stay at 5-6 CTAs/SM
+  // BR partial-sum tables, so they take 8 rows at a time
   static constexpr int RB = NACC == 1 ? (1 << ROW_BITS) : 8;
 };
 
@@ -213,17 +213,19 @@ template <int D, class F, bool STATS> struct TiledCfg {
 template <int D, class F, bool STATS> struct WarpSmem {
   static constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
   static constexpr int RB = TiledCfg<D, F, STATS>::RB;
-  double rows0[RB][4];                    // rows of the batch (x,y,z,pad)
-  double rowsS[RB][4];                    // rows shifted by a periodic image
+  // rows of the batch, one array per dimension: a drain round reads rows[d][i] for 32
+  // arbitrary i — 16 doubles span the 32 banks exactly once, so any pattern is conflict free
+  double rows0[MAXD][RB];
+  double rowsS[MAXD][RB];                 // rows shifted by a periodic image
   // rows relative to the bucket-stencil origin, fp32, for the pre-filter: row PAIRS packed
   // per dimension (x_2p, x_2p+1), (y..), (z..), pad — the operands of f32x2 instructions;
   // padded with far-away dummy rows
   unsigned long long rowsf2[RB / 2 + 1][4];
-  unsigned long long part[NACC][RB][32];  // partial sums [row][lane]
-  uint32_t lq[32][QSTRIDE];               // lane-private accepted-pair queues: (j << ROW_BITS) | row
+  unsigned long long part[NACC][RB][PCOL]; // partial sums [row][lane & 15]
+  uint32_t lq[QCAP][32];                  // lane-private accepted-pair queues, slot major: (j << ROW_BITS) | row
+  uint32_t wq[QCAP * 32];                 // the same pairs compacted for the drain
   uint32_t run_pref[32];                  // candidate-run directory: inclusive prefix of run lengths
   uint32_t run_delta[32];                 //   j = k + run_delta[run]
-  uint32_t dq_pref[32];                   // drain directory: inclusive prefix of queue lengths
   uint32_t danger;
   uint32_t pad_[3];
 };
@@ -243,11 +245,6 @@ __device__ __forceinline__ int reach_last_dim(double r2, double gap2, double sid
   return m < w_last ? m : w_last;
 }
 
-// Drain the lane-private queues: the queued (j, row) pairs of all lanes are
-// dealt out evenly, 32 per round, so the expensive part of the product (sqrt,
-// divide, the user's math) runs at full lane utilisation instead of on the ~15 %
-// of lanes that pass the cut-off test.  dx and |dx|^2 are recomputed here with
-// the same operations in the same order as in the test.
 // one 32-byte record (x, y, z, b) per lane: a single 256-bit load (LDG.E.256, sm_100)
 __device__ __forceinline__ void ld_rec(const double *rec, double &x, double &y, double &z, double &w) {
   unsigned long long a, b, c, d;
@@ -258,6 +255,16 @@ __device__ __forceinline__ void ld_rec(const double *rec, double &x, double &y, 
   w = __longlong_as_double((long long)d);
 }
 
+// 32-bit shared-window addresses for the queue: a store and a bump per accepted pair
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 struct DrainCtx {
   const double *pos; // packed records (plan.posb)
   const double *b;
@@ -265,11 +272,17 @@ struct DrainCtx {
   double r2;
 };
 
+// Drain the lane-private queues.  The queued (j, row) pairs of all lanes are
+// first compacted into one warp-wide list (an exclusive scan of the queue
+// lengths gives every lane its offset), then dealt out 32 per round, so the
+// expensive part of the product (sqrt, divide, the user's math) runs at full
+// lane utilisation instead of on the ~15 % of lanes that pass the cut-off test.
+// dx and |dx|^2 are recomputed here in fp64 with the reference's operations in
+// the reference's order.
 template <int D, class F, bool STATS, class SM>
 __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, int lane, uint32_t cnt, uint32_t r0,
-                                          const double (*rowp)[4], uint32_t image_id) {
+                                          const double (*rowp)[SM::RB], uint32_t image_id) {
   constexpr int BR = F::BR, BC = F::BC;
-  constexpr int U = 1; // pairs per lane per round (U = 2 was measured: no gain, costs a CTA of occupancy)
   uint32_t pin = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -277,79 +290,82 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
     if (lane >= o) pin += t;
   }
   const uint32_t total = __shfl_sync(0xFFFFFFFFu, pin, 31);
+  const uint32_t maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
+  {
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm.wq + (pin - cnt));
+    uint32_t src = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
+    for (uint32_t s = 0; s < maxc; ++s, dst += 4u, src += 128u)
+      if (s < cnt) sts32(dst, lds32(src));
+  }
   __syncwarp();
-  sm.dq_pref[lane] = pin;
-  __syncwarp();
-  for (uint32_t base = 0; base < total; base += 32 * U) {
-    bool live[U];
-    uint32_t j[U], i[U];
-    // deal the queued pairs out evenly: pair k belongs to the lane `o` with
-    // dq_pref[o-1] <= k < dq_pref[o]
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t k = base + 32 * u + lane;
-      live[u] = k < total;
-      const uint32_t ks = live[u] ? k : total - 1;
-      uint32_t o = 0;
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1)
-        if (sm.dq_pref[o + step - 1] <= ks) o += step;
-      const uint32_t local = ks - (o ? sm.dq_pref[o - 1] : 0u);
-      const uint32_t ent = sm.lq[o][local];
-      j[u] = ent >> ROW_BITS;
-      i[u] = ent & ((1u << ROW_BITS) - 1u);
-    }
-    // all global loads first: one 256-bit load brings the candidate's position and b
-    double pj[U][D], bj[U][BC];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
+  const int col = lane & (PCOL - 1);
+  for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t k = base + lane;
+    const bool live = k < total;
+    const uint32_t ent = sm.wq[live ? k : 0u];
+    const uint32_t j = ent >> ROW_BITS;
+    const uint32_t i = ent & ((1u << ROW_BITS) - 1u);
+    // one 256-bit load brings the candidate's position and b
+    double pj[D], bj[BC];
+    {
       double rec[4];
-      ld_rec(p.pos + (size_t)j[u] * 4, rec[0], rec[1], rec[2], rec[3]);
+      ld_rec(p.pos + (size_t)j * 4, rec[0], rec[1], rec[2], rec[3]);
 #pragma unroll
-      for (int d = 0; d < D; ++d) pj[u][d] = rec[d];
+      for (int d = 0; d < D; ++d) pj[d] = rec[d];
       if (!STATS) {
         if (BC == 1) {
-          bj[u][0] = rec[3];
+          bj[0] = rec[3];
         } else {
 #pragma unroll
-          for (int c = 0; c < BC; ++c) bj[u][c] = p.b[(size_t)j[u] * BC + c];
+          for (int c = 0; c < BC; ++c) bj[c] = p.b[(size_t)j * BC + c];
         }
       }
     }
+    double dx[D];
+    double d2 = 0;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      double dx[D];
-      double d2 = 0;
+    for (int d = 0; d < D; ++d) {
+      dx[d] = pj[d] - rowp[d][i];
+      d2 = d2 + dx[d] * dx[d];
+    }
+    // the queue holds the survivors of the conservative fp32 pre-filter; this is
+    // the reference's exact predicate (src/Search.h:438-446)
+    const bool ok = live && !(d2 > p.r2);
+    if (ok && d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
+    // lanes l and l+16 share a column of the partial-sum table: the two halves of
+    // the warp update it one after the other
+    if (STATS) {
+      const unsigned long long hv = mix64((uint64_t)j * 81u + (uint64_t)image_id);
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        dx[d] = pj[u][d] - rowp[i[u]][d];
-        d2 = d2 + dx[d] * dx[d];
-      }
-      // the queue holds the survivors of the conservative fp32 pre-filter; this is
-      // the reference's exact predicate (src/Search.h:438-446)
-      const bool ok = live[u] && !(d2 > p.r2);
-      if (ok && d2 > p.r2lo) atomicOr(&sm.danger, 1u << i[u]);
-      if (STATS) {
-        if (ok) {
-          sm.part[0][i[u]][lane] += 1ull;
-          sm.part[1][i[u]][lane] += mix64((uint64_t)j[u] * 81u + (uint64_t)image_id);
+      for (int half = 0; half < 2; ++half) {
+        if (ok && (lane >> 4) == half) {
+          sm.part[0][i][col] += 1ull;
+          sm.part[1][i][col] += hv;
         }
-      } else {
-        // F is evaluated unconditionally (it is pure; j, i are valid indices even for
-        // a pair that fails the test) so the two chains interleave; only the
-        // accumulation is predicated
-        double blk[BR * BC];
-        f(dx, d2, r0 + i[u], j[u], blk);
+        __syncwarp();
+      }
+    } else {
+      // F is evaluated unconditionally (it is pure; j, i are valid indices even for
+      // a pair that fails the test); only the accumulation is predicated
+      double blk[BR * BC];
+      f(dx, d2, r0 + i, j, blk);
+      double s[BR];
 #pragma unroll
-        for (int a2 = 0; a2 < BR; ++a2) {
-          double s = 0;
+      for (int a2 = 0; a2 < BR; ++a2) {
+        s[a2] = 0;
 #pragma unroll
-          for (int c = 0; c < BC; ++c) s += blk[a2 * BC + c] * bj[u][c];
-          if (ok) {
-            double *slot = reinterpret_cast<double *>(&sm.part[a2][i[u]][lane]);
-            *slot += s;
+        for (int c = 0; c < BC; ++c) s[a2] += blk[a2 * BC + c] * bj[c];
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (ok && (lane >> 4) == half) {
+#pragma unroll
+          for (int a2 = 0; a2 < BR; ++a2) {
+            double *slot = reinterpret_cast<double *>(&sm.part[a2][i][col]);
+            *slot += s[a2];
           }
         }
+        __syncwarp();
       }
     }
   }
@@ -388,15 +404,16 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 // exact fp64 test accepts is ever dropped.  The two rows of a step are the two
 // halves of packed f32x2 operands (FADD2 / FFMA2): 4 tests cost 4 D packed
 // instructions.  Survivors cost one predicated 4-byte store into the lane's own
-// queue; the exact un-fused fp64 predicate is applied to them in drain_queues.
-// (6.45 candidates are tested per accepted pair, so this loop is kept off the
-// fp64 pipe altogether.)
+// queue (slot-major layout: the bank is the lane, never a conflict) and a
+// pointer bump; the exact un-fused fp64 predicate is applied to them in
+// drain_queues.  (6.45 candidates are tested per accepted pair, so this loop is
+// kept off the fp64 pipe altogether.)
 template <int D, class F, bool STATS, class SM>
 __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_r2, const F &f, int lane,
                                           const float *pA, const float *pB, uint32_t jA, uint32_t jB, bool vA, bool vB,
-                                          int nr, const double (*rowp)[4], uint32_t image_id, uint32_t r0,
-                                          uint32_t &cnt) {
-  uint32_t *myq = sm.lq[lane];
+                                          int nr, const double (*rowp)[SM::RB], uint32_t image_id, uint32_t r0,
+                                          uint32_t &qa) {
+  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
   // invalid candidates are parked far away instead of being predicated out
   unsigned long long a[D], b[D];
 #pragma unroll
@@ -425,15 +442,15 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
     float a0, a1, b0, b1;
     unpack2(accA, a0, a1);
     unpack2(accB, b0, b1);
-    if (a0 <= pre_r2) myq[cnt++] = eA;
-    if (a1 <= pre_r2) myq[cnt++] = eA + 1u;
-    if (b0 <= pre_r2) myq[cnt++] = eB;
-    if (b1 <= pre_r2) myq[cnt++] = eB + 1u;
+    if (a0 <= pre_r2) { sts32(qa, eA); qa += 128u; }
+    if (a1 <= pre_r2) { sts32(qa, eA + 1u); qa += 128u; }
+    if (b0 <= pre_r2) { sts32(qa, eB); qa += 128u; }
+    if (b1 <= pre_r2) { sts32(qa, eB + 1u); qa += 128u; }
     eA += 2u;
     eB += 2u;
-    if (__any_sync(0xFFFFFFFFu, cnt >= (uint32_t)QDRAIN)) {
-      drain_queues<D, F, STATS>(sm, dc, f, lane, cnt, r0, rowp, image_id);
-      cnt = 0;
+    if (__any_sync(0xFFFFFFFFu, qa >= q0 + QDRAIN * 128u)) {
+      drain_queues<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 7, r0, rowp, image_id);
+      qa = q0;
     }
   }
 }
@@ -455,6 +472,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
   const uint32_t *__restrict__ bbeg = p.q.bucket_begin;
   const uint32_t *__restrict__ bend = p.q.bucket_end;
   constexpr int L = D - 1; // last (fastest, memory-contiguous) dimension
+  constexpr int DS = D > 1 ? D - 1 : 1;
   // number of offset tuples in the D-1 slow dimensions
   int nslow = 1;
 #pragma unroll
@@ -472,6 +490,28 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
   const DrainCtx dc{p.posb, p.b, p.r2lo, p.r2};
   const double *__restrict__ posb = p.posb;
   const float pre_r2 = p.pre_r2;
+  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
+  const int S = g.size[L];
+
+  // offsets of run `rid` of the stencil in the slow dimensions, the squared gap they
+  // already spend, and how far the last dimension still reaches (trimmed stencil)
+  auto decode_run = [&](int rid, int *od, int &wz) {
+    int rem = rid;
+    double gap2 = 0.0;
+#pragma unroll
+    for (int d = D - 2; d >= 0; --d) {
+      const int span = 2 * p.w[d] + 1;
+      od[d] = (rem % span) - p.w[d];
+      rem /= span;
+      const double gap = (double)max(abs(od[d]) - 1, 0) * g.side[d];
+      gap2 += gap * gap;
+    }
+    wz = p.trim ? reach_last_dim(p.r2, gap2, g.side[L], p.w[L]) : p.w[L];
+  };
+  // the first 32 runs are the same for every bucket: decode them once
+  int od_first[DS], wz_first;
+  od_first[0] = 0;
+  decode_run(lane, od_first, wz_first);
 
   while (true) {
     // warp-level dynamic scheduler: no block barrier anywhere in this kernel
@@ -481,27 +521,44 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
     if (grab >= own_cells) break;
     const uint32_t grab_end = min(grab + p.grab, own_cells);
 
-    for (uint32_t cell = first_cell + grab; cell < first_cell + grab_end; ++cell) {
-      const uint32_t rb = bbeg[cell], re = bend[cell];
-      if (rb == re) continue;
-      // bucket coordinates of the target (inverse of collapse_index)
-      int tc[D];
-      {
-        uint32_t rem = cell;
+    // bucket coordinates of the first bucket of the grab (inverse of collapse_index);
+    // the following ones are reached by counting up, last dimension fastest
+    int tc[D];
+    {
+      const uint32_t cell = first_cell + grab;
+      uint32_t rem = cell;
 #pragma unroll
-        for (int d = D - 1; d >= 0; --d) {
-          tc[d] = (int)(rem % (uint32_t)g.size[d]);
-          rem /= (uint32_t)g.size[d];
-        }
-        if (D > 1) { // local layer -> global layer (slab window; identity on a single GPU)
-          int gl = g.win_lo + (int)(cell / per_layer);
-          if (gl < 0) gl += g.size[0];
-          if (gl >= g.size[0]) gl -= g.size[0];
-          tc[0] = gl;
+      for (int d = D - 1; d >= 0; --d) {
+        tc[d] = (int)(rem % (uint32_t)g.size[d]);
+        rem /= (uint32_t)g.size[d];
+      }
+      if (D > 1) { // local layer -> global layer (slab window; identity on a single GPU)
+        int gl = g.win_lo + (int)(cell / per_layer);
+        if (gl < 0) gl += g.size[0];
+        if (gl >= g.size[0]) gl -= g.size[0];
+        tc[0] = gl;
+      }
+    }
+    --tc[L]; // the loop advances before it works
+
+    for (uint32_t cell = first_cell + grab; cell < first_cell + grab_end; ++cell) {
+      // advance the bucket coordinates to `cell`
+      if (++tc[L] == S) {
+        if (D > 1) {
+          tc[L] = 0;
+          if (D > 2) {
+            if (++tc[D > 2 ? 1 : 0] == g.size[D > 2 ? 1 : 0]) {
+              tc[D > 2 ? 1 : 0] = 0;
+              if (++tc[0] >= g.size[0]) tc[0] -= g.size[0]; // next (global) layer of the window
+            }
+          } else {
+            if (++tc[0] >= g.size[0]) tc[0] -= g.size[0];
+          }
         }
       }
+      const uint32_t rb = bbeg[cell], re = bend[cell];
+      if (rb == re) continue;
       const int zlo = tc[L] - p.w[L], zhi = tc[L] + p.w[L];
-      const int S = g.size[L];
       // does any neighbour of this bucket lie across a periodic boundary / outside?
       bool boundary = (zlo < 0) | (zhi >= S);
 #pragma unroll
@@ -521,7 +578,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
 #pragma unroll
           for (int d = 0; d < D; ++d) {
             const double r = pos[(size_t)(r0 + lane) * D + d];
-            sm.rows0[lane][d] = r;
+            sm.rows0[d][lane] = r;
             const double fl = (r - g.bmin[d]) * g.inv_side[d];
             const double fr = fl - floor(fl);
             my_danger |= ((int)floor(fl) != tc[d]) | (fr < p.tolf[d]) | (fr > 1.0 - p.tolf[d]) |
@@ -529,43 +586,44 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
           }
         }
         if (lane == 0) sm.danger = 0;
+        __syncwarp();
         if (lane < RB + 2) {
           // fp32 copy relative to the stencil origin (lower corner of the first neighbour
           // bucket), packed in row pairs; rows >= nr are dummies far away from everything
           float *rf = reinterpret_cast<float *>(&sm.rowsf2[0][0]);
 #pragma unroll
           for (int d = 0; d < D; ++d)
-            rf[(((lane >> 1) * 4) + d) * 2 + (lane & 1)] = lane < nr ? (float)(sm.rows0[lane][d] - origin[d]) : 3.0e18f;
+            rf[(((lane >> 1) * 4) + d) * 2 + (lane & 1)] = lane < nr ? (float)(sm.rows0[d][lane] - origin[d]) : 3.0e18f;
         }
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
-          for (int i = 0; i < nr; ++i) sm.part[a][i][lane] = 0ull;
+          for (int e = lane; e < nr * PCOL; e += 32) (&sm.part[a][0][0])[e] = 0ull;
         __syncwarp();
-        uint32_t cnt = 0; // entries in this lane's queue
+        uint32_t qa = q0; // next free slot of this lane's queue (shared-window address)
 
         // ---- phase 1: neighbour runs in the primary image, concatenated so that
-        //      every step tests 32 candidates (one run = the 2w+1 buckets along the
+        //      every step tests 64 candidates (one run = the 2w+1 buckets along the
         //      last dimension, contiguous in the sorted arrays) ----
         for (int rbase = 0; rbase < nslow; rbase += 32) {
           uint32_t len = 0, jb = 0;
           const int rid = rbase + lane;
           if (rid < nslow) {
+            int od[DS], wz;
+            if (rbase == 0) {
+#pragma unroll
+              for (int d = 0; d < DS; ++d) od[d] = od_first[d];
+              wz = wz_first;
+            } else {
+              decode_run(rid, od, wz);
+            }
             int nc[D];
             bool ok = true;
-            int rem = rid;
-            double gap2 = 0.0;
 #pragma unroll
-            for (int d = D - 2; d >= 0; --d) {
-              const int span = 2 * p.w[d] + 1;
-              const int od = (rem % span) - p.w[d];
-              const int u = tc[d] + od;
-              rem /= span;
+            for (int d = 0; d < D - 1; ++d) {
+              const int u = tc[d] + od[d];
               ok &= (u >= 0) & (u < g.size[d]);
               nc[d] = u;
-              const double gap = (double)max(abs(od) - 1, 0) * g.side[d];
-              gap2 += gap * gap;
             }
-            const int wz = p.trim ? reach_last_dim(p.r2, gap2, g.side[L], p.w[L]) : p.w[L]; // trimmed stencil
             const int a = max(tc[L] - wz, 0), bnd = min(tc[L] + wz, S - 1);
             if (ok && wz >= 0 && a <= bnd) {
               nc[L] = a;
@@ -608,18 +666,18 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
               for (int d = 0; d < D; ++d) pj[h][d] = (float)(rec[d] - origin[d]);
             }
             test_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
-                                   image_id0, r0, cnt);
+                                   image_id0, r0, qa);
           }
         }
         // pairs queued so far belong to the primary image
-        if (__any_sync(0xFFFFFFFFu, cnt != 0)) {
-          drain_queues<D, F, STATS>(sm, dc, f, lane, cnt, r0, sm.rows0, image_id0);
-          cnt = 0;
+        if (__any_sync(0xFFFFFFFFu, qa != q0)) {
+          drain_queues<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rows0, image_id0);
+          qa = q0;
         }
         if (boundary) {
           // ---- phase 2 (buckets at a periodic boundary only): runs reached through
           //      a periodic image; cur = r + image * L exactly as src/Search.h:188-190 ----
-          int o[D > 1 ? D - 1 : 1];
+          int o[DS];
 #pragma unroll
           for (int d = 0; d < D - 1; ++d) o[d] = -p.w[d];
           bool more = true;
@@ -660,7 +718,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
                 __syncwarp();
                 if (lane < nr) {
 #pragma unroll
-                  for (int d = 0; d < D; ++d) sm.rowsS[lane][d] = sm.rows0[lane][d] + (double)img[d] * g.L[d];
+                  for (int d = 0; d < D; ++d) sm.rowsS[d][lane] = sm.rows0[d][lane] + (double)img[d] * g.L[d];
                 }
                 __syncwarp();
                 const uint32_t image_id = STATS ? (uint32_t)image_linear_index<D>(g, img) : 0u;
@@ -679,12 +737,12 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
                     for (int d = 0; d < D; ++d) pj[h][d] = (float)((rec[d] - (double)img[d] * g.L[d]) - origin[d]);
                   }
                   test_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
-                                         image_id, r0, cnt);
+                                         image_id, r0, qa);
                 }
                 // leave no pair of this image in the queues (rowsS is reused)
-                if (__any_sync(0xFFFFFFFFu, cnt != 0)) {
-                  drain_queues<D, F, STATS>(sm, dc, f, lane, cnt, r0, sm.rowsS, image_id);
-                  cnt = 0;
+                if (__any_sync(0xFFFFFFFFu, qa != q0)) {
+                  drain_queues<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rowsS, image_id);
+                  qa = q0;
                 }
               }
             }
@@ -713,9 +771,10 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
             if (slot < p.danger_capacity) p.danger_list[slot] = r0 + lane;
           } else if (STATS) {
             unsigned long long c = 0, hsum = 0;
-            for (int k = 0; k < 32; ++k) {
-              c += sm.part[0][lane][(k + lane) & 31];
-              hsum += sm.part[1][lane][(k + lane) & 31];
+#pragma unroll
+            for (int k = 0; k < PCOL; ++k) {
+              c += sm.part[0][lane][(k + lane) & (PCOL - 1)];
+              hsum += sm.part[1][lane][(k + lane) & (PCOL - 1)];
             }
             if (p.stat_count) p.stat_count[r0 + lane] = (uint32_t)c;
             if (p.stat_hash) p.stat_hash[r0 + lane] = hsum;
@@ -723,7 +782,8 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
 #pragma unroll
             for (int a2 = 0; a2 < NACC; ++a2) {
               double s = 0;
-              for (int k = 0; k < 32; ++k) s += *reinterpret_cast<double *>(&sm.part[a2][lane][(k + lane) & 31]);
+#pragma unroll
+              for (int k = 0; k < PCOL; ++k) s += *reinterpret_cast<double *>(&sm.part[a2][lane][(k + lane) & (PCOL - 1)]);
               p.y[(size_t)(r0 + lane) * BR + a2] += s;
             }
           }
