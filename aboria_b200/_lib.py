@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libabr.so")
+# ABR_LIB_PATH: another build of the same library (tuning experiments); still no fallback
+LIB_PATH = os.environ.get("ABR_LIB_PATH") or os.path.join(_HERE, "lib", "libabr.so")
 MAX_VARS, MAX_PARAMS, MAX_D = 4, 8, 3
 
 _lib = None

@@ -106,7 +106,7 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
   p->use_tiled = tiled ? 1 : 0;
   {
     // small grids: hand out single buckets so that every resident warp gets work
-    const uint64_t warps = (uint64_t)h->sm_count * 28;
+    const uint64_t warps = (uint64_t)h->sm_count * 32;
     uint64_t gsz = p->q.g.ncells / (4 * warps);
     p->grab = (uint32_t)(gsz < 1 ? 1 : (gsz > 8 ? 8 : gsz));
   }

@@ -196,9 +196,19 @@ template <int D, class F> inline int launch_assemble(const abr_matvec_plan &p, c
 template <class F, class = void> struct needs_dx { static constexpr bool value = true; };
 template <class F> struct needs_dx<F, decltype((void)F::NEEDS_DX)> { static constexpr bool value = F::NEEDS_DX; };
 
-constexpr int QDRAIN = 12;            // drain when any lane holds this many (a test step adds <= 4)
+#ifndef ABR_QDRAIN
+#define ABR_QDRAIN 14
+#endif
+#ifndef ABR_TILED_CTAS
+#define ABR_TILED_CTAS 8
+#endif
+constexpr int QDRAIN = ABR_QDRAIN;    // drain when any lane holds this many (a test step adds <= 4)
 constexpr int QCAP = QDRAIN - 1 + 4;  // most accepted pairs a lane can hold
 constexpr int ROW_BITS = 4;
+#ifndef ABR_WQ
+#define ABR_WQ 256
+#endif
+constexpr int WQ = ABR_WQ;            // pairs compacted per drain pass
 constexpr int PCOL = 16;              // columns of the partial-sum table (lanes l and l+16 share one)
 
 template <int D, class F, bool STATS> struct TiledCfg {
@@ -223,7 +233,7 @@ template <int D, class F, bool STATS> struct WarpSmem {
   unsigned long long rowsf2[RB / 2 + 1][4];
   unsigned long long part[NACC][RB][PCOL]; // partial sums [row][lane & 15]
   uint32_t lq[QCAP][32];                  // lane-private accepted-pair queues, slot major: (j << ROW_BITS) | row
-  uint32_t wq[QCAP * 32];                 // the same pairs compacted for the drain
+  uint32_t wq[WQ];                        // the same pairs compacted for the drain, WQ at a time
   uint32_t run_pref[32];                  // candidate-run directory: inclusive prefix of run lengths
   uint32_t run_delta[32];                 //   j = k + run_delta[run]
   uint32_t danger;
@@ -246,9 +256,10 @@ __device__ __forceinline__ int reach_last_dim(double r2, double gap2, double sid
 }
 
 // one 32-byte record (x, y, z, b) per lane: a single 256-bit load (LDG.E.256, sm_100)
-__device__ __forceinline__ void ld_rec(const double *rec, double &x, double &y, double &z, double &w) {
-  unsigned long long a, b, c, d;
-  asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(rec));
+__device__ __forceinline__ void ld_rec(const double *base, uint32_t j, double &x, double &y, double &z, double &w) {
+  unsigned long long a, b, c, d, addr;
+  asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr) : "r"(j), "l"(base));
+  asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(addr));
   x = __longlong_as_double((long long)a);
   y = __longlong_as_double((long long)b);
   z = __longlong_as_double((long long)c);
@@ -290,86 +301,90 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
     if (lane >= o) pin += t;
   }
   const uint32_t total = __shfl_sync(0xFFFFFFFFu, pin, 31);
-  const uint32_t maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
-  {
-    uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm.wq + (pin - cnt));
-    uint32_t src = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
-    for (uint32_t s = 0; s < maxc; ++s, dst += 4u, src += 128u)
-      if (s < cnt) sts32(dst, lds32(src));
-  }
-  __syncwarp();
+  const uint32_t excl = pin - cnt; // this lane's pairs are numbers excl .. pin-1 of the warp's list
+  const uint32_t lq0 = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
+  const uint32_t wq0 = (uint32_t)__cvta_generic_to_shared(&sm.wq[0]);
   const int col = lane & (PCOL - 1);
-  for (uint32_t base = 0; base < total; base += 32) {
-    const uint32_t k = base + lane;
-    const bool live = k < total;
-    const uint32_t ent = sm.wq[live ? k : 0u];
-    const uint32_t j = ent >> ROW_BITS;
-    const uint32_t i = ent & ((1u << ROW_BITS) - 1u);
-    // one 256-bit load brings the candidate's position and b
-    double pj[D], bj[BC];
+  // the compacted list is produced WQ pairs at a time (almost always a single pass)
+  for (uint32_t wbase = 0; wbase < total; wbase += WQ) {
     {
-      double rec[4];
-      ld_rec(p.pos + (size_t)j * 4, rec[0], rec[1], rec[2], rec[3]);
-#pragma unroll
-      for (int d = 0; d < D; ++d) pj[d] = rec[d];
-      if (!STATS) {
-        if (BC == 1) {
-          bj[0] = rec[3];
-        } else {
-#pragma unroll
-          for (int c = 0; c < BC; ++c) bj[c] = p.b[(size_t)j * BC + c];
-        }
-      }
+      const uint32_t lo = max(excl, wbase), hi = min(pin, wbase + WQ);
+      for (uint32_t k = lo; k < hi; ++k) sts32(wq0 + (k - wbase) * 4u, lds32(lq0 + (k - excl) * 128u));
     }
-    double dx[D];
-    double d2 = 0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      dx[d] = pj[d] - rowp[d][i];
-      d2 = d2 + dx[d] * dx[d];
-    }
-    // the queue holds the survivors of the conservative fp32 pre-filter; this is
-    // the reference's exact predicate (src/Search.h:438-446)
-    const bool ok = live && !(d2 > p.r2);
-    if (ok && d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
-    // lanes l and l+16 share a column of the partial-sum table: the two halves of
-    // the warp update it one after the other
-    if (STATS) {
-      const unsigned long long hv = mix64((uint64_t)j * 81u + (uint64_t)image_id);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (ok && (lane >> 4) == half) {
-          sm.part[0][i][col] += 1ull;
-          sm.part[1][i][col] += hv;
-        }
-        __syncwarp();
-      }
-    } else {
-      // F is evaluated unconditionally (it is pure; j, i are valid indices even for
-      // a pair that fails the test); only the accumulation is predicated
-      double blk[BR * BC];
-      f(dx, d2, r0 + i, j, blk);
-      double s[BR];
-#pragma unroll
-      for (int a2 = 0; a2 < BR; ++a2) {
-        s[a2] = 0;
-#pragma unroll
-        for (int c = 0; c < BC; ++c) s[a2] += blk[a2 * BC + c] * bj[c];
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (ok && (lane >> 4) == half) {
-#pragma unroll
-          for (int a2 = 0; a2 < BR; ++a2) {
-            double *slot = reinterpret_cast<double *>(&sm.part[a2][i][col]);
-            *slot += s[a2];
+    __syncwarp();
+    const uint32_t wtotal = min(total - wbase, (uint32_t)WQ);
+    for (uint32_t base = 0; base < wtotal; base += 32) {
+      const uint32_t k = base + lane;
+      const bool live = k < wtotal;
+      const uint32_t ent = sm.wq[live ? k : 0u];
+      const uint32_t j = ent >> ROW_BITS;
+      const uint32_t i = ent & ((1u << ROW_BITS) - 1u);
+      // one 256-bit load brings the candidate's position and b
+      double pj[D], bj[BC];
+      {
+        double rec[4];
+        ld_rec(p.pos, j, rec[0], rec[1], rec[2], rec[3]);
+  #pragma unroll
+        for (int d = 0; d < D; ++d) pj[d] = rec[d];
+        if (!STATS) {
+          if (BC == 1) {
+            bj[0] = rec[3];
+          } else {
+  #pragma unroll
+            for (int c = 0; c < BC; ++c) bj[c] = p.b[(size_t)j * BC + c];
           }
         }
-        __syncwarp();
+      }
+      double dx[D];
+      double d2 = 0;
+  #pragma unroll
+      for (int d = 0; d < D; ++d) {
+        dx[d] = pj[d] - rowp[d][i];
+        d2 = d2 + dx[d] * dx[d];
+      }
+      // the queue holds the survivors of the conservative fp32 pre-filter; this is
+      // the reference's exact predicate (src/Search.h:438-446)
+      const bool ok = live && !(d2 > p.r2);
+      if (ok && d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
+      // lanes l and l+16 share a column of the partial-sum table: the two halves of
+      // the warp update it one after the other
+      if (STATS) {
+        const unsigned long long hv = mix64((uint64_t)j * 81u + (uint64_t)image_id);
+  #pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (ok && (lane >> 4) == half) {
+            sm.part[0][i][col] += 1ull;
+            sm.part[1][i][col] += hv;
+          }
+          __syncwarp();
+        }
+      } else {
+        // F is evaluated unconditionally (it is pure; j, i are valid indices even for
+        // a pair that fails the test); only the accumulation is predicated
+        double blk[BR * BC];
+        f(dx, d2, r0 + i, j, blk);
+        double s[BR];
+  #pragma unroll
+        for (int a2 = 0; a2 < BR; ++a2) {
+          s[a2] = 0;
+  #pragma unroll
+          for (int c = 0; c < BC; ++c) s[a2] += blk[a2 * BC + c] * bj[c];
+        }
+  #pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (ok && (lane >> 4) == half) {
+  #pragma unroll
+            for (int a2 = 0; a2 < BR; ++a2) {
+              double *slot = reinterpret_cast<double *>(&sm.part[a2][i][col]);
+              *slot += s[a2];
+            }
+          }
+          __syncwarp();
+        }
       }
     }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // packed fp32 pairs (Blackwell FADD2 / FFMA2): one instruction, two rows
@@ -455,10 +470,10 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
   }
 }
 
-// occupancy target: the shared-memory footprint allows 7 CTAs/SM for scalar kernels
-// (needs <= 73 registers), 5 for D x 1 block kernels
+// occupancy target: 8 CTAs/SM for scalar kernels (6.6 KB of shared memory per warp, 64
+// registers), 5 for D x 1 block kernels
 template <int D, class F, bool STATS>
-__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::NACC == 1 ? 7 : 5))
+__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::NACC == 1 ? ABR_TILED_CTAS : 5))
 tiled_kernel(const abr_matvec_plan p, const F f) {
   constexpr int BR = F::BR;
   constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
@@ -661,7 +676,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
                 if (sm.run_pref[rho + step - 1] <= ks) rho += step;
               jj[h] = ks + sm.run_delta[rho];
               double rec[4];
-              ld_rec(posb + (size_t)jj[h] * 4, rec[0], rec[1], rec[2], rec[3]);
+              ld_rec(posb, jj[h], rec[0], rec[1], rec[2], rec[3]);
 #pragma unroll
               for (int d = 0; d < D; ++d) pj[h][d] = (float)(rec[d] - origin[d]);
             }
@@ -732,7 +747,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
                     vv[h] = cb + 32 * h + lane < je;
                     // pre-filter only: move the candidate by -image*L instead of the row by +image*L
                     double rec[4];
-                    ld_rec(posb + (size_t)jj[h] * 4, rec[0], rec[1], rec[2], rec[3]);
+                    ld_rec(posb, jj[h], rec[0], rec[1], rec[2], rec[3]);
 #pragma unroll
                     for (int d = 0; d < D; ++d) pj[h][d] = (float)((rec[d] - (double)img[d] * g.L[d]) - origin[d]);
                   }
