@@ -385,7 +385,7 @@ int abr_distance_search_stats(abr_handle hh, const double *row_pos, size_t n_row
 int abr_last_counters(abr_handle hh, uint64_t counters[4]) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !counters) return ABR_ERR_INVALID;
-  ABR_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(abr::DevScalars), cudaMemcpyDeviceToHost, h->stream));
+  abr::publish_scalars(h);
   ABR_CUDA(h, cudaStreamSynchronize(h->stream));
   counters[0] = h->h_scalars->danger_count;
   counters[1] = h->n_aliased;

@@ -75,8 +75,7 @@ struct Handle {
   DevBuf danger_list;
   DevBuf posb; // packed (x, y, z, b) records of the column particles for the tiled product
   DevScalars *d_scalars = nullptr;
-  DevScalars *h_scalars = nullptr; // pinned: [0] read-back mirror, [1], [2] alternating slots for initial values
-  int init_slot = 0;
+  DevScalars *h_scalars = nullptr; // pinned read-back mirror, written by k_publish_scalars
   const uint32_t *sorted_keys = nullptr;
   uint64_t ncells = 0;
   bool built = false;
@@ -109,6 +108,9 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
                    size_t *n_alive_host, const ReorderSpec *reorder, bool presorted = false);
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
                    const size_t *elem_bytes, const int32_t *order, size_t n_out, const uint32_t *n_dev);
+
+void fill_u32(Handle *h, uint32_t *p, uint32_t v, uint64_t n); // kernel fill (no memset node)
+void publish_scalars(Handle *h);                               // d_scalars -> pinned h_scalars by a kernel store
 
 // abr_matvec.cu
 struct MatvecCall {

@@ -12,8 +12,12 @@ namespace abr {
 // column particle with ONE 256-bit load instead of four scattered 8-byte loads
 // (the LSU data pipe was the binding limit, profiles/r1m_*).  Costs one streaming
 // pass (64 B/particle) per product.
-template <int D> __global__ void __launch_bounds__(256) k_pack_posb(const double *__restrict__ pos, const double *__restrict__ b, double *__restrict__ posb, uint32_t n) {
+template <int D> __global__ void __launch_bounds__(256) k_pack_posb(const double *__restrict__ pos, const double *__restrict__ b, double *__restrict__ posb, uint32_t n, DevScalars *scal) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) { // reset the tile scheduler and the exact-walk list of the product that follows (no memset node: see abr_build.cu)
+    scal->work_counter = 0;
+    scal->danger_count = 0;
+  }
   if (j >= n) return;
   double r[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -114,17 +118,16 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
     ABR_CUDA(h, h->danger_list.reserve((size_t)c.n_rows * sizeof(uint32_t)));
     p->danger_list = h->danger_list.as<uint32_t>();
     p->danger_capacity = (uint32_t)c.n_rows;
-    ABR_CUDA(h, cudaMemsetAsync(&h->d_scalars->work_counter, 0, 2 * sizeof(uint32_t), h->stream));
     // packed column records; b rides along when the block has one column
     ABR_CUDA(h, h->posb.reserve((size_t)h->n_sorted * 4 * sizeof(double) + 32));
     double *posb = h->posb.as<double>();
     const uint32_t n32 = (uint32_t)h->n_sorted;
     const double *bpack = (BC == 1 && c.b) ? c.b : nullptr;
-    const unsigned gb = (n32 + 255) / 256;
+    const unsigned gb = (n32 + 255) / 256 > 0 ? (n32 + 255) / 256 : 1;
     switch (D) {
-    case 1: k_pack_posb<1><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32); break;
-    case 2: k_pack_posb<2><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32); break;
-    default: k_pack_posb<3><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32); break;
+    case 1: k_pack_posb<1><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32, h->d_scalars); break;
+    case 2: k_pack_posb<2><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32, h->d_scalars); break;
+    default: k_pack_posb<3><<<gb, 256, 0, h->stream>>>(h->pos_sorted, bpack, posb, n32, h->d_scalars); break;
     }
     h->launches += 1;
     p->posb = posb;
