@@ -89,6 +89,13 @@ int abr_destroy(abr_handle hh) {
   h->bucket_end.release();
   h->danger_list.release();
   h->posb.release();
+  for (int i = 0; i < 2; ++i) {
+    h->idm_k[i].release();
+    h->idm_i[i].release();
+  }
+  h->idm_max.release();
+  h->id_map_key.release();
+  h->id_map_value.release();
   if (h->d_scalars) cudaFree(h->d_scalars);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   delete h;
@@ -371,6 +378,38 @@ int abr_sparse_assemble(abr_handle hh, const double *row_pos, size_t n_rows, int
   ABR_CUDA(h, cudaSetDevice(h->device));
   abr::MatvecCall c{row_pos, n_rows, rows_are_cols, radius, radius_per_row, nullptr, nullptr, nullptr, nullptr, -1};
   return abr::run_assemble(h, c, k, row_ptr, col_idx, values, capacity, nnz_host);
+}
+
+int abr_sparse_coeff(abr_handle hh, const double *row_pos, size_t n_rows, const abr_kernel_desc *k, double radius, const double *radius_per_row,
+                     const uint64_t *ii, const uint64_t *jj, size_t m, double *out) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::MatvecCall c{row_pos, n_rows, 0, radius, radius_per_row, nullptr, nullptr, nullptr, nullptr, 1};
+  return abr::run_coeff(h, c, k, ii, jj, m, out);
+}
+
+int abr_id_map_build(abr_handle hh, const uint64_t *ids, size_t n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  return abr::build_id_map(h, ids, n);
+}
+
+int abr_id_map_get(abr_handle hh, const uint64_t **key, const uint64_t **value, size_t *n_host) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (key) *key = h->id_map_n ? h->id_map_key.as<uint64_t>() : nullptr;
+  if (value) *value = h->id_map_n ? h->id_map_value.as<uint64_t>() : nullptr;
+  if (n_host) *n_host = h->id_map_n;
+  return ABR_OK;
+}
+
+int abr_id_find(abr_handle hh, const uint64_t *query_ids, size_t m, uint64_t *index_out) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  return abr::find_ids(h, query_ids, m, index_out);
 }
 
 int abr_distance_search_stats(abr_handle hh, const double *row_pos, size_t n_rows, double radius, const double *radius_per_row, int lnorm,

@@ -1054,4 +1054,147 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
   return set_error(h, ABR_ERR_STATE, "build: grid did not converge");
 }
 
+// ---------------------------------------------------------------------------
+// id map (neighbour_search_base::init_id_map and the id-map update of
+// update_positions, src/NeighbourSearchBase.h:294-298, :440-486):
+// m_id_map_key = ids of the particles in their (post-reorder) order,
+// m_id_map_value = 0..n-1, sort_by_key(key, value).  The 64-bit ids are sorted
+// with the same 8-bit LSD passes as the bucket keys, low word first, then (only
+// if some id needs more than 32 bits) the high word gathered through the
+// permutation; passes above the most significant byte in use are skipped.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_id_split(const uint64_t *__restrict__ ids, uint32_t n, uint32_t *__restrict__ lo,
+                                                  unsigned long long *__restrict__ maxid) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = 0;
+  if (i < n) {
+    v = ids[i];
+    lo[i] = (uint32_t)v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    v = t > v ? t : v;
+  }
+  if ((threadIdx.x & 31) == 0 && v != 0) atomicMax(maxid, v);
+}
+__global__ void __launch_bounds__(256) k_id_hi_by_perm(const uint64_t *__restrict__ ids, const uint32_t *__restrict__ perm, uint32_t n,
+                                                       uint32_t *__restrict__ hi) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) hi[k] = (uint32_t)(ids[perm ? perm[k] : k] >> 32);
+}
+__global__ void __launch_bounds__(256) k_id_emit(const uint64_t *__restrict__ ids, const uint32_t *__restrict__ perm, uint32_t n,
+                                                 uint64_t *__restrict__ key, uint64_t *__restrict__ value) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    const uint32_t src = perm ? perm[k] : k;
+    key[k] = ids[src];
+    value[k] = src;
+  }
+}
+// src/CellListOrdered.h:379-388 find(id): lower_bound over the sorted keys
+__global__ void __launch_bounds__(256) k_id_find(const uint64_t *__restrict__ key, const uint64_t *__restrict__ value, uint64_t n,
+                                                 const uint64_t *__restrict__ query, uint64_t m, uint64_t *__restrict__ out) {
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const uint64_t id = query[q];
+  uint64_t lo = 0, len = n;
+  while (len > 0) { // std::lower_bound
+    const uint64_t half = len >> 1;
+    if (key[lo + half] < id) {
+      lo += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  out[q] = (lo != n && !(id < key[lo])) ? value[lo] : n;
+}
+
+// stable LSD passes over the bytes [0, nbytes) of a 32-bit key array, carrying a
+// permutation (null = identity on entry); returns the buffers holding the result
+static int lsd_passes_u32(Handle *h, uint32_t *kbuf[2], uint32_t *ibuf[2], int &cur, bool &have_perm, uint32_t n32, int nbytes) {
+  const uint32_t num_tiles = (n32 + RS_TILE - 1) / RS_TILE;
+  uint32_t *hist = h->tile_hist.as<uint32_t>();
+  const TileTab dense{nullptr, nullptr, nullptr, nullptr, nullptr};
+  GatherCols no_cols;
+  no_cols.ncols = 0;
+  ABR_CUDA(h, cudaFuncSetAttribute(k_radix_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixScatterSmem)));
+  for (int pass = 0; pass < nbytes; ++pass) {
+    const int shift = pass * 8;
+    k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(kbuf[cur], n32, shift, num_tiles, hist, dense);
+    cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
+    if (e != cudaSuccess) return check_cuda(h, e, "id map scan");
+    k_radix_scatter<false><<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(kbuf[cur], have_perm ? ibuf[cur] : nullptr, kbuf[cur ^ 1],
+                                                                                            ibuf[cur ^ 1], hist, shift, n32, num_tiles, dense, no_cols);
+    h->launches += 2;
+    cur ^= 1;
+    have_perm = true;
+  }
+  ABR_CUDA(h, cudaGetLastError());
+  return ABR_OK;
+}
+
+int build_id_map(Handle *h, const uint64_t *ids, size_t n) {
+  if (n >= 0xFFFFFFF0ull) return set_error(h, ABR_ERR_UNSUPPORTED, "id map: too many particles");
+  h->id_map_n = 0;
+  if (n == 0) return ABR_OK;
+  if (!ids) return set_error(h, ABR_ERR_INVALID, "id map: null id column");
+  const uint32_t n32 = (uint32_t)n;
+  const uint32_t num_tiles = (n32 + RS_TILE - 1) / RS_TILE;
+  for (int i = 0; i < 2; ++i) {
+    ABR_CUDA(h, h->idm_k[i].reserve(n * sizeof(uint32_t)));
+    ABR_CUDA(h, h->idm_i[i].reserve(n * sizeof(uint32_t)));
+  }
+  ABR_CUDA(h, h->tile_hist.reserve((size_t)RADIX * num_tiles * sizeof(uint32_t)));
+  ABR_CUDA(h, h->id_map_key.reserve(n * sizeof(uint64_t)));
+  ABR_CUDA(h, h->id_map_value.reserve(n * sizeof(uint64_t)));
+  ABR_CUDA(h, h->idm_max.reserve(sizeof(unsigned long long)));
+  uint32_t *kbuf[2] = {h->idm_k[0].as<uint32_t>(), h->idm_k[1].as<uint32_t>()};
+  uint32_t *ibuf[2] = {h->idm_i[0].as<uint32_t>(), h->idm_i[1].as<uint32_t>()};
+  unsigned long long *dmax = h->idm_max.as<unsigned long long>();
+  fill_u32(h, reinterpret_cast<uint32_t *>(dmax), 0u, 2);
+  const unsigned gb = grid_for(n, 256);
+  k_id_split<<<gb, 256, 0, h->stream>>>(ids, n32, kbuf[0], dmax);
+  h->launches += 1;
+  unsigned long long maxid = 0; // not on the hot path: a plain read-back decides how many byte passes are needed
+  ABR_CUDA(h, cudaMemcpyAsync(&maxid, dmax, sizeof(maxid), cudaMemcpyDeviceToHost, h->stream));
+  ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+  auto bytes_of = [](uint32_t v) {
+    int b = 0;
+    while (v) {
+      ++b;
+      v >>= 8;
+    }
+    return b;
+  };
+  const uint32_t max_hi = (uint32_t)(maxid >> 32);
+  const int lo_bytes = max_hi ? 4 : bytes_of((uint32_t)maxid);
+  int cur = 0;
+  bool have_perm = false;
+  int rc = lsd_passes_u32(h, kbuf, ibuf, cur, have_perm, n32, lo_bytes);
+  if (rc) return rc;
+  if (max_hi) {
+    k_id_hi_by_perm<<<gb, 256, 0, h->stream>>>(ids, have_perm ? ibuf[cur] : nullptr, n32, kbuf[cur]);
+    h->launches += 1;
+    rc = lsd_passes_u32(h, kbuf, ibuf, cur, have_perm, n32, bytes_of(max_hi));
+    if (rc) return rc;
+  }
+  k_id_emit<<<gb, 256, 0, h->stream>>>(ids, have_perm ? ibuf[cur] : nullptr, n32, h->id_map_key.as<uint64_t>(), h->id_map_value.as<uint64_t>());
+  h->launches += 1;
+  ABR_CUDA(h, cudaGetLastError());
+  h->id_map_n = n;
+  return ABR_OK;
+}
+
+int find_ids(Handle *h, const uint64_t *query, size_t m, uint64_t *index_out) {
+  if (m == 0) return ABR_OK;
+  if (!query || !index_out) return set_error(h, ABR_ERR_INVALID, "id find: null pointer");
+  k_id_find<<<grid_for(m, 256), 256, 0, h->stream>>>(h->id_map_key.as<uint64_t>(), h->id_map_value.as<uint64_t>(), (uint64_t)h->id_map_n, query,
+                                                     (uint64_t)m, index_out);
+  h->launches += 1;
+  ABR_CUDA(h, cudaGetLastError());
+  return ABR_OK;
+}
+
 } // namespace abr

@@ -73,6 +73,8 @@ struct Handle {
   size_t two_level_min_n = (size_t)1 << 20;  // use the two-level build from this many particles (abr_set_option)
   DevBuf bucket_begin, bucket_end;
   DevBuf danger_list;
+  DevBuf idm_k[2], idm_i[2], idm_max, id_map_key, id_map_value; // id map (m_id_map_key / m_id_map_value) + sort scratch
+  size_t id_map_n = 0;
   DevBuf posb; // packed (x, y, z, b) records of the column particles for the tiled product
   DevScalars *d_scalars = nullptr;
   DevScalars *h_scalars = nullptr; // pinned read-back mirror, written by k_publish_scalars
@@ -109,6 +111,8 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
                    const size_t *elem_bytes, const int32_t *order, size_t n_out, const uint32_t *n_dev);
 
+int build_id_map(Handle *h, const uint64_t *ids, size_t n);
+int find_ids(Handle *h, const uint64_t *query, size_t m, uint64_t *index_out);
 void fill_u32(Handle *h, uint32_t *p, uint32_t v, uint64_t n); // kernel fill (no memset node)
 void publish_scalars(Handle *h);                               // d_scalars -> pinned h_scalars by a kernel store
 
@@ -131,6 +135,7 @@ int run_pair_stats(Handle *h, const MatvecCall &c);
 int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm);
 int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint32_t *row_ptr, int32_t *col_idx, double *values,
                  size_t capacity, uint64_t *nnz_host);
+int run_coeff(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, const uint64_t *ii, const uint64_t *jj, size_t m, double *out);
 int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, const void *functor,
                       int BR, int BC);
 

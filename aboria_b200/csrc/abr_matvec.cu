@@ -202,6 +202,52 @@ template <int D> static int dispatch_assemble(Handle *h, const abr_matvec_plan &
   return ABR_OK;
 }
 
+// ---- coeff --------------------------------------------------------------------
+template <int D> static int dispatch_coeff(Handle *h, const abr_matvec_plan &p, const abr_kernel_desc *k, const uint64_t *ii, const uint64_t *jj,
+                                          uint64_t m, double *out) {
+  using namespace functors;
+  int e = -1;
+  switch (k->kernel_id) {
+  case ABR_K_CONST_SUM: e = launch_coeff<D>(p, ConstSum{k->row_vars[0], k->col_vars[0]}, ii, jj, m, out); break;
+  case ABR_K_CONST_SUM_DIFF: e = launch_coeff<D>(p, ConstSumDiff{k->row_vars[0], k->col_vars[0]}, ii, jj, m, out); break;
+  case ABR_K_INV_DIST: e = launch_coeff<D>(p, InvDist{k->params[0]}, ii, jj, m, out); break;
+  case ABR_K_INV_DIST_AA: e = launch_coeff<D>(p, InvDistAA{k->params[0], k->row_vars[0], k->col_vars[0]}, ii, jj, m, out); break;
+  case ABR_K_WENDLAND_C2: e = launch_coeff<D>(p, WendlandC2{k->params[0]}, ii, jj, m, out); break;
+  case ABR_K_LJ_FORCE: e = launch_coeff<D>(p, LJForce<D>{k->params[0], k->params[1]}, ii, jj, m, out); break;
+  case ABR_K_SPH_DENSITY: e = launch_coeff<D>(p, SphDensity<D>{k->params[0], k->params[1], k->params[2]}, ii, jj, m, out); break;
+  case ABR_K_SPH_PRESSURE:
+    e = launch_coeff<D>(p, SphPressure<D>{k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]}, ii, jj, m, out);
+    break;
+  default: return set_error(h, ABR_ERR_INVALID, "coeff: unknown kernel_id");
+  }
+  if (e != 0) return check_cuda(h, (cudaError_t)e, "coeff launch");
+  h->launches += 1;
+  return ABR_OK;
+}
+
+int run_coeff(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, const uint64_t *ii, const uint64_t *jj, size_t m, double *out) {
+  if (!k) return set_error(h, ABR_ERR_INVALID, "coeff: null kernel descriptor");
+  if (m == 0) return ABR_OK;
+  if (!c.row_pos || !ii || !jj || !out) return set_error(h, ABR_ERR_INVALID, "coeff: null pointer");
+  if (!h->domain_set) return set_error(h, ABR_ERR_STATE, "coeff: domain has not been set");
+  if (!h->pos_sorted) return set_error(h, ABR_ERR_STATE, "coeff: abr_query_set_particles not called");
+  abr_matvec_plan p;
+  memset(&p, 0, sizeof(p));
+  p.q.g = h->grid();
+  p.q.pos = h->pos_sorted;
+  p.q.n = (uint32_t)h->n_sorted;
+  p.row_pos = c.row_pos;
+  p.n_rows = (uint32_t)c.n_rows;
+  p.radius = c.radius;
+  p.radius_per_row = c.radius_per_row;
+  p.stream = h->stream;
+  switch (h->D) {
+  case 1: return dispatch_coeff<1>(h, p, k, ii, jj, m, out);
+  case 2: return dispatch_coeff<2>(h, p, k, ii, jj, m, out);
+  default: return dispatch_coeff<3>(h, p, k, ii, jj, m, out);
+  }
+}
+
 int scan_exclusive_u32(Handle *h, uint32_t *data, uint64_t m); // abr_build.cu
 
 int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint32_t *row_ptr, int32_t *col_idx, double *values,

@@ -42,6 +42,11 @@ class Query:
     def bucket_indices(self):
         return self.particles._bucket_view()[0]
 
+    def find(self, ids):
+        """find(id) (src/CellListOrdered.h:379-388) for a batch of ids: the position of
+        the particle with that id, or size() (the reference's end pointer) when absent."""
+        return self.particles._find_ids(ids)
+
 
 class Particles:
     """Struct-of-columns particle container on one GPU (Particles<VAR,D,...,
@@ -72,6 +77,7 @@ class Particles:
         self.searchable = False
         self._order = None
         self.n_buckets = 0
+        self._id_map = False
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -195,7 +201,44 @@ class Particles:
         self._other = dict(zip(names, src))
         self.columns = {k: t[:na] for k, t in zip(names, dst)}
         self.n_buckets = self.grid()[2]
+        if self._id_map:
+            self._update_id_map()
         return na
+
+    # -- find by id ------------------------------------------------------------
+    def init_id_search(self):
+        """Particles::init_id_search (src/Particles.h) -> init_id_map + update
+        (src/NeighbourSearchBase.h:294-298, :440-486); kept up to date by every
+        later update_positions, as in the reference."""
+        self._id_map = True
+        self._update_id_map()
+
+    def _update_id_map(self):
+        self._sync_stream()
+        ids = self.columns["id"]
+        check(self._h, self._lib.abr_id_map_build(self._h, _ptr(ids), ids.shape[0]))
+
+    def id_map(self):
+        """(m_id_map_key, m_id_map_value) as int64 device tensors"""
+        k, v = C.c_void_p(), C.c_void_p()
+        n = C.c_size_t()
+        check(self._h, self._lib.abr_id_map_get(self._h, C.byref(k), C.byref(v), C.byref(n)))
+        check(self._h, self._lib.abr_synchronize(self._h))
+        if n.value == 0:
+            e = torch.empty(0, dtype=torch.int64, device=self.device)
+            return e, e.clone()
+        kt = torch.as_tensor(_DevArray(k.value, n.value, "<i8"), device=self.device).clone()
+        vt = torch.as_tensor(_DevArray(v.value, n.value, "<i8"), device=self.device).clone()
+        return kt, vt
+
+    def _find_ids(self, ids):
+        if not self._id_map:
+            raise AbrError("init_id_search not called on this particle set")
+        self._sync_stream()
+        q = torch.as_tensor(ids, dtype=torch.int64, device=self.device).contiguous().reshape(-1)
+        out = torch.empty(q.shape[0], dtype=torch.int64, device=self.device)
+        check(self._h, self._lib.abr_id_find(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        return out
 
     def get_alive_indicies(self):
         """m_alive_indices after the sort: new[k] = old[order[k]]"""
@@ -329,6 +372,30 @@ class SparseOperator:
         del keep
         return npairs.value if count_pairs else None
 
+    def coeff(self, i, j):
+        """K.coeff(i, j) (src/Operators.h:149-151 -> src/Kernels.h:102-112 over
+        detail::sparse_kernel): matrix entries for index arrays i, j.  Note the strict
+        `|dx|^2 < r^2` and the minimum-image dx of this path (src/detail/Kernels.h:358-367)."""
+        cols, rows = self.col_particles, self.row_particles
+        cols._sync_stream()
+        d, keep = self._desc()
+        it = torch.as_tensor(i, dtype=torch.int64, device=cols.device).contiguous().reshape(-1)
+        jt = torch.as_tensor(j, dtype=torch.int64, device=cols.device).contiguous().reshape(-1)
+        if it.shape != jt.shape:
+            raise ValueError("i and j must have the same length")
+        if it.numel() and (int(it.min()) < 0 or int(it.max()) >= self.rows() or int(jt.min()) < 0 or int(jt.max()) >= self.cols()):
+            raise ValueError("coeff: index out of range")  # the reference ASSERTs (src/Kernels.h:103-104)
+        rpr = None
+        if self.radius_per_row is not None:
+            rpr = torch.as_tensor(self.radius_per_row, dtype=torch.float64, device=cols.device).contiguous()
+        out = torch.empty(it.shape[0], dtype=torch.float64, device=cols.device)
+        rp = rows.get("position")
+        cp = cols.get("position")
+        check(cols._h, cols._lib.abr_query_set_particles(cols._h, _ptr(cp), cols.size()))
+        check(cols._h, cols._lib.abr_sparse_coeff(cols._h, _ptr(rp), rows.size(), C.byref(d), self.radius, _ptr(rpr), _ptr(it), _ptr(jt), it.shape[0], _ptr(out)))
+        del keep
+        return out
+
     def assemble(self, values=True):
         """K.assemble(triplets) (src/Kernels.h:653-685) as CSR on the device:
         returns (row_ptr int32[n_rows+1], col_idx int32[nnz], values float64[nnz, BR, BC] | None)."""
@@ -379,6 +446,114 @@ class SparseOperator:
             return y.cpu()
         out_host.copy_(y, non_blocking=False)
         return out_host
+
+
+class ZeroOperator:
+    """create_zero_operator(rows, cols) (src/Operators.h:531-537, KernelZero): a block of zeros"""
+
+    def __init__(self, rows, cols, block_rows=1, block_cols=1):
+        self.row_particles, self.col_particles = rows, cols
+        self.block_rows, self.block_cols = block_rows, block_cols
+
+    def rows(self):
+        return self.row_particles.size() * self.block_rows
+
+    def cols(self):
+        return self.col_particles.size() * self.block_cols
+
+    def evaluate(self, y, b):
+        return None
+
+    def coeff(self, i, j):
+        it = torch.as_tensor(i).reshape(-1)
+        return torch.zeros(it.shape[0], dtype=torch.float64, device=self.col_particles.device)
+
+
+def create_zero_operator(row_particles, col_particles):
+    return ZeroOperator(row_particles, col_particles)
+
+
+class BlockOperator:
+    """create_block_operator<NI,NJ>(blocks...) (src/Operators.h:541-548): an NI x NJ
+    arrangement of operators behind one MatrixReplacement.  The product follows
+    src/detail/Operators.h:170-198: block (I, J) is evaluated on
+    y.segment(start_row(I), rows(I)) and x.segment(start_col(J), cols(J)) and
+    accumulates into y; coeff() picks the block that owns (i, j)
+    (src/Operators.h:242-251).  Host-side composition only: every block runs its own
+    device kernels."""
+
+    def __init__(self, NI, NJ, blocks):
+        blocks = list(blocks)
+        if len(blocks) != NI * NJ:
+            raise ValueError("create_block_operator: need NI*NJ blocks")
+        self.NI, self.NJ, self.blocks = NI, NJ, blocks
+        for I in range(NI):
+            for J in range(NJ):
+                blk = self.block(I, J)
+                if blk.rows() != self.block(I, 0).rows() or blk.cols() != self.block(0, J).cols():
+                    raise ValueError("create_block_operator: block sizes do not line up")
+
+    def block(self, I, J):
+        return self.blocks[I * self.NJ + J]
+
+    def _row_starts(self):
+        s = [0]
+        for I in range(self.NI):
+            s.append(s[-1] + self.block(I, 0).rows())
+        return s
+
+    def _col_starts(self):
+        s = [0]
+        for J in range(self.NJ):
+            s.append(s[-1] + self.block(0, J).cols())
+        return s
+
+    def rows(self):
+        return self._row_starts()[-1]
+
+    def cols(self):
+        return self._col_starts()[-1]
+
+    def evaluate(self, y, b):
+        rs, cs = self._row_starts(), self._col_starts()
+        if b.shape[0] != cs[-1] or y.shape[0] != rs[-1]:
+            raise ValueError("vector has incompatible size")
+        for I in range(self.NI):
+            for J in range(self.NJ):
+                self.block(I, J).evaluate(y[rs[I]:rs[I + 1]], b[cs[J]:cs[J + 1]])
+
+    def matvec(self, b, out=None):
+        dev = b.device
+        y = torch.zeros(self.rows(), dtype=torch.float64, device=dev) if out is None else out.zero_()
+        self.evaluate(y, b)
+        return y
+
+    __mul__ = matvec
+    __matmul__ = matvec
+
+    def coeff(self, i, j):
+        it = torch.as_tensor(i, dtype=torch.int64).reshape(-1)
+        jt = torch.as_tensor(j, dtype=torch.int64).reshape(-1)
+        rs, cs = self._row_starts(), self._col_starts()
+        dev = None
+        out = None
+        for I in range(self.NI):
+            for J in range(self.NJ):
+                m = (it >= rs[I]) & (it < rs[I + 1]) & (jt >= cs[J]) & (jt < cs[J + 1])
+                if not bool(m.any()):
+                    continue
+                v = self.block(I, J).coeff(it[m] - rs[I], jt[m] - cs[J])
+                if out is None:
+                    dev = v.device
+                    out = torch.zeros(it.shape[0], dtype=torch.float64, device=dev)
+                out[m.to(dev)] = v
+        if out is None:
+            raise ValueError("coeff: index out of range")
+        return out
+
+
+def create_block_operator(NI, NJ, *blocks):
+    return BlockOperator(NI, NJ, blocks)
 
 
 def create_sparse_operator(row_particles, col_particles, radius, kernel):

@@ -189,6 +189,52 @@ template <int D, class F> inline int launch_assemble(const abr_matvec_plan &p, c
 }
 
 // ---------------------------------------------------------------------------
+// coeff_kernel: KernelBase::coeff(i, j) over detail::sparse_kernel
+// (src/Kernels.h:102-112, src/detail/Kernels.h:336-367) for m (i, j) entries:
+// dx = correct_dx_for_periodicity(p_col - p_row) (src/Particles.h:480-494), the
+// block is F(dx, a, b) when dx.squaredNorm() < r^2 — STRICT, unlike the search
+// predicate — and zero otherwise.
+// ---------------------------------------------------------------------------
+template <int D, class F>
+__global__ void __launch_bounds__(128) coeff_kernel(const abr_matvec_plan p, const F f, const uint64_t *__restrict__ ii,
+                                                   const uint64_t *__restrict__ jj, uint64_t m, double *__restrict__ out) {
+  constexpr int BR = F::BR, BC = F::BC;
+  const Grid &g = p.q.g;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t pi = ii[q] / BR, pj = jj[q] / BC;
+    const int ioff = (int)(ii[q] - pi * BR), joff = (int)(jj[q] - pj * BC);
+    double dx[D];
+    double n2 = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double v = p.q.pos[pj * D + d] - p.row_pos[pi * D + d];
+      if (g.periodic[d]) {
+        const double w = g.bmax[d] - g.bmin[d];
+        while (v > w / 2) v -= w;
+        while (v <= -w / 2) v += w;
+      }
+      dx[d] = v;
+      n2 += v * v;
+    }
+    const double R = p.radius_per_row ? p.radius_per_row[pi] : p.radius;
+    double val = 0.0;
+    if (n2 < R * R) {
+      double blk[BR * BC];
+      f(dx, n2, (uint32_t)pi, (uint32_t)pj, blk);
+      val = blk[ioff * BC + joff];
+    }
+    out[q] = val;
+  }
+}
+
+template <int D, class F> inline int launch_coeff(const abr_matvec_plan &p, const F &f, const uint64_t *ii, const uint64_t *jj, uint64_t m,
+                                                  double *out) {
+  const unsigned grid = (unsigned)((m + 127) / 128 < 65535u * 16u ? (m + 127) / 128 : 65535u * 16u);
+  if (grid > 0) coeff_kernel<D, F><<<grid, 128, 0, p.stream>>>(p, f, ii, jj, m, out);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // tiled_kernel
 // ---------------------------------------------------------------------------
 // does the functor read dx?  (default yes; functors that only need |dx|^2 set

@@ -196,6 +196,32 @@ int abr_sparse_assemble(abr_handle h, const double *row_pos, size_t n_rows, int 
                         uint32_t *row_ptr, int32_t *col_idx, double *values, size_t capacity,
                         uint64_t *nnz_host);
 
+/* KernelBase::coeff(i, j) over detail::sparse_kernel (src/Kernels.h:102-112,
+ * src/detail/Kernels.h:336-367; reached from MatrixReplacement::coeff,
+ * src/Operators.h:149-151) for m matrix entries at once: out[q] = K(ii[q], jj[q]).
+ * Row particle ii/BR at row_pos, column particle jj/BC of the handle's particle
+ * set; dx = correct_dx_for_periodicity(p_col - p_row) (src/Particles.h:480-494)
+ * and the entry is non-zero only when dx.squaredNorm() < radius^2 — a STRICT
+ * comparison, unlike the `<=` of the search that the product uses.  Needs the
+ * domain (abr_domain_set) and abr_query_set_particles, not the cell list. */
+int abr_sparse_coeff(abr_handle h, const double *row_pos, size_t n_rows,
+                     const abr_kernel_desc *kernel_host, double radius, const double *radius_per_row,
+                     const uint64_t *ii, const uint64_t *jj, size_t m, double *out);
+
+/* Find-by-id (neighbour_search_base::init_id_map and the id-map update of
+ * update_positions, src/NeighbourSearchBase.h:294-298, :440-486): builds
+ * m_id_map_key (ids in ascending order) and m_id_map_value (position of that
+ * particle) from the id column in its CURRENT order, i.e. call it after every
+ * abr_update_positions, as the reference does inside update_positions.
+ * ids are the reference's size_t (u64), assumed unique (src/Particles.h). */
+int abr_id_map_build(abr_handle h, const uint64_t *ids, size_t n);
+/* device views of m_id_map_key / m_id_map_value (n entries each) */
+int abr_id_map_get(abr_handle h, const uint64_t **key, const uint64_t **value, size_t *n_host);
+/* CellListOrderedQuery::find (src/CellListOrdered.h:379-388) for m ids at once:
+ * index_out[q] = position of the particle with id query_ids[q], or n — the
+ * reference's end pointer — when there is none. */
+int abr_id_find(abr_handle h, const uint64_t *query_ids, size_t m, uint64_t *index_out);
+
 /* Neighbour-set diagnostics used by the parity tests: per row the number of
  * accepted (j,image) pairs of euclidean_search (src/Search.h:839-845) and an
  * order-independent 64-bit hash of that set.  path 0 = cell-tiled kernel (needs

@@ -757,6 +757,70 @@ uint64_t orc_sparse_assemble(void *h, const double *row_pos, size_t n_rows, int 
   return nnz;
 }
 
+// ---------------------------------------------------------------------------
+// src/NeighbourSearchBase.h:440-486 update of the id map for the ordered case
+// (update range == whole set): m_id_map_value = sequence(0..n), m_id_map_key[k] =
+// id of the particle at (post-reorder) position k, then sort_by_key(key, value)
+// (detail/Algorithms.h:173-182: std::sort on the zipped pair with a key-only
+// comparator).  ids are unique in the reference (src/Particles.h next_id), so the
+// result does not depend on the stability of the sort.
+// ---------------------------------------------------------------------------
+void orc_id_map_build(const uint64_t *ids, size_t n, uint64_t *key, uint64_t *value) {
+  std::vector<std::pair<uint64_t, uint64_t>> kv(n);
+  for (size_t k = 0; k < n; ++k) kv[k] = {ids[k], (uint64_t)k};
+  std::sort(kv.begin(), kv.end(), [](const std::pair<uint64_t, uint64_t> &a, const std::pair<uint64_t, uint64_t> &b) { return a.first < b.first; });
+  for (size_t k = 0; k < n; ++k) {
+    key[k] = kv[k].first;
+    value[k] = kv[k].second;
+  }
+}
+
+// src/CellListOrdered.h:379-388 find(id): lower_bound over m_id_map_key; returns the
+// particle index m_id_map_value[...] or n (the reference's "end" pointer) when absent
+void orc_id_find(const uint64_t *key, const uint64_t *value, size_t n, const uint64_t *query, size_t m, uint64_t *index_out) {
+  for (size_t q = 0; q < m; ++q) {
+    const uint64_t id = query[q];
+    const uint64_t *first = std::lower_bound(key, key + n, id);
+    index_out[q] = (first != key + n && !(id < *first)) ? value[first - key] : (uint64_t)n;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// KernelBase::coeff(i, j) (src/Kernels.h:102-112) over detail::sparse_kernel
+// (src/detail/Kernels.h:336-367): pi = i / BR, pj = j / BC;
+// dx = correct_dx_for_periodicity(pos_col[pj] - pos_row[pi]) (src/Particles.h:480-494:
+// per periodic dimension `while (dx > w/2) dx -= w; while (dx <= -w/2) dx += w`);
+// block = dx.squaredNorm() < pow(radius(a), 2) ? F(dx, a, b) : 0   -- STRICT '<', unlike
+// the search predicate of the product; returns block(i % BR, j % BC).
+// ---------------------------------------------------------------------------
+void orc_sparse_coeff(void *h, const double *row_pos, const double *col_pos, const uint64_t *ii, const uint64_t *jj, size_t m,
+                      int kernel_id, const double *params, const double *const *row_vars, const double *const *col_vars,
+                      double radius, const double *radius_per_row, int BR, int BC, double *out) {
+  Oracle *o = static_cast<Oracle *>(h);
+  const int D = o->D;
+  KernelCtx k{kernel_id, D, params, row_vars, col_vars};
+  for (size_t q = 0; q < m; ++q) {
+    const size_t pi = ii[q] / BR, ioff = ii[q] - pi * BR;
+    const size_t pj = jj[q] / BC, joff = jj[q] - pj * BC;
+    double dx[MAXD];
+    for (int d = 0; d < D; ++d) {
+      dx[d] = col_pos[pj * D + d] - row_pos[pi * D + d];
+      if (o->periodic[d]) {
+        const double w = o->bmax[d] - o->bmin[d];
+        while (dx[d] > w / 2) dx[d] -= w;
+        while (dx[d] <= -w / 2) dx[d] += w;
+      }
+    }
+    double n2 = 0; // src/Vector.h squaredNorm: sequential sum from 0
+    for (int d = 0; d < D; ++d) n2 += dx[d] * dx[d];
+    const double R = radius_per_row ? radius_per_row[pi] : radius;
+    double blk[MAXD * MAXD];
+    for (int e = 0; e < BR * BC; ++e) blk[e] = 0.0;
+    if (n2 < R * R) eval_kernel(k, dx, pi, pj, blk);
+    out[q] = blk[ioff * BC + joff];
+  }
+}
+
 // brute force of tests/neighbours.h:739-764: counts j with
 // squaredNorm(pj - pi - image*(max-min)) <= r2 over 3^D images (periodic) or
 // the single image (non periodic).  NOTE the operation order differs from the

@@ -61,6 +61,10 @@ def lib():
         L.orc_sparse_assemble.restype = C.c_uint64
         L.orc_sparse_assemble.argtypes = [vp, dp, C.c_size_t, C.c_int, dp, C.POINTER(dp), C.POINTER(dp), C.c_double, dp, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int32), dp]
         L.orc_brute_force_counts.argtypes = [C.c_int, dp, C.c_size_t, dp, dp, C.c_int, C.c_double, C.POINTER(C.c_uint32)]
+        u64p = C.POINTER(C.c_uint64)
+        L.orc_id_map_build.argtypes = [u64p, C.c_size_t, u64p, u64p]
+        L.orc_id_find.argtypes = [u64p, u64p, C.c_size_t, u64p, C.c_size_t, u64p]
+        L.orc_sparse_coeff.argtypes = [vp, dp, dp, u64p, u64p, C.c_size_t, C.c_int, dp, C.POINTER(dp), C.POINTER(dp), C.c_double, dp, C.c_int, C.c_int, dp]
         L.orc_max_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -252,6 +256,49 @@ def _assemble(self, row_pos, kernel_id, params, radius, BR=1, BC=1, row_vars=(),
 
 
 Oracle.assemble = _assemble
+
+
+def _coeff(self, row_pos, col_pos, ii, jj, kernel_id, params, radius, BR=1, BC=1, row_vars=(), col_vars=(), radius_per_row=None):
+    """K.coeff(i, j) (src/Kernels.h:102-112 over detail::sparse_kernel, src/detail/Kernels.h:336-367) for arrays ii, jj"""
+    row_pos, col_pos = _f64(row_pos), _f64(col_pos)
+    ii = np.ascontiguousarray(ii, dtype=np.uint64)
+    jj = np.ascontiguousarray(jj, dtype=np.uint64)
+    params = _f64(params if len(params) else [0.0])
+    rv = [_f64(v) for v in row_vars]
+    cv = [_f64(v) for v in col_vars]
+    dpp = C.POINTER(C.c_double)
+    RV = (dpp * max(1, len(rv)))(*[_dp(v) for v in rv])
+    CV = (dpp * max(1, len(cv)))(*[_dp(v) for v in cv])
+    rpr = _f64(radius_per_row) if radius_per_row is not None else None
+    out = np.zeros(len(ii), dtype=np.float64)
+    u64p = C.POINTER(C.c_uint64)
+    lib().orc_sparse_coeff(self.h, _dp(row_pos), _dp(col_pos), ii.ctypes.data_as(u64p), jj.ctypes.data_as(u64p), len(ii), int(kernel_id), _dp(params),
+                           RV, CV, float(radius), _dp(rpr), BR, BC, _dp(out))
+    return out
+
+
+Oracle.coeff = _coeff
+
+
+def id_map_build(ids):
+    """the id map of src/NeighbourSearchBase.h:440-486: (key, value) sorted by id"""
+    ids = np.ascontiguousarray(ids, dtype=np.uint64)
+    key = np.zeros(len(ids), dtype=np.uint64)
+    value = np.zeros(len(ids), dtype=np.uint64)
+    u64p = C.POINTER(C.c_uint64)
+    lib().orc_id_map_build(ids.ctypes.data_as(u64p), len(ids), key.ctypes.data_as(u64p), value.ctypes.data_as(u64p))
+    return key, value
+
+
+def id_find(key, value, query):
+    """CellListOrderedQuery::find (src/CellListOrdered.h:379-388): index or n"""
+    key = np.ascontiguousarray(key, dtype=np.uint64)
+    value = np.ascontiguousarray(value, dtype=np.uint64)
+    query = np.ascontiguousarray(query, dtype=np.uint64)
+    out = np.zeros(len(query), dtype=np.uint64)
+    u64p = C.POINTER(C.c_uint64)
+    lib().orc_id_find(key.ctypes.data_as(u64p), value.ctypes.data_as(u64p), len(key), query.ctypes.data_as(u64p), len(query), out.ctypes.data_as(u64p))
+    return out
 
 
 def max_threads():

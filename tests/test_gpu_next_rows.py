@@ -1,0 +1,171 @@
+"""GPU parity tests for the SURVEY §8f rows next to the hot path: find-by-id,
+coeff(i, j), block operators.  Bit-exact for the id map and the found indices;
+coefficients equal to the oracle's within 2 ulp-level tolerance (same kernel
+functions as the product, TOL 1e-12 relative)."""
+import numpy as np
+import pytest
+import torch
+
+import aboria_b200 as ab
+from aboria_b200 import kernels as K
+from aboria_b200 import synth
+from oracle import oracle as orc
+from util import build_both, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("N,idmax", [(1, 10), (100, 100), (5000, 1 << 20), (70000, 1 << 31), (70000, (1 << 40) + 12345), (3000, (1 << 63) - 1)])
+def test_id_map_parity(N, idmax):
+    # ids: unique, arbitrary 64-bit values; compare m_id_map_key / m_id_map_value with the oracle
+    rng = np.random.default_rng(N + (idmax & 0xFFFF))
+    if idmax <= 4 * N:
+        ids = rng.permutation(max(N, idmax))[:N].astype(np.uint64)
+    else:
+        ids = np.unique(rng.integers(0, idmax, size=2 * N, dtype=np.uint64))
+        ids = rng.permutation(ids)[:N]
+        ids[0] = np.uint64(idmax - 1) if N > 1 else ids[0]
+        ids = np.array(sorted(set(ids.tolist())), dtype=np.uint64)
+        ids = rng.permutation(ids)
+    n = len(ids)
+    p = ab.Particles(3, n)
+    p.set("position", torch.from_numpy(synth.uniform_positions(n, 3)))
+    p.set("id", torch.from_numpy(ids.view(np.int64).copy()))
+    p.init_id_search()
+    key, value = p.id_map()
+    okey, ovalue = orc.id_map_build(ids)
+    assert np.array_equal(key.cpu().numpy().view(np.uint64), okey)
+    assert np.array_equal(value.cpu().numpy().view(np.uint64), ovalue)
+    q = np.concatenate([ids[: min(n, 1000)], rng.integers(0, idmax, size=1000, dtype=np.uint64), np.array([0, idmax], dtype=np.uint64)])
+    got = p.get_query().find(torch.from_numpy(q.view(np.int64).copy())).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, orc.id_find(okey, ovalue, q))
+
+
+def test_id_search_documentation_example_and_reorder():
+    # tests/id_search.h:64-99, then the id map must follow init_neighbour_search's reorder
+    # (src/NeighbourSearchBase.h:440-486 runs inside every update_positions)
+    N = 100
+    rng = np.random.default_rng(3)
+    ids = rng.permutation(N).astype(np.int64)
+    pos = synth.uniform_positions(N, 3)
+    p = ab.Particles(3, N)
+    p.set("position", torch.from_numpy(pos.copy()))
+    p.set("id", torch.from_numpy(ids.copy()))
+    p.init_id_search()
+    f = p.get_query().find([2, 2 * N]).cpu().numpy()
+    assert p.get("id")[int(f[0])].item() == 2
+    assert f[1] == N  # end of the particle vector
+    p.init_neighbour_search(0.0, 1.0, True)
+    f = p.get_query().find(np.arange(N)).cpu().numpy()
+    assert np.array_equal(p.get("id").cpu().numpy()[f], np.arange(N))
+    # positions found through the id are the original ones
+    assert np.array_equal(p.get("position").cpu().numpy()[f], pos[np.argsort(ids)])
+    with pytest.raises(ab.AbrError):
+        ab.Particles(3, 4).get_query().find([1])
+
+
+KERNELS = [
+    ("const_sum", lambda D: K.const_sum("a", "a"), orc.K_CONST_SUM, lambda D: [], 1),
+    ("const_sum_diff", lambda D: K.const_sum_diff("a", "a"), orc.K_CONST_SUM_DIFF, lambda D: [], 2),
+    ("inv_dist", lambda D: K.inv_dist(0.1), orc.K_INV_DIST, lambda D: [0.1], 1),
+    ("wendland", lambda D: K.wendland_c2(0.07), orc.K_WENDLAND_C2, lambda D: [0.07], 1),
+    ("lj", lambda D: K.lj_force(D, 0.05, 1.0), orc.K_LJ_FORCE, lambda D: [0.05, 1.0], None),
+]
+
+
+@pytest.mark.parametrize("D,periodic", [(1, True), (2, False), (3, True), (3, False)])
+@pytest.mark.parametrize("kname,kmake,kid,kparams,br", KERNELS)
+def test_coeff_parity(D, periodic, kname, kmake, kid, kparams, br):
+    N, r = 600, 0.14
+    BR = D if br is None else br
+    rng = np.random.default_rng(D * 7 + int(periodic))
+    pos = rng.random((N, D))
+    a = rng.random(N)
+    o, out, p = build_both(pos, 0.0, 1.0, periodic, variables={"a": torch.float64})
+    order = out["order"]
+    p2 = ab.Particles(D, N, variables={"a": torch.float64})
+    p2.set("position", torch.from_numpy(pos.copy()))
+    p2.set("a", torch.from_numpy(a.copy()))
+    p2.init_neighbour_search(0.0, 1.0, periodic)
+    a_sorted = a[order]
+    op = ab.create_sparse_operator(p2, p2, r, kmake(D))
+    m = 20000
+    ii = rng.integers(0, N * BR, size=m)
+    jj = rng.integers(0, N, size=m)
+    # make sure close pairs are among them: neighbours of the first rows
+    cnt, j, im, dx = o.search_point(out["pos"][0], r)
+    ii[: len(j)] = 0
+    jj[: len(j)] = j
+    got = op.coeff(ii, jj).cpu().numpy()
+    ref = o.coeff(out["pos"], out["pos"], ii, jj, kid, kparams(D), r, BR=BR, BC=1, row_vars=[a_sorted], col_vars=[a_sorted])
+    assert np.array_equal(got == 0.0, ref == 0.0)  # the strict predicate selects the same entries
+    assert np.count_nonzero(ref) > 50
+    assert rel_l2(got, ref) <= TOL
+    with pytest.raises(ValueError):
+        op.coeff([N * BR], [0])
+
+
+def test_coeff_golden_and_strict_predicate():
+    # tests/operators.h:873-881 dense matrix [[3,3,0],[3,3,3],[0,3,3]] via coeff
+    diameter = 0.1
+    pos = np.array([[0, 0, 0], [diameter * 0.9, 0, 0], [diameter * 1.8, 0, 0]], dtype=np.float64)
+    p = ab.Particles(3, 3, variables={"s1": torch.float64, "s2": torch.float64})
+    p.set("position", torch.from_numpy(pos.copy()))
+    p.set("s1", torch.full((3,), 1.0, dtype=torch.float64))
+    p.set("s2", torch.full((3,), 2.0, dtype=torch.float64))
+    p.init_neighbour_search(-1.0, 1.0, False)
+    ids = p.get("id").cpu().numpy()
+    C = ab.create_sparse_operator(p, p, diameter, K.const_sum("s1", "s2"))
+    ii, jj = np.divmod(np.arange(9), 3)
+    c = C.coeff(ii, jj).cpu().numpy().reshape(3, 3)
+    expect = np.array([[0.0 if {int(ids[i]), int(ids[j])} == {0, 2} else 3.0 for j in range(3)] for i in range(3)])
+    assert np.array_equal(c, expect)
+    # a pair at exactly r: in the product (<=), not in coeff (<); minimum image through the boundary
+    pos = np.array([[0.125, 0.5, 0.5], [0.375, 0.5, 0.5], [0.9375, 0.5, 0.5]])
+    p = ab.Particles(3, 3, variables={"s1": torch.float64, "s2": torch.float64})
+    p.set("position", torch.from_numpy(pos.copy()))
+    p.set("s1", torch.full((3,), 1.0, dtype=torch.float64))
+    p.set("s2", torch.full((3,), 2.0, dtype=torch.float64))
+    p.init_neighbour_search(0.0, 1.0, True)
+    x = p.get("position").cpu().numpy()[:, 0]
+    a, b, cc = [int(np.argmin(np.abs(x - v))) for v in (0.125, 0.375, 0.9375)]
+    C = ab.create_sparse_operator(p, p, 0.25, K.const_sum("s1", "s2"))
+    c = C.coeff(ii, jj).cpu().numpy().reshape(3, 3)
+    assert c[a, b] == 0.0 and c[b, a] == 0.0 and c[a, cc] == 3.0 and c[cc, a] == 3.0
+    cnt, _ = p.pair_stats(0.25)
+    assert cnt.cpu().numpy()[[a, b, cc]].tolist() == [3, 2, 2]
+
+
+def test_block_operator():
+    # create_block_operator<2,2>(A, B, C, Zero) (src/Operators.h:541-548) over sparse blocks:
+    # product and coeff equal those of the dense composition of the blocks
+    rng = np.random.default_rng(11)
+    n1, n2, r = 500, 300, 0.2
+    def make(n, seed):
+        p = ab.Particles(3, n)
+        p.set("position", torch.from_numpy(synth.uniform_positions(n, 3, seed=seed)))
+        p.init_neighbour_search(0.0, 1.0, True)
+        return p
+    p1, p2 = make(n1, 1), make(n2, 2)
+    A = ab.create_sparse_operator(p1, p1, r, K.inv_dist(0.1))
+    B = ab.create_sparse_operator(p1, p2, r, K.wendland_c2(0.1))
+    Ct = ab.create_sparse_operator(p2, p1, r, K.wendland_c2(0.1))
+    Z = ab.create_zero_operator(p2, p2)
+    Full = ab.create_block_operator(2, 2, A, B, Ct, Z)
+    assert Full.rows() == n1 + n2 and Full.cols() == n1 + n2
+    v = torch.from_numpy(rng.random(n1 + n2)).to(p1.device)
+    y = (Full * v).cpu().numpy()
+    yA = (A * v[:n1]).cpu().numpy() + (B * v[n1:]).cpu().numpy()
+    yC = (Ct * v[:n1]).cpu().numpy()
+    assert np.array_equal(y[:n1], yA) or rel_l2(y[:n1], yA) <= TOL
+    assert np.array_equal(y[n1:], yC)
+    # dense composition through coeff: (Full.coeff) x v == Full * v up to the pairs at exactly r (none here)
+    ii, jj = np.divmod(np.arange((n1 + n2) * (n1 + n2)), n1 + n2)
+    dense = Full.coeff(ii, jj).cpu().numpy().reshape(n1 + n2, n1 + n2)
+    assert np.all(dense[n1:, n1:] == 0.0)
+    assert rel_l2(dense @ v.cpu().numpy(), y) <= 1e-11
+    with pytest.raises(ValueError):
+        ab.create_block_operator(2, 2, A, B, Ct)
+    with pytest.raises(ValueError):
+        ab.create_block_operator(2, 2, A, A, Ct, Z)

@@ -239,3 +239,59 @@ def test_manhattan_and_chebyshev_random_vs_brute_force():
                 d = ps[None, :, :] - (ps[:, None, :] + sft)
                 brute += (fn(d) <= r).sum(1)
             assert np.array_equal(cnt, brute), (lnorm, periodic)
+
+
+def test_id_search_golden():
+    # tests/id_search.h:64-99: N particles with ids 0..N-1 in shuffled order; find(2) points
+    # at the particle with id 2, find(2N) at the end of the particle vector
+    N = 100
+    ids = np.random.default_rng(0).permutation(N).astype(np.uint64)
+    key, value = orc.id_map_build(ids)
+    assert np.array_equal(key, np.arange(N, dtype=np.uint64))
+    assert np.array_equal(ids[value.astype(np.int64)], key)
+    found = orc.id_find(key, value, [2, 2 * N])
+    assert ids[int(found[0])] == 2
+    assert found[1] == N
+    # tests/id_search.h:126-205 (helper_d_random): random ids to look up, brute force as the check
+    rng = np.random.default_rng(1)
+    ids = rng.choice(10 * N, size=N, replace=False).astype(np.uint64)
+    key, value = orc.id_map_build(ids)
+    q = rng.integers(0, 10 * N, size=500).astype(np.uint64)
+    got = orc.id_find(key, value, q)
+    for qi, gi in zip(q, got):
+        w = np.where(ids == qi)[0]
+        assert gi == (w[0] if len(w) else N)
+
+
+def test_sparse_operator_coeff_golden():
+    # tests/operators.h:873-881: C.coeff(i, j) equals the assembled dense matrix
+    # [[3,3,0],[3,3,3],[0,3,3]] (and :939-941 for the 2x1 block operator)
+    diameter = 0.1
+    pos = np.array([[0, 0, 0], [diameter * 0.9, 0, 0], [diameter * 1.8, 0, 0]], dtype=np.float64)
+    o = orc.Oracle(3)
+    out = o.init_neighbour_search(pos, -1.0, 1.0, False)
+    s1, s2 = np.full(3, 1.0), np.full(3, 2.0)
+    ii, jj = np.divmod(np.arange(9), 3)
+    c = o.coeff(out["pos"], out["pos"], ii, jj, orc.K_CONST_SUM, [], diameter, row_vars=[s1], col_vars=[s2]).reshape(3, 3)
+    ids = out["order"]
+    expect = np.array([[0.0 if {int(ids[i]), int(ids[j])} == {0, 2} else 3.0 for j in range(3)] for i in range(3)])
+    assert np.array_equal(c, expect)
+    ii, jj = np.divmod(np.arange(18), 3)
+    c2 = o.coeff(out["pos"], out["pos"], ii, jj, orc.K_CONST_SUM_DIFF, [], diameter, BR=2, BC=1, row_vars=[s1], col_vars=[s2]).reshape(6, 3)
+    assert np.array_equal(c2[0::2], expect)
+    assert np.array_equal(c2[1::2], -expect / 3.0)
+    # the coeff predicate is strict and uses the minimum image (src/detail/Kernels.h:358-367):
+    # a pair at exactly r is IN the product (<=) but NOT in coeff (<)
+    pos = np.array([[0.125, 0.5, 0.5], [0.375, 0.5, 0.5], [0.9375, 0.5, 0.5]])  # exactly representable
+    o = orc.Oracle(3)
+    out = o.init_neighbour_search(pos, 0.0, 1.0, True)
+    sp = out["pos"]
+    r = 0.25
+    ii, jj = np.divmod(np.arange(9), 3)
+    c = o.coeff(sp, sp, ii, jj, orc.K_CONST_SUM, [], r, row_vars=[s1], col_vars=[s2]).reshape(3, 3)
+    cnt, _ = o.pair_stats(sp, r)
+    x = sp[:, 0]
+    a, b, cc = [int(np.argmin(np.abs(x - v))) for v in (0.125, 0.375, 0.9375)]
+    assert c[a, b] == 0.0 and c[b, a] == 0.0          # |dx| == r exactly: excluded by '<'
+    assert c[a, cc] == 3.0 and c[cc, a] == 3.0        # 0.125 <-> 0.9375 through the periodic boundary (|dx| = 0.1875)
+    assert cnt[a] == 3 and cnt[b] == 2 and cnt[cc] == 2   # the search (<=) does take the pair at exactly r
