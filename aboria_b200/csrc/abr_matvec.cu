@@ -6,6 +6,10 @@
 #include "abr_internal.h"
 #include "aboria_b200/device_kernel.cuh"
 
+#ifndef ABR_FAST_INVDIST
+#define ABR_FAST_INVDIST 1
+#endif
+
 namespace abr {
 
 // (x, y, z, b) records for the tiled kernel: the drain gathers position and b of a
@@ -156,6 +160,7 @@ template <int D> static int dispatch_builtin(Handle *h, const abr_matvec_plan &p
     return launch_checked<D, ConstSumDiff, false>(h, p, ConstSumDiff{k->row_vars[0], k->col_vars[0]});
   case ABR_K_INV_DIST:
     if (k->block_rows != 1 || k->block_cols != 1) break;
+    if (ABR_FAST_INVDIST && k->params[0] >= 1e-100 && k->params[0] <= 1e100 && p.use_tiled) return launch_checked<D, InvDistFast, false>(h, p, InvDistFast{k->params[0]});
     return launch_checked<D, InvDist, false>(h, p, InvDist{k->params[0]});
   case ABR_K_INV_DIST_AA:
     if (k->block_rows != 1 || k->block_cols != 1) break;

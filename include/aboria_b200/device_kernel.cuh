@@ -40,6 +40,28 @@ __device__ __forceinline__ double sqrt_d2(double d2) {
   return pos ? s : 0.0;
 }
 
+// Variants without the library's special-case paths, for arguments known to be
+// normal numbers (the host checks the kernel's parameters before choosing them):
+// hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22) + one third-order correction, error
+// ~1 ulp — inside the 1e-12 budget — and no divergent slow-path call in the drain.
+__device__ __forceinline__ double sqrt_d2_fast(double d2) {
+  const bool pos = d2 > 1e-280; // below: a coincident pair
+  const double x = pos ? d2 : 1.0;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  y = fma(c, y * e, y);
+  const double s = x * y;
+  return pos ? s : 0.0;
+}
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);
+}
+
 namespace functors {
 
 // tests/operators.h:842-847
@@ -68,6 +90,16 @@ struct InvDist {
   double eps;
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
     blk[0] = __drcp_rn(sqrt_d2(d2) + eps);
+  }
+};
+// the same for eps in [1e-100, 1e100] (|dx| + eps is then a normal number far from
+// overflow): branch-free sqrt and reciprocal
+struct InvDistFast {
+  static constexpr bool NEEDS_DX = false;
+  static constexpr int BR = 1, BC = 1;
+  double eps;
+  __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
+    blk[0] = rcp_fast(sqrt_d2_fast(d2) + eps);
   }
 };
 // tests/operators.h:251-256
