@@ -118,13 +118,47 @@ struct TileTab {
   const uint32_t *total;   // number of tiles in use (device)
 };
 
+// One element of one column, src -> dst.  All loads of a batch (up to CB 8-byte words)
+// are issued before the first store, so an element costs one memory round trip per
+// batch instead of one per word (the reorder kernels are latency bound, profiles/).
+template <int CB = 8>
 __device__ __forceinline__ void copy_element(const uint8_t *__restrict__ s, uint8_t *__restrict__ t, uint32_t eb) {
   if ((eb & 7u) == 0 && (((uintptr_t)s | (uintptr_t)t) & 7u) == 0) {
-    for (uint32_t w = 0; w < eb / 8; ++w) reinterpret_cast<uint64_t *>(t)[w] = __ldg(reinterpret_cast<const uint64_t *>(s) + w);
+    const uint64_t *s8 = reinterpret_cast<const uint64_t *>(s);
+    uint64_t *t8 = reinterpret_cast<uint64_t *>(t);
+    const uint32_t words = eb / 8;
+    for (uint32_t w0 = 0; w0 < words; w0 += CB) {
+      uint64_t v[CB];
+#pragma unroll
+      for (int i = 0; i < CB; ++i)
+        if (w0 + i < words) v[i] = __ldg(s8 + w0 + i);
+#pragma unroll
+      for (int i = 0; i < CB; ++i)
+        if (w0 + i < words) t8[w0 + i] = v[i];
+    }
   } else if ((eb & 3u) == 0 && (((uintptr_t)s | (uintptr_t)t) & 3u) == 0) {
-    for (uint32_t w = 0; w < eb / 4; ++w) reinterpret_cast<uint32_t *>(t)[w] = __ldg(reinterpret_cast<const uint32_t *>(s) + w);
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s);
+    uint32_t *t4 = reinterpret_cast<uint32_t *>(t);
+    const uint32_t words = eb / 4;
+    for (uint32_t w0 = 0; w0 < words; w0 += CB) {
+      uint32_t v[CB];
+#pragma unroll
+      for (int i = 0; i < CB; ++i)
+        if (w0 + i < words) v[i] = __ldg(s4 + w0 + i);
+#pragma unroll
+      for (int i = 0; i < CB; ++i)
+        if (w0 + i < words) t4[w0 + i] = v[i];
+    }
   } else {
-    for (uint32_t w = 0; w < eb; ++w) t[w] = __ldg(s + w);
+    for (uint32_t w0 = 0; w0 < eb; w0 += CB) {
+      uint8_t v[CB];
+#pragma unroll
+      for (int i = 0; i < CB; ++i)
+        if (w0 + i < eb) v[i] = __ldg(s + w0 + i);
+#pragma unroll
+      for (int i = 0; i < CB; ++i)
+        if (w0 + i < eb) t[w0 + i] = v[i];
+    }
   }
 }
 
@@ -200,6 +234,16 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
   if (!ti.live) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t lane_lt = (1u << lane) - 1u;
+  if (MOVE_RECORDS) {
+    // the records of this tile are a contiguous window of every column: start pulling it
+    // into L2 now, the copy at the end of the kernel then runs at L2 latency
+    for (int c = 0; c < cols.ncols; ++c) {
+      const uint64_t bytes = (uint64_t)ti.count * cols.eb[c];
+      const uint8_t *base = cols.src[c] + (uint64_t)ti.start * cols.eb[c];
+      for (uint64_t off = (uint64_t)tid * 128; off < bytes; off += (uint64_t)RS_THREADS * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
+  }
   for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
   __syncthreads();
 
@@ -288,7 +332,7 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     if (MOVE_RECORDS) {
       for (int c = 0; c < cols.ncols; ++c) {
         const uint32_t eb = cols.eb[c];
-        copy_element(cols.src[c] + (uint64_t)src * eb, cols.dst[c] + (uint64_t)out * eb, eb);
+        copy_element<4>(cols.src[c] + (uint64_t)src * eb, cols.dst[c] + (uint64_t)out * eb, eb);
       }
     }
   }
@@ -589,7 +633,7 @@ k_gather_phased(const GatherCols cols, const int32_t *__restrict__ order, uint64
 // Final reorder of the two-level build, all columns in one launch: the permutation
 // is read once per particle and every source element sits in the L2-resident bin of
 // its destination.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_gather_fused(const GatherCols cols, const uint32_t *__restrict__ perm, uint32_t n_out, const uint32_t *__restrict__ n_dev) {
   if (n_dev) n_out = min(n_out, *n_dev);
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -598,7 +642,7 @@ k_gather_fused(const GatherCols cols, const uint32_t *__restrict__ perm, uint32_
 #pragma unroll 1
   for (int c = 0; c < cols.ncols; ++c) {
     const uint32_t eb = cols.eb[c];
-    copy_element(cols.src[c] + (uint64_t)o * eb, cols.dst[c] + (uint64_t)k * eb, eb);
+    copy_element<4>(cols.src[c] + (uint64_t)o * eb, cols.dst[c] + (uint64_t)k * eb, eb);
   }
 }
 
