@@ -11,7 +11,7 @@ from ._lib import AbrError, LIB_PATH  # noqa: F401
 
 def __getattr__(name):
     if name in ("Particles", "SparseOperator", "create_sparse_operator", "Query", "BlockOperator", "ZeroOperator",
-                "create_block_operator", "create_zero_operator"):
+                "create_block_operator", "create_zero_operator", "accumulate_within_distance"):
         from . import particles
 
         return getattr(particles, name)

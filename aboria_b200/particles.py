@@ -556,6 +556,27 @@ def create_block_operator(NI, NJ, *blocks):
     return BlockOperator(NI, NJ, blocks)
 
 
+def accumulate_within_distance(row_particles, col_particles, radius, kernel, init=0.0):
+    """AccumulateWithinDistance<std::plus<T>> evaluated for every row particle
+    (src/Symbolic.h:420-444 -> sparse_sum_impl, src/detail/Contexts.h:247-289):
+        s_a = init;  for b in euclidean_search(cols, r_a, radius): s_a = s_a + expr(dx, a, b)
+    with `expr` given as a kernel function (the restricted expression subset: anything
+    written as a device functor F(dx, a, b), scalar or BR x 1 vector valued — e.g. the
+    density and pressure sums of tests/sph.h:295-353, kernels.sph_density / sph_pressure).
+    It is the sparse product with b == 1 accumulated onto `init`, so it runs on the same
+    cell-tiled kernel.  Returns a (n_rows,) or (n_rows, BR) device tensor."""
+    if kernel.block_cols != 1:
+        raise ValueError("accumulate_within_distance: the summand must be scalar or BR x 1")
+    op = SparseOperator(row_particles, col_particles, radius, kernel)
+    dev = col_particles.device
+    ones = torch.ones(op.cols(), dtype=torch.float64, device=dev)
+    y = torch.empty(op.rows(), dtype=torch.float64, device=dev)
+    br = kernel.block_rows
+    y.view(-1, br)[:] = torch.as_tensor(init, dtype=torch.float64, device=dev)
+    op.evaluate(y, ones)
+    return y if br == 1 else y.view(-1, br)
+
+
 def create_sparse_operator(row_particles, col_particles, radius, kernel):
     """create_sparse_operator(rows, cols, radius | radius_function, f)
     (src/Operators.h:478-516).  `radius` may be a float or a per-row array

@@ -8,6 +8,9 @@
 //     update_positions()                                     Particles.h:526-531, 694-724
 //   create_sparse_operator(rows, cols, radius, f)            Operators.h:478-516
 //   K * b                                                    Operators.h:153 -> Kernels.h:720-751
+//   K.coeff(i, j), K.assemble(triplets)                      Operators.h:149-151, Kernels.h:653-685
+//   create_zero_operator, create_block_operator<NI,NJ>       Operators.h:531-548
+//   init_id_search(), get_query().find(id)                   NeighbourSearchBase.h:294-298, CellListOrdered.h:379-388
 // on top of the C-ABI in abr.h.  Plain C++14, no CUDA headers needed: the user
 // TU is compiled by the host compiler and linked with libabr.so.
 //
@@ -148,8 +151,8 @@ public:
 
   typedef particle_value<DomainD, UserVars...> value_type;
 
-  Particles() : next_id_(0), searchable_(false) { open(); }
-  explicit Particles(size_t n) : next_id_(0), searchable_(false) {
+  Particles() : next_id_(0), searchable_(false), id_map_(false) { open(); }
+  explicit Particles(size_t n) : next_id_(0), searchable_(false), id_map_(false) {
     open();
     resize(n);
   }
@@ -227,7 +230,42 @@ public:
     download_all(std::make_index_sequence<n_columns>());
     n_device_ = n_alive;
     searchable_ = true;
+    if (id_map_) update_id_map();
   }
+
+  // find-by-id (src/NeighbourSearchBase.h:294-298, :440-486): an id -> position map sorted
+  // by id, rebuilt by every update_positions like the reference's
+  void init_id_search() {
+    id_map_ = true;
+    if (n_device_ != size() || !dev_[1]) { // no device copy yet (no neighbour search): ship the id column
+      free_device();
+      alloc_device(size());
+      upload_all(std::make_index_sequence<n_columns>());
+      n_device_ = size();
+    }
+    update_id_map();
+  }
+  // the part of CellListOrderedQuery this path uses (src/CellListOrdered.h:285-599)
+  struct Query {
+    const Particles *p;
+    size_t number_of_particles() const { return p->size(); }
+    // find(id) (src/CellListOrdered.h:379-388): the reference returns a pointer into the
+    // particle set, `begin + n` when the id is absent; here: the index, n when absent
+    size_t find(const size_t id_to_find) const {
+      ABR_CHECK(p->id_map_, "init_id_search not called on this particle set");
+      abr_handle h = p->h_;
+      uint64_t *q = nullptr;
+      detail::check_rc(h, abr_malloc(h, (void **)&q, 2 * sizeof(uint64_t)), "find");
+      const uint64_t idv = id_to_find;
+      uint64_t out = 0;
+      detail::check_rc(h, abr_memcpy_h2d(h, q, &idv, sizeof(idv)), "find");
+      detail::check_rc(h, abr_id_find(h, q, 1, q + 1), "find");
+      detail::check_rc(h, abr_memcpy_d2h(h, &out, q + 1, sizeof(out)), "find");
+      abr_free(h, q);
+      return (size_t)out;
+    }
+  };
+  Query get_query() const { return Query{this}; }
 
   bool searchable() const { return searchable_; }
   abr_handle handle() const { return h_; }
@@ -243,6 +281,9 @@ public:
   }
 
 private:
+  void update_id_map() {
+    detail::check_rc(h_, abr_id_map_build(h_, static_cast<const uint64_t *>(dev_[1]), n_device_), "init_id_search");
+  }
   void open() {
     h_ = nullptr;
     int rc = abr_create(&h_, 0, nullptr);
@@ -288,6 +329,7 @@ private:
   data_type data_;
   size_t next_id_;
   bool searchable_;
+  bool id_map_;
   abr_handle h_;
   void *dev_[n_columns], *dev_other_[n_columns];
   size_t elem_bytes_[n_columns];
@@ -403,6 +445,69 @@ public:
     return y;
   }
 
+  // K.coeff(i, j) (src/Operators.h:149-151 -> src/Kernels.h:102-112 over detail::sparse_kernel,
+  // src/detail/Kernels.h:336-367): minimum-image dx, STRICT |dx|^2 < r^2
+  double coeff(const size_t i, const size_t j) const {
+    ABR_CHECK(i < rows(), "i greater than rows()");
+    ABR_CHECK(j < cols(), "j greater than cols()");
+    abr_handle h = cols_.handle();
+    const bool same = (const void *)&rows_ == (const void *)&cols_;
+    const double *row_pos = same ? cols_.device_positions() : upload_row_positions();
+    KernelDesc k = k_;
+    k.bind(rows_, cols_);
+    uint64_t *ij = nullptr;
+    detail::check_rc(h, abr_malloc(h, (void **)&ij, 3 * sizeof(uint64_t)), "coeff");
+    const uint64_t host_ij[2] = {i, j};
+    detail::check_rc(h, abr_memcpy_h2d(h, ij, host_ij, sizeof(host_ij)), "coeff");
+    detail::check_rc(h, abr_query_set_particles(h, cols_.device_positions(), cols_.device_size()), "coeff");
+    detail::check_rc(h, abr_sparse_coeff(h, row_pos, rows_.size(), &k.d, radius_, nullptr, ij, ij + 1, 1, reinterpret_cast<double *>(ij + 2)), "coeff");
+    double out = 0;
+    detail::check_rc(h, abr_memcpy_d2h(h, &out, ij + 2, sizeof(out)), "coeff");
+    abr_free(h, ij);
+    if (!same) abr_free(h, const_cast<double *>(row_pos));
+    return out;
+  }
+
+  // K.assemble(std::vector<Triplet>&, startI, startJ) (src/Kernels.h:653-685): one
+  // (row, col, value) triplet per scalar entry, rows in order, the entries of a row in the
+  // order of the reference's search iterator.  Triplet: any type constructible from
+  // (row, col, value), e.g. Eigen::Triplet<double>.
+  template <typename Triplet> void assemble(std::vector<Triplet> &triplets, const size_t startI = 0, const size_t startJ = 0) const {
+    ABR_CHECK(cols_.searchable(), "column particles have no neighbour search");
+    abr_handle h = cols_.handle();
+    const bool same = (const void *)&rows_ == (const void *)&cols_;
+    const double *row_pos = same ? cols_.device_positions() : upload_row_positions();
+    KernelDesc k = k_;
+    k.bind(rows_, cols_);
+    const size_t nr = rows_.size(), BR = k.d.block_rows, BC = k.d.block_cols;
+    uint32_t *row_ptr = nullptr;
+    detail::check_rc(h, abr_malloc(h, (void **)&row_ptr, (nr + 1) * sizeof(uint32_t)), "assemble");
+    uint64_t nnz = 0;
+    detail::check_rc(h, abr_sparse_assemble(h, row_pos, nr, same ? 1 : 0, &k.d, radius_, nullptr, row_ptr, nullptr, nullptr, 0, &nnz), "assemble");
+    int32_t *col = nullptr;
+    double *val = nullptr;
+    detail::check_rc(h, abr_malloc(h, (void **)&col, (nnz + 1) * sizeof(int32_t)), "assemble");
+    detail::check_rc(h, abr_malloc(h, (void **)&val, (nnz * BR * BC + 1) * sizeof(double)), "assemble");
+    detail::check_rc(h, abr_sparse_assemble(h, row_pos, nr, same ? 1 : 0, &k.d, radius_, nullptr, row_ptr, col, val, nnz, &nnz), "assemble");
+    std::vector<uint32_t> hp(nr + 1);
+    std::vector<int32_t> hc(nnz);
+    std::vector<double> hv(nnz * BR * BC);
+    detail::check_rc(h, abr_memcpy_d2h(h, hp.data(), row_ptr, (nr + 1) * sizeof(uint32_t)), "assemble");
+    if (nnz) {
+      detail::check_rc(h, abr_memcpy_d2h(h, hc.data(), col, nnz * sizeof(int32_t)), "assemble");
+      detail::check_rc(h, abr_memcpy_d2h(h, hv.data(), val, nnz * BR * BC * sizeof(double)), "assemble");
+    }
+    for (size_t i = 0; i < nr; ++i)
+      for (uint32_t e = hp[i]; e < hp[i + 1]; ++e)
+        for (size_t ii = 0; ii < BR; ++ii)
+          for (size_t jj = 0; jj < BC; ++jj)
+            triplets.push_back(Triplet(i * BR + ii + startI, (size_t)hc[e] * BC + jj + startJ, hv[((size_t)e * BR + ii) * BC + jj]));
+    abr_free(h, row_ptr);
+    abr_free(h, col);
+    abr_free(h, val);
+    if (!same) abr_free(h, const_cast<double *>(row_pos));
+  }
+
 private:
   const double *upload_row_positions() const {
     abr_handle h = cols_.handle();
@@ -423,6 +528,128 @@ template <typename RowParticles, typename ColParticles, typename KernelDesc>
 SparseOperator<RowParticles, ColParticles, KernelDesc> create_sparse_operator(const RowParticles &rows, const ColParticles &cols,
                                                                              const double radius, const KernelDesc &k) {
   return SparseOperator<RowParticles, ColParticles, KernelDesc>(rows, cols, radius, k);
+}
+
+// ---- zero and block operators -------------------------------------------------------
+// create_zero_operator (src/Operators.h:531-537, KernelZero)
+template <typename RowParticles, typename ColParticles> class ZeroOperator {
+public:
+  ZeroOperator(const RowParticles &rows, const ColParticles &cols) : rows_(rows), cols_(cols) {}
+  size_t rows() const { return rows_.size(); }
+  size_t cols() const { return cols_.size(); }
+  template <typename LHS, typename RHS> void evaluate(LHS &, const RHS &) const {}
+  double coeff(size_t, size_t) const { return 0.0; }
+  template <typename Triplet> void assemble(std::vector<Triplet> &, size_t = 0, size_t = 0) const {}
+
+private:
+  const RowParticles &rows_;
+  const ColParticles &cols_;
+};
+template <typename RowParticles, typename ColParticles>
+ZeroOperator<RowParticles, ColParticles> create_zero_operator(const RowParticles &rows, const ColParticles &cols) {
+  return ZeroOperator<RowParticles, ColParticles>(rows, cols);
+}
+
+// create_block_operator<NI,NJ>(blocks...) (src/Operators.h:541-548): NI x NJ blocks, row
+// major, behind one operator.  Product as in src/detail/Operators.h:170-198 (block (I,J)
+// works on y.segment(start_row(I)) and x.segment(start_col(J)) and accumulates), coeff as
+// in src/Operators.h:242-251, assemble with the block's start offsets (:253-262).
+namespace detail {
+// a window of a vector with data()/size()/operator[]
+struct segment {
+  double *p;
+  size_t n;
+  double *data() { return p; }
+  const double *data() const { return p; }
+  size_t size() const { return n; }
+  double &operator[](size_t i) { return p[i]; }
+  const double &operator[](size_t i) const { return p[i]; }
+};
+} // namespace detail
+
+template <unsigned int NI, unsigned int NJ, typename... Ops> class BlockOperator {
+  static_assert(sizeof...(Ops) == NI * NJ, "create_block_operator: need NI*NJ blocks");
+
+public:
+  explicit BlockOperator(const Ops &... ops) : blocks_(ops...) {}
+  size_t rows() const { return row_start(NI); }
+  size_t cols() const { return col_start(NJ); }
+
+  template <typename LHS, typename RHS> void evaluate(LHS &lhs, const RHS &rhs) const {
+    ABR_CHECK((size_t)lhs.size() == rows(), "lhs vector has incompatible size");
+    ABR_CHECK((size_t)rhs.size() == cols(), "rhs vector has incompatible size");
+    eval_all(lhs, rhs, std::make_index_sequence<NI * NJ>());
+  }
+  template <typename VectorType> VectorType operator*(const VectorType &b) const {
+    VectorType y(rows());
+    for (size_t i = 0; i < rows(); ++i) y[i] = 0.0;
+    evaluate(y, b);
+    return y;
+  }
+  double coeff(const size_t i, const size_t j) const {
+    double out = 0.0;
+    coeff_all(i, j, out, std::make_index_sequence<NI * NJ>());
+    return out;
+  }
+  template <typename Triplet> void assemble(std::vector<Triplet> &triplets) const {
+    assemble_all(triplets, std::make_index_sequence<NI * NJ>());
+  }
+
+private:
+  template <size_t K> size_t block_rows() const { return std::get<K>(blocks_).rows(); }
+  template <size_t K> size_t block_cols() const { return std::get<K>(blocks_).cols(); }
+  // sizes of block row I = rows of block (I, 0); of block column J = cols of block (0, J)
+  size_t rows_of(size_t I) const { return rows_of_impl(I, std::make_index_sequence<NI * NJ>()); }
+  size_t cols_of(size_t J) const { return cols_of_impl(J, std::make_index_sequence<NI * NJ>()); }
+  template <size_t... K> size_t rows_of_impl(size_t I, std::index_sequence<K...>) const {
+    size_t r = 0;
+    int dummy[] = {((K == I * NJ) ? (r = block_rows<K>(), 0) : 0)...};
+    (void)dummy;
+    return r;
+  }
+  template <size_t... K> size_t cols_of_impl(size_t J, std::index_sequence<K...>) const {
+    size_t c = 0;
+    int dummy[] = {((K == J) ? (c = block_cols<K>(), 0) : 0)...};
+    (void)dummy;
+    return c;
+  }
+  size_t row_start(size_t I) const {
+    size_t s = 0;
+    for (size_t i = 0; i < I; ++i) s += rows_of(i);
+    return s;
+  }
+  size_t col_start(size_t J) const {
+    size_t s = 0;
+    for (size_t j = 0; j < J; ++j) s += cols_of(j);
+    return s;
+  }
+  template <typename LHS, typename RHS, size_t... K> void eval_all(LHS &lhs, const RHS &rhs, std::index_sequence<K...>) const {
+    int dummy[] = {(eval_one<K>(lhs, rhs), 0)...};
+    (void)dummy;
+  }
+  template <size_t K, typename LHS, typename RHS> void eval_one(LHS &lhs, const RHS &rhs) const {
+    const size_t I = K / NJ, J = K % NJ;
+    detail::segment y{lhs.data() + row_start(I), rows_of(I)};
+    const detail::segment x{const_cast<double *>(rhs.data()) + col_start(J), cols_of(J)};
+    std::get<K>(blocks_).evaluate(y, x);
+  }
+  template <size_t... K> void coeff_all(size_t i, size_t j, double &out, std::index_sequence<K...>) const {
+    int dummy[] = {(coeff_one<K>(i, j, out), 0)...};
+    (void)dummy;
+  }
+  template <size_t K> void coeff_one(size_t i, size_t j, double &out) const {
+    const size_t I = K / NJ, J = K % NJ;
+    if (i >= row_start(I) && i < row_start(I + 1) && j >= col_start(J) && j < col_start(J + 1))
+      out += std::get<K>(blocks_).coeff(i - row_start(I), j - col_start(J));
+  }
+  template <typename Triplet, size_t... K> void assemble_all(std::vector<Triplet> &t, std::index_sequence<K...>) const {
+    int dummy[] = {(std::get<K>(blocks_).assemble(t, row_start(K / NJ), col_start(K % NJ)), 0)...};
+    (void)dummy;
+  }
+  std::tuple<Ops...> blocks_;
+};
+template <unsigned int NI, unsigned int NJ, typename... Ops> BlockOperator<NI, NJ, Ops...> create_block_operator(const Ops &... ops) {
+  return BlockOperator<NI, NJ, Ops...>(ops...);
 }
 
 } // namespace Aboria

@@ -280,6 +280,22 @@ def _coeff(self, row_pos, col_pos, ii, jj, kernel_id, params, radius, BR=1, BC=1
 Oracle.coeff = _coeff
 
 
+def _accumulate_within_distance(self, row_pos, kernel_id, params, radius, BR=1, row_vars=(), col_vars=(), init=0.0):
+    """AccumulateWithinDistance<std::plus> per row (src/detail/Contexts.h:247-289 sparse_sum_impl):
+    sum = init; for b in distance_search<2>(cols, r_a, radius): sum = sum + expr(dx, a, b), in the
+    iterator's order.  Restated through orc_sparse_matvec with rhs == 1 (x * 1.0 is exact) and
+    lhs preset to init: the same sequential additions in the same order."""
+    n = np.asarray(row_pos).shape[0]
+    y0 = np.empty((n, BR), dtype=np.float64)
+    y0[:] = np.asarray(init, dtype=np.float64)
+    ncols = self.pos.shape[0]
+    y, _ = self.sparse_matvec(row_pos, kernel_id, params, radius, np.ones(ncols), BR=BR, BC=1, row_vars=row_vars, col_vars=col_vars, y=y0.reshape(-1).copy())
+    return y if BR == 1 else y.reshape(n, BR)
+
+
+Oracle.accumulate_within_distance = _accumulate_within_distance
+
+
 def id_map_build(ids):
     """the id map of src/NeighbourSearchBase.h:440-486: (key, value) sorted by id"""
     ids = np.ascontiguousarray(ids, dtype=np.uint64)

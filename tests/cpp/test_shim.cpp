@@ -2,8 +2,12 @@
 // linked with libabr.so).  Ports of the reference's own tests for this path:
 //   test_sparse_operator   /root/reference/tests/operators.h:810-933
 //   test_documentation     /root/reference/tests/operators.h:121-311 (sparse part)
+//   test_block_operator    /root/reference/tests/operators.h:963-1100 (with sparse blocks)
+//   test_id_search         /root/reference/tests/id_search.h:64-99
 // plus the container semantics of init_neighbour_search
 // (src/NeighbourSearchBase.h:185-238, src/Particles.h:694-724).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -85,6 +89,27 @@ static void test_sparse_operator() {
   TS_ASSERT_EQUALS(ans[4], 15.0);
   TS_ASSERT_EQUALS(ans[5], -5.0);
 
+  // C.coeff(i, j) equals the assembled matrix (tests/operators.h:873-897): 7 non-zeros, all 3
+  struct triplet {
+    size_t r, c;
+    double v;
+    triplet(size_t r_, size_t c_, double v_) : r(r_), c(c_), v(v_) {}
+  };
+  std::vector<triplet> trip;
+  C.assemble(trip);
+  TS_ASSERT_EQUALS(trip.size(), 7u);
+  double dense[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (const triplet &t : trip) {
+    dense[t.r][t.c] = t.v;
+    TS_ASSERT_EQUALS(t.v, C.coeff(t.r, t.c));
+  }
+  for (size_t i = 0; i < n; i++)
+    for (size_t j = 0; j < n; j++) TS_ASSERT_EQUALS(dense[i][j], C.coeff(i, j));
+  std::vector<triplet> trip2;
+  C2.assemble(trip2);
+  TS_ASSERT_EQUALS(trip2.size(), 14u); // tests/operators.h:938
+  for (const triplet &t : trip2) TS_ASSERT_EQUALS(t.v, C2.coeff(t.r, t.c));
+
   // evaluate accumulates (lhs += K rhs)
   vector_type acc = {1, 1, 1};
   C.evaluate(acc, v);
@@ -157,8 +182,85 @@ static void test_container_semantics() {
   }
 }
 
+static void test_block_operator() {
+  // tests/operators.h:963-1100 builds [[A, B], [C, 0]] from dense blocks; dense kernels are
+  // outside this path, so the same arrangement is made of sparse blocks
+  ABORIA_VARIABLE(scalar1, double, "scalar1")
+  ABORIA_VARIABLE(scalar2, double, "scalar2")
+  typedef Particles<std::tuple<scalar1, scalar2>> ParticlesType;
+  typedef position_d<3> position;
+  ParticlesType particles, augment;
+  const double diameter = 0.1;
+  ParticlesType::value_type p;
+  for (int i = 0; i < 3; ++i) {
+    get<position>(p) = vdouble3(diameter * 0.9 * i, 0, 0);
+    get<scalar1>(p) = 1 + i;
+    get<scalar2>(p) = 0.1 * (1 + i);
+    particles.push_back(p);
+  }
+  get<scalar1>(p) = 0;
+  get<scalar2>(p) = 0.5;
+  get<position>(p) = vdouble3(-diameter * 0.5, 0, 0);
+  augment.push_back(p);
+  particles.init_neighbour_search(vdouble3::Constant(-1), vdouble3::Constant(1), vbool3::Constant(false));
+  augment.init_neighbour_search(vdouble3::Constant(-1), vdouble3::Constant(1), vbool3::Constant(false));
+  const size_t n = 3;
+  auto A = create_sparse_operator(particles, particles, diameter, kernels::const_sum<scalar1, scalar2>());
+  auto B = create_sparse_operator(particles, augment, diameter, kernels::const_sum<scalar1, scalar2>());
+  auto C = create_sparse_operator(augment, particles, diameter, kernels::const_sum<scalar2, scalar1>());
+  auto Zero = create_zero_operator(augment, augment);
+  auto Full = create_block_operator<2, 2>(A, B, C, Zero);
+  TS_ASSERT_EQUALS(Full.rows(), n + 1);
+  TS_ASSERT_EQUALS(Full.cols(), n + 1);
+  vector_type v = {1, 2, 3, 4};
+  vector_type ans = Full * v;
+  // dense composition through coeff
+  for (size_t i = 0; i < n + 1; ++i) {
+    double sum = 0;
+    for (size_t j = 0; j < n + 1; ++j) sum += Full.coeff(i, j) * v[j];
+    TS_ASSERT(std::fabs(sum - ans[i]) <= 1e-14 * (1 + std::fabs(sum)));
+  }
+  TS_ASSERT_EQUALS(Full.coeff(n, n), 0.0);
+  // particle at -0.05 is within 0.1 of x = 0 only
+  size_t nz_last_row = 0;
+  for (size_t j = 0; j < n; ++j) nz_last_row += Full.coeff(n, j) != 0.0;
+  TS_ASSERT_EQUALS(nz_last_row, 1u);
+  struct triplet {
+    size_t r, c;
+    double v;
+    triplet(size_t r_, size_t c_, double v_) : r(r_), c(c_), v(v_) {}
+  };
+  std::vector<triplet> trip;
+  Full.assemble(trip);
+  TS_ASSERT_EQUALS(trip.size(), 7u + 1u + 1u);
+  for (const triplet &t : trip) TS_ASSERT_EQUALS(t.v, Full.coeff(t.r, t.c));
+}
+
+static void test_id_search() {
+  // tests/id_search.h:64-99
+  const size_t N = 100;
+  typedef Particles<> particle_type;
+  particle_type particles(N);
+  std::default_random_engine g;
+  auto &ids = get<id>(particles);
+  std::shuffle(ids.begin(), ids.end(), g);
+  particles.init_id_search();
+  const size_t id_2 = particles.get_query().find(2);
+  TS_ASSERT(id_2 < N);
+  TS_ASSERT_EQUALS(get<id>(particles)[id_2], 2u);
+  const size_t id_2N = particles.get_query().find(2 * N);
+  TS_ASSERT_EQUALS(id_2N, particles.size()); // "end of the particle vector"
+  // the map follows the reorder of init_neighbour_search
+  std::uniform_real_distribution<double> uniform(0, 1);
+  for (size_t i = 0; i < N; ++i) get<particle_type::position>(particles)[i] = vdouble3(uniform(g), uniform(g), uniform(g));
+  particles.init_neighbour_search(vdouble3::Constant(0), vdouble3::Constant(1), vbool3::Constant(true));
+  for (size_t want = 0; want < N; want += 7) TS_ASSERT_EQUALS(get<id>(particles)[particles.get_query().find(want)], want);
+}
+
 int main() {
   test_sparse_operator();
+  test_block_operator();
+  test_id_search();
   test_documentation();
   test_container_semantics();
   if (failures) {

@@ -169,3 +169,29 @@ def test_block_operator():
         ab.create_block_operator(2, 2, A, B, Ct)
     with pytest.raises(ValueError):
         ab.create_block_operator(2, 2, A, A, Ct, Z)
+
+
+def test_accumulate_within_distance_sph_sums():
+    # tests/sph.h:295-353: rho[a] = sum(b, norm(dx) < 2h, mass * W(norm(dx), h)) and the vector-valued
+    # pressure sum, as AccumulateWithinDistance<std::plus> (src/detail/Contexts.h:247-289)
+    N, D = 4000, 3
+    h = 1.5 * N ** (-1.0 / 3.0)
+    r = 2 * h
+    mass, wcon = 1.0 / N, 21.0 / (256.0 * np.pi)
+    pos = synth.uniform_positions(N, D, seed=9)
+    o, out, p0 = build_both(pos, 0.0, 1.0, [True, True, False])
+    p = ab.Particles(D, N, variables={"pdr2": torch.float64})
+    p.set("position", torch.from_numpy(pos.copy()))
+    p.init_neighbour_search(0.0, 1.0, [True, True, False])
+    rho = ab.accumulate_within_distance(p, p, r, K.sph_density(h, mass, wcon)).cpu().numpy()
+    rho_ref = o.accumulate_within_distance(out["pos"], orc.K_SPH_DENSITY, [h, mass, wcon], r)
+    assert rel_l2(rho, rho_ref) <= TOL
+    # non-zero initial value (set_init, src/Symbolic.h:437-439)
+    rho7 = ab.accumulate_within_distance(p, p, r, K.sph_density(h, mass, wcon), init=7.0).cpu().numpy()
+    assert rel_l2(rho7, o.accumulate_within_distance(out["pos"], orc.K_SPH_DENSITY, [h, mass, wcon], r, init=7.0)) <= TOL
+    pdr2 = np.random.default_rng(4).random(N) + 0.5  # P/rho^2 column, in post-reorder order
+    p.set("pdr2", torch.from_numpy(pdr2))
+    acc = ab.accumulate_within_distance(p, p, r, K.sph_pressure(D, h, mass, wcon, "pdr2")).cpu().numpy()
+    acc_ref = o.accumulate_within_distance(out["pos"], orc.K_SPH_PRESSURE, [h, mass, wcon], r, BR=D, row_vars=[pdr2], col_vars=[pdr2])
+    assert acc.shape == (N, D)
+    assert rel_l2(acc, acc_ref) <= 1e-11  # near-cancelling force sums: looser absolute scale
