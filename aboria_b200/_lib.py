@@ -51,6 +51,8 @@ SIGNATURES = {
     "abr_sparse_matvec": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(KernelDesc), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "abr_sparse_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(KernelDesc), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
     "abr_sparse_coeff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(KernelDesc), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "abr_bucket_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
+    "abr_fast_bucket_search_counts": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     "abr_id_map_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "abr_id_map_get": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "abr_id_find": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

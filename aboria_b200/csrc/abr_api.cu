@@ -94,6 +94,10 @@ int abr_destroy(abr_handle hh) {
     h->idm_i[i].release();
   }
   h->idm_max.release();
+  h->scan_tmp2.release();
+  h->pair_i.release();
+  h->pair_j.release();
+  h->pair_q.release();
   h->id_map_key.release();
   h->id_map_value.release();
   if (h->d_scalars) cudaFree(h->d_scalars);
@@ -387,6 +391,20 @@ int abr_sparse_coeff(abr_handle hh, const double *row_pos, size_t n_rows, const 
   ABR_CUDA(h, cudaSetDevice(h->device));
   abr::MatvecCall c{row_pos, n_rows, 0, radius, radius_per_row, nullptr, nullptr, nullptr, nullptr, 1};
   return abr::run_coeff(h, c, k, ii, jj, m, out);
+}
+
+int abr_bucket_pairs(abr_handle hh, uint32_t *bucket_i, uint32_t *bucket_j, int8_t *quadrant, size_t capacity, uint64_t *n_pairs_host) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  return abr::run_bucket_pairs(h, bucket_i, bucket_j, quadrant, capacity, n_pairs_host);
+}
+
+int abr_fast_bucket_search_counts(abr_handle hh, double radius, uint32_t *count) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  return abr::run_fast_bucket_search_counts(h, radius, count);
 }
 
 int abr_id_map_build(abr_handle hh, const uint64_t *ids, size_t n) {

@@ -73,6 +73,7 @@ struct Handle {
   size_t two_level_min_n = (size_t)1 << 20;  // use the two-level build from this many particles (abr_set_option)
   DevBuf bucket_begin, bucket_end;
   DevBuf danger_list;
+  DevBuf scan_tmp2, pair_i, pair_j, pair_q; // bucket-pair traversal (abr_pairs.cu)
   DevBuf idm_k[2], idm_i[2], idm_max, id_map_key, id_map_value; // id map (m_id_map_key / m_id_map_value) + sort scratch
   size_t id_map_n = 0;
   DevBuf posb; // packed (x, y, z, b) records of the column particles for the tiled product
@@ -136,6 +137,9 @@ int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm);
 int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint32_t *row_ptr, int32_t *col_idx, double *values,
                  size_t capacity, uint64_t *nnz_host);
 int run_coeff(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, const uint64_t *ii, const uint64_t *jj, size_t m, double *out);
+// abr_pairs.cu
+int run_bucket_pairs(Handle *h, uint32_t *bucket_i, uint32_t *bucket_j, int8_t *quadrant, uint64_t capacity, uint64_t *n_host);
+int run_fast_bucket_search_counts(Handle *h, double radius, uint32_t *count);
 int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, const void *functor,
                       int BR, int BC);
 

@@ -42,6 +42,29 @@ class Query:
     def bucket_indices(self):
         return self.particles._bucket_view()[0]
 
+    def neighbouring_buckets(self):
+        """get_neighbouring_buckets(query) (src/Search.h:857-860): the bucket pairs of the
+        fast cell-list search in iterator order, as (bucket_i, bucket_j int32 tensors,
+        quadrant int8 tensor [n, D]); position offset of a pair = quadrant * (high - low)."""
+        p = self.particles
+        p._sync_stream()
+        n = C.c_uint64()
+        check(p._h, p._lib.abr_bucket_pairs(p._h, None, None, None, 0, C.byref(n)))
+        m = max(int(n.value), 1)
+        bi = torch.empty(m, dtype=torch.int32, device=p.device)
+        bj = torch.empty(m, dtype=torch.int32, device=p.device)
+        qd = torch.empty((m, p.D), dtype=torch.int8, device=p.device)
+        check(p._h, p._lib.abr_bucket_pairs(p._h, _ptr(bi), _ptr(bj), _ptr(qd), int(n.value), C.byref(n)))
+        return bi[: n.value], bj[: n.value], qd[: n.value]
+
+    def fast_bucket_search_counts(self, radius):
+        """neighbour counts through the bucket-pair traversal (tests/neighbours.h:892-951)"""
+        p = self.particles
+        p._sync_stream()
+        cnt = torch.zeros(max(p.size(), 1), dtype=torch.int32, device=p.device)
+        check(p._h, p._lib.abr_fast_bucket_search_counts(p._h, float(radius), _ptr(cnt)))
+        return cnt[: p.size()]
+
     def find(self, ids):
         """find(id) (src/CellListOrdered.h:379-388) for a batch of ids: the position of
         the particle with that id, or size() (the reference's end pointer) when absent."""

@@ -208,6 +208,21 @@ int abr_sparse_coeff(abr_handle h, const double *row_pos, size_t n_rows,
                      const abr_kernel_desc *kernel_host, double radius, const double *radius_per_row,
                      const uint64_t *ii, const uint64_t *jj, size_t m, double *out);
 
+/* get_neighbouring_buckets(query) -> bucket_pair_iterator (src/Search.h:498-764,
+ * :857-860), the "fast cell-list search" of tests/neighbours.h:281-300: every pair
+ * of touching buckets (i, j) once — first inside the domain (j after i in the box
+ * around i), then across every periodic boundary with the quadrant q whose position
+ * offset is q * (bmax - bmin) — in exactly the order the reference iterator yields
+ * them.  bucket_i / bucket_j: collapsed bucket numbers; quadrant: D int8 per pair.
+ * Two-call protocol: bucket_i == NULL counts only (n_pairs_host). */
+int abr_bucket_pairs(abr_handle h, uint32_t *bucket_i, uint32_t *bucket_j, int8_t *quadrant,
+                     size_t capacity, uint64_t *n_pairs_host);
+/* The loops the reference documents for that iterator (tests/neighbours.h:892-951):
+ * count[k] = number of particles within `radius` of particle k (|dx|^2 < r^2, STRICT,
+ * k itself included), every unordered pair tested once through the bucket pairs.
+ * Valid when the bucket side is >= radius, as the reference requires. */
+int abr_fast_bucket_search_counts(abr_handle h, double radius, uint32_t *count);
+
 /* Find-by-id (neighbour_search_base::init_id_map and the id-map update of
  * update_positions, src/NeighbourSearchBase.h:294-298, :440-486): builds
  * m_id_map_key (ids in ascending order) and m_id_map_value (position of that

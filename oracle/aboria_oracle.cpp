@@ -821,6 +821,217 @@ void orc_sparse_coeff(void *h, const double *row_pos, const double *col_pos, con
   }
 }
 
+// ---------------------------------------------------------------------------
+// get_neighbouring_buckets(query) -> bucket_pair_iterator (src/Search.h:498-764,
+// :857-860), the "fast cell-list search" of tests/neighbours.h:281-300.
+// Restated literally: the iterator state (m_periodic, m_i, m_j, m_domain_domain) and
+// its increment(), on top of lattice_iterator (src/LatticeIterator.h:48-291, last
+// dimension fastest).
+// ---------------------------------------------------------------------------
+namespace {
+struct LatticeIt {
+  int D = 0;
+  int mn[MAXD], mx[MAXD], idx[MAXD];
+  bool valid = false;
+  LatticeIt() {}
+  LatticeIt(int D_, const int *a, const int *b) : D(D_), valid(true) { // [a, b)
+    for (int d = 0; d < D; ++d) {
+      mn[d] = a[d];
+      mx[d] = b[d];
+      idx[d] = a[d];
+    }
+  }
+  void set(const int *v) { // operator=(const int_d&), LatticeIterator.h:118-123
+    valid = true;
+    for (int d = 0; d < D; ++d) {
+      idx[d] = v[d];
+      valid = valid && v[d] >= mn[d] && v[d] < mx[d];
+    }
+  }
+  void inc() { // LatticeIterator.h:269-280
+    for (int i = D - 1; i >= 0; --i) {
+      ++idx[i];
+      if (idx[i] < mx[i]) break;
+      if (i != 0) {
+        idx[i] = mn[i];
+      } else {
+        valid = false;
+      }
+    }
+  }
+  bool next_is_end() const { // (it + 1) == false
+    LatticeIt t = *this;
+    t.inc();
+    return !t.valid;
+  }
+};
+
+// src/Search.h:675-707 get_neighbouring_buckets(query, bucket)
+LatticeIt neighbouring_buckets(const Oracle &q, const int *bucket) {
+  int start[MAXD], end[MAXD];
+  bool no_buckets = false;
+  for (int i = 0; i < q.D; ++i) {
+    start[i] = bucket[i] - 1;
+    end[i] = bucket[i] + 1;
+    if (start[i] < 0) {
+      start[i] = 0;
+    } else if (start[i] > q.end_bucket[i]) {
+      no_buckets = true;
+      start[i] = q.end_bucket[i];
+    }
+    if (end[i] < 0) {
+      no_buckets = true;
+      end[i] = 0;
+    } else if (end[i] > q.end_bucket[i]) {
+      end[i] = q.end_bucket[i];
+    }
+  }
+  if (no_buckets) return LatticeIt();
+  int endp1[MAXD];
+  for (int i = 0; i < q.D; ++i) endp1[i] = end[i] + 1;
+  return LatticeIt(q.D, start, endp1);
+}
+// :709-720 get_neighbouring_buckets(query, bucket, quadrant): bucket + quadrant * (end_bucket + 1)
+LatticeIt neighbouring_buckets_q(const Oracle &q, const int *bucket, const int *quadrant) {
+  int b[MAXD];
+  for (int i = 0; i < q.D; ++i) b[i] = bucket[i] + quadrant[i] * (q.end_bucket[i] + 1);
+  return neighbouring_buckets(q, b);
+}
+// :722-751 get_regular_buckets(query, quadrant)
+LatticeIt regular_buckets(const Oracle &q, const int *quadrant) {
+  int start[MAXD], endp1[MAXD];
+  for (int i = 0; i < q.D; ++i) {
+    start[i] = 0;
+    int end = q.end_bucket[i];
+    if (q.periodic[i]) {
+      if (quadrant[i] > 0) {
+        start[i] = 0;
+        end = 0;
+      } else if (quadrant[i] < 0) {
+        start[i] = q.end_bucket[i];
+        end = q.end_bucket[i];
+      }
+    }
+    endp1[i] = end + 1;
+  }
+  return LatticeIt(q.D, start, endp1);
+}
+} // namespace
+
+// Walks the whole iterator; per step writes the collapsed bucket numbers of i and j and
+// the periodic quadrant (D ints in -1..1; m_position_offset = quadrant * (bmax - bmin)).
+// Pass null outputs to count.
+uint64_t orc_bucket_pairs(void *h, uint32_t *bucket_i, uint32_t *bucket_j, int8_t *quadrant, uint64_t capacity) {
+  const Oracle &q = *static_cast<Oracle *>(h);
+  const int D = q.D;
+  // constructor, :541-575
+  int pstart[MAXD], pend[MAXD], zero[MAXD];
+  for (int i = 0; i < D; ++i) {
+    pstart[i] = q.periodic[i] ? -1 : 0;
+    pend[i] = q.periodic[i] ? 2 : 1;
+    zero[i] = 0;
+  }
+  LatticeIt m_periodic(D, pstart, pend);
+  m_periodic.set(zero);
+  bool m_valid = true, m_domain_domain = true;
+  LatticeIt m_i = regular_buckets(q, m_periodic.idx), m_j;
+  if (m_i.next_is_end()) {
+    m_domain_domain = false;
+    m_periodic.inc();
+    if (!m_periodic.valid) {
+      m_valid = false;
+    } else {
+      m_i = regular_buckets(q, m_periodic.idx);
+      m_j = neighbouring_buckets_q(q, m_i.idx, m_periodic.idx);
+    }
+  } else {
+    m_j = neighbouring_buckets_q(q, m_i.idx, m_periodic.idx);
+    m_j.set(m_i.idx);
+    m_j.inc();
+  }
+  uint64_t count = 0;
+  while (m_valid) {
+    if (bucket_i && count < capacity) {
+      bucket_i[count] = (uint32_t)collapse_index_vector(D, q.size, m_i.idx);
+      bucket_j[count] = (uint32_t)collapse_index_vector(D, q.size, m_j.idx);
+      for (int d = 0; d < D; ++d) quadrant[count * D + d] = (int8_t)m_periodic.idx[d];
+    }
+    ++count;
+    // increment(), :627-667
+    m_j.inc();
+    if (!m_j.valid) {
+      m_i.inc();
+      if (m_domain_domain ? m_i.next_is_end() : !m_i.valid) {
+        m_domain_domain = false;
+        m_periodic.inc();
+        if (!m_periodic.valid) {
+          m_valid = false;
+        } else {
+          m_i = regular_buckets(q, m_periodic.idx);
+          m_j = neighbouring_buckets_q(q, m_i.idx, m_periodic.idx);
+        }
+      } else {
+        m_j = neighbouring_buckets_q(q, m_i.idx, m_periodic.idx);
+        if (m_domain_domain) {
+          m_j.set(m_i.idx);
+          m_j.inc();
+        }
+      }
+    }
+  }
+  return count;
+}
+
+// The fast cell-list search of tests/neighbours.h:892-951 (the user-side loops the
+// reference documents for this iterator): per particle the number of neighbours with
+// |p_i + offset - p_j|^2 < r^2 (STRICT), each unordered pair found once and counted for
+// both particles, plus the self count.
+void orc_fast_bucket_search_counts(void *h, double radius, uint32_t *count) {
+  const Oracle &q = *static_cast<Oracle *>(h);
+  const int D = q.D;
+  const double r2 = radius * radius;
+  for (size_t i = 0; i < q.n; ++i) count[i] = 0;
+  const uint64_t np = orc_bucket_pairs(h, nullptr, nullptr, nullptr, 0);
+  std::vector<uint32_t> bi(np), bj(np);
+  std::vector<int8_t> qd(np * D);
+  orc_bucket_pairs(h, bi.data(), bj.data(), qd.data(), np);
+  for (uint64_t k = 0; k < np; ++k) {
+    double off[MAXD];
+    for (int d = 0; d < D; ++d) off[d] = qd[k * D + d] * (q.bmax[d] - q.bmin[d]);
+    for (unsigned a = q.bucket_begin[bi[k]]; a < q.bucket_end[bi[k]]; ++a) {
+      double pa[MAXD];
+      for (int d = 0; d < D; ++d) pa[d] = q.pos[(size_t)a * D + d] + off[d];
+      for (unsigned b = q.bucket_begin[bj[k]]; b < q.bucket_end[bj[k]]; ++b) {
+        double n2 = 0;
+        for (int d = 0; d < D; ++d) {
+          const double t = pa[d] - q.pos[(size_t)b * D + d];
+          n2 += t * t;
+        }
+        if (n2 < r2) {
+          count[a]++;
+          count[b]++;
+        }
+      }
+    }
+  }
+  for (size_t c = 0; c < q.bucket_begin.size(); ++c) {
+    for (unsigned a = q.bucket_begin[c]; a < q.bucket_end[c]; ++a) {
+      count[a]++; // self is a neighbour
+      for (unsigned b = a + 1; b < q.bucket_end[c]; ++b) {
+        double n2 = 0;
+        for (int d = 0; d < D; ++d) {
+          const double t = q.pos[(size_t)a * D + d] - q.pos[(size_t)b * D + d];
+          n2 += t * t;
+        }
+        if (n2 < r2) {
+          count[a]++;
+          count[b]++;
+        }
+      }
+    }
+  }
+}
+
 // brute force of tests/neighbours.h:739-764: counts j with
 // squaredNorm(pj - pi - image*(max-min)) <= r2 over 3^D images (periodic) or
 // the single image (non periodic).  NOTE the operation order differs from the

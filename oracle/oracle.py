@@ -65,6 +65,9 @@ def lib():
         L.orc_id_map_build.argtypes = [u64p, C.c_size_t, u64p, u64p]
         L.orc_id_find.argtypes = [u64p, u64p, C.c_size_t, u64p, C.c_size_t, u64p]
         L.orc_sparse_coeff.argtypes = [vp, dp, dp, u64p, u64p, C.c_size_t, C.c_int, dp, C.POINTER(dp), C.POINTER(dp), C.c_double, dp, C.c_int, C.c_int, dp]
+        L.orc_bucket_pairs.restype = C.c_uint64
+        L.orc_bucket_pairs.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int8), C.c_uint64]
+        L.orc_fast_bucket_search_counts.argtypes = [vp, C.c_double, C.POINTER(C.c_uint32)]
         L.orc_max_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -294,6 +297,28 @@ def _accumulate_within_distance(self, row_pos, kernel_id, params, radius, BR=1, 
 
 
 Oracle.accumulate_within_distance = _accumulate_within_distance
+
+
+def _bucket_pairs(self):
+    """get_neighbouring_buckets(query) (src/Search.h:498-764): (bucket_i, bucket_j, quadrant[n, D]) in iterator order"""
+    n = lib().orc_bucket_pairs(self.h, None, None, None, 0)
+    bi = np.zeros(max(n, 1), dtype=np.uint32)
+    bj = np.zeros(max(n, 1), dtype=np.uint32)
+    qd = np.zeros((max(n, 1), self.D), dtype=np.int8)
+    u32p = C.POINTER(C.c_uint32)
+    lib().orc_bucket_pairs(self.h, bi.ctypes.data_as(u32p), bj.ctypes.data_as(u32p), qd.ctypes.data_as(C.POINTER(C.c_int8)), n)
+    return bi[:n], bj[:n], qd[:n]
+
+
+def _fast_bucket_search_counts(self, radius):
+    """per-particle neighbour counts through the bucket-pair traversal (tests/neighbours.h:892-951)"""
+    out = np.zeros(self.pos.shape[0], dtype=np.uint32)
+    lib().orc_fast_bucket_search_counts(self.h, float(radius), out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out
+
+
+Oracle.bucket_pairs = _bucket_pairs
+Oracle.fast_bucket_search_counts = _fast_bucket_search_counts
 
 
 def id_map_build(ids):

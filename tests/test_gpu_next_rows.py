@@ -195,3 +195,28 @@ def test_accumulate_within_distance_sph_sums():
     acc_ref = o.accumulate_within_distance(out["pos"], orc.K_SPH_PRESSURE, [h, mass, wcon], r, BR=D, row_vars=[pdr2], col_vars=[pdr2])
     assert acc.shape == (N, D)
     assert rel_l2(acc, acc_ref) <= 1e-11  # near-cancelling force sums: looser absolute scale
+
+
+FAST_CASES = [(1, 14, 0.1, False), (1, 14, 0.1, True), (1, 1000, 0.1, True), (1, 1000, 0.1, False), (2, 1000, 0.1, True),
+              (2, 1000, 0.1, False), (2, 1000, 0.5, True), (2, 1000, 0.5, False), (2, 1000, 0.2, True), (2, 1000, 0.2, False),
+              (3, 1000, 0.2, True), (3, 1000, 0.2, False), (3, 200000, 0.03, True), (3, 50, 0.9, True), (2, 30, 1.0, True)]
+
+
+@pytest.mark.parametrize("D,N,r,periodic", FAST_CASES)
+def test_bucket_pair_iterator_parity(D, N, r, periodic):
+    # get_neighbouring_buckets(query) (src/Search.h:498-764): the device produces the reference
+    # iterator's sequence of (i, j, quadrant) bit for bit, and the fast cell-list search over it
+    # (tests/neighbours.h:892-951, case list :1330-1366) gives the oracle's / brute-force counts
+    rng = np.random.default_rng(17 * D + N)
+    pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+    required_bucket_number = N * r ** D / 2.0 ** D
+    o, out, p = build_both(pos, -1.0, 1.0, periodic, required_bucket_number)
+    bi, bj, qd = o.bucket_pairs()
+    gi, gj, gq = p.get_query().neighbouring_buckets()
+    assert np.array_equal(gi.cpu().numpy().view(np.uint32), bi)
+    assert np.array_equal(gj.cpu().numpy().view(np.uint32), bj)
+    assert np.array_equal(gq.cpu().numpy(), qd)
+    cnt = p.get_query().fast_bucket_search_counts(r).cpu().numpy().view(np.uint32)
+    assert np.array_equal(cnt, o.fast_bucket_search_counts(r))
+    if N <= 5000:
+        assert np.array_equal(cnt, orc.brute_force_counts(out["pos"], [-1.0] * D, [1.0] * D, periodic, r))

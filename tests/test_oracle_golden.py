@@ -295,3 +295,33 @@ def test_sparse_operator_coeff_golden():
     assert c[a, b] == 0.0 and c[b, a] == 0.0          # |dx| == r exactly: excluded by '<'
     assert c[a, cc] == 3.0 and c[cc, a] == 3.0        # 0.125 <-> 0.9375 through the periodic boundary (|dx| = 0.1875)
     assert cnt[a] == 3 and cnt[b] == 2 and cnt[cc] == 2   # the search (<=) does take the pair at exactly r
+
+
+FAST_CASES = [(1, 14, 0.1, False), (1, 14, 0.1, True), (1, 1000, 0.1, True), (1, 1000, 0.1, False), (2, 1000, 0.1, True),
+              (2, 1000, 0.1, False), (2, 1000, 0.5, True), (2, 1000, 0.5, False), (2, 1000, 0.2, True), (2, 1000, 0.2, False),
+              (3, 1000, 0.2, True), (3, 1000, 0.2, False)]
+
+
+@pytest.mark.parametrize("D,N,r,periodic", FAST_CASES)
+def test_fast_bucketsearch_vs_brute_force(D, N, r, periodic):
+    # tests/neighbours.h:1149-1248 with the case list :1330-1366: neighbour counts found through
+    # get_neighbouring_buckets (bucket_pair_iterator, src/Search.h:498-764) equal the brute-force counts
+    rng = np.random.default_rng(17 * D + N)
+    pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+    o = orc.Oracle(D)
+    required_bucket_number = N * r ** D / 2.0 ** D
+    out = o.init_neighbour_search(pos, -1.0, 1.0, periodic, required_bucket_number)
+    _, side = o.grid()
+    assert np.all(side >= r)  # the assumption of the fast search
+    bi, bj, qd = o.bucket_pairs()
+    assert len(bi) > 0 and np.all(bi < len(out["bucket_begin"])) and np.all(bj < len(out["bucket_begin"]))
+    # every unordered pair of touching buckets appears exactly once (no duplicates) when the grid has >= 3 buckets per side
+    size, _ = o.grid()
+    if np.all(size >= 3):
+        keys = set()
+        for a, b, q in zip(bi.tolist(), bj.tolist(), map(tuple, qd.tolist())):
+            assert (a, b, q) not in keys
+            keys.add((a, b, q))
+    cnt = o.fast_bucket_search_counts(r)
+    bf = orc.brute_force_counts(out["pos"], [-1.0] * D, [1.0] * D, periodic, r)
+    assert np.array_equal(cnt, bf)
