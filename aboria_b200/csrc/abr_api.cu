@@ -439,6 +439,15 @@ int abr_distance_search_stats(abr_handle hh, const double *row_pos, size_t n_row
   return abr::run_norm_stats(h, c, lnorm);
 }
 
+int abr_distance_search_stats_scaled(abr_handle hh, const double *row_pos, size_t n_rows, double radius, const double *radius_per_row, int lnorm,
+                                     const double *scale_host, uint32_t *count, uint64_t *hash) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::MatvecCall c{row_pos, n_rows, 0, radius, radius_per_row, nullptr, nullptr, count, hash, 1};
+  return abr::run_norm_stats(h, c, lnorm, scale_host);
+}
+
 int abr_last_counters(abr_handle hh, uint64_t counters[4]) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !counters) return ABR_ERR_INVALID;

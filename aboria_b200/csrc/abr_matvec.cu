@@ -322,8 +322,21 @@ int run_pair_stats(Handle *h, const MatvecCall &c) {
   }
 }
 
-template <int D> static int launch_norm_stats(Handle *h, const abr_matvec_plan &p, int lnorm) {
+template <int D> static int launch_norm_stats(Handle *h, const abr_matvec_plan &p, int lnorm, const double *scale_host) {
   const unsigned grid = (unsigned)((p.n_rows + 127) / 128);
+  if (scale_host) { // ScaleTransform (src/Transform.h:140-160)
+    ScaleArg sc;
+    for (int d = 0; d < MAXD; ++d) sc.s[d] = d < D ? scale_host[d] : 1.0;
+    switch (lnorm) {
+    case -1: norm_stats_kernel<D, -1, true><<<grid, 128, 0, p.stream>>>(p, sc); break;
+    case 1: norm_stats_kernel<D, 1, true><<<grid, 128, 0, p.stream>>>(p, sc); break;
+    case 2: norm_stats_kernel<D, 2, true><<<grid, 128, 0, p.stream>>>(p, sc); break;
+    default: return set_error(h, ABR_ERR_UNSUPPORTED, "distance_search: norm must be -1 (Chebyshev), 1 (Manhattan) or 2 (Euclidean)");
+    }
+    h->launches += 1;
+    ABR_CUDA(h, cudaGetLastError());
+    return ABR_OK;
+  }
   switch (lnorm) {
   case -1: norm_stats_kernel<D, -1><<<grid, 128, 0, p.stream>>>(p); break;
   case 1: norm_stats_kernel<D, 1><<<grid, 128, 0, p.stream>>>(p); break;
@@ -335,7 +348,7 @@ template <int D> static int launch_norm_stats(Handle *h, const abr_matvec_plan &
   return ABR_OK;
 }
 
-int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm) {
+int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm, const double *scale_host) {
   if (c.n_rows == 0) return ABR_OK;
   if (!c.row_pos) return set_error(h, ABR_ERR_INVALID, "distance_search: null pointer");
   abr_matvec_plan p;
@@ -344,9 +357,9 @@ int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm) {
   int rc = make_plan(h, w, 1, &p);
   if (rc) return rc;
   switch (h->D) {
-  case 1: return launch_norm_stats<1>(h, p, lnorm);
-  case 2: return launch_norm_stats<2>(h, p, lnorm);
-  default: return launch_norm_stats<3>(h, p, lnorm);
+  case 1: return launch_norm_stats<1>(h, p, lnorm, scale_host);
+  case 2: return launch_norm_stats<2>(h, p, lnorm, scale_host);
+  default: return launch_norm_stats<3>(h, p, lnorm, scale_host);
   }
 }
 

@@ -297,7 +297,7 @@ class Particles:
         """tuning knobs of the library (no effect on results), see abr_set_option"""
         check(self._h, self._lib.abr_set_option(self._h, name.encode(), float(value)))
 
-    def distance_search_stats(self, radius, lnorm, queries=None):
+    def distance_search_stats(self, radius, lnorm, queries=None, scale=None):
         """distance_search<lnorm> / chebyshev_search (-1) / manhatten_search (1) /
         euclidean_search (2) from `queries` (default: the particles themselves):
         per query the neighbour count and pair-set hash."""
@@ -306,6 +306,10 @@ class Particles:
         n = qp.shape[0]
         cnt = torch.zeros(n, dtype=torch.int32, device=self.device)
         hs = torch.zeros(n, dtype=torch.int64, device=self.device)
+        if scale is not None:  # create_scale_transform(scale) (src/Transform.h:140-172)
+            sc = np.ascontiguousarray(np.broadcast_to(np.asarray(scale, dtype=np.float64), (self.D,)))
+            check(self._h, self._lib.abr_distance_search_stats_scaled(self._h, _ptr(qp), n, float(radius), None, int(lnorm), sc.ctypes.data, _ptr(cnt), _ptr(hs)))
+            return cnt, hs
         check(self._h, self._lib.abr_distance_search_stats(self._h, _ptr(qp), n, float(radius), None, int(lnorm), _ptr(cnt), _ptr(hs)))
         return cnt, hs
 

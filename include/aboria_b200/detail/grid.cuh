@@ -101,8 +101,11 @@ template <int LN> struct DistHelper {
 // lattice_iterator_within_distance<Query,LNormNumber,IdentityTransform>
 // (src/NeighbourSearchBase.h:1720-2009), restated for the device.
 // ---------------------------------------------------------------------------
-template <int D, int LN = 2> struct BucketWalk {
+// SC = true: ScaleTransform (src/Transform.h:140-160; v -> v * scale, a box's extent ->
+// (bmax - bmin) * scale) applied wherever the reference applies m_transform.
+template <int D, int LN = 2, bool SC = false> struct BucketWalk {
   const Grid &g;
+  const double *sc;
   double qp[D];
   double half[D];
   double r2;
@@ -119,7 +122,9 @@ template <int D, int LN = 2> struct BucketWalk {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const double centre = ((double)b[i] + 0.5) * g.side[i] + g.bmin[i];
-      const double t = fmax(fabs(centre - qp[i]) - half[i], 0.0);
+      double dxi = centre - qp[i];
+      if (SC) dxi = dxi * sc[i];
+      const double t = fmax(fabs(dxi) - half[i], 0.0);
       acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(t));
     }
     return acc;
@@ -129,8 +134,9 @@ template <int D, int LN = 2> struct BucketWalk {
     double acc = 0;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const double dx = 0.5 * (g.bmin[i] + g.bmax[i]) - qp[i];
-      const double hl = 0.5 * (g.bmax[i] - g.bmin[i]);
+      double dx = 0.5 * (g.bmin[i] + g.bmax[i]) - qp[i];
+      if (SC) dx = dx * sc[i];
+      const double hl = SC ? 0.5 * ((g.bmax[i] - g.bmin[i]) * sc[i]) : 0.5 * (g.bmax[i] - g.bmin[i]);
       const double t = fmax(fabs(dx) - hl, 0.0);
       acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(t));
     }
@@ -174,15 +180,16 @@ template <int D, int LN = 2> struct BucketWalk {
     }
   }
   // :1779-1804
-  __device__ inline BucketWalk(const Grid &grid, const double *point, double R2)
-      : g(grid), r2(R2), quadrant(0), valid(true) {
+  __device__ inline BucketWalk(const Grid &grid, const double *point, double R2, const double *scale = nullptr)
+      : g(grid), sc(scale), r2(R2), quadrant(0), valid(true) {
 #pragma unroll
     for (int i = 0; i < D; ++i) qp[i] = point[i];
     if (outside_domain()) {
       valid = false;
     } else {
 #pragma unroll
-      for (int i = 0; i < D; ++i) half[i] = 0.5 * g.side[i];
+      for (int i = 0; i < D; ++i) // :1790-1799
+        half[i] = SC ? 0.5 * ((0.5 * g.side[i] - (-0.5 * g.side[i])) * sc[i]) : 0.5 * g.side[i];
       reset_min_and_index();
     }
   }
@@ -221,8 +228,8 @@ template <int D, int LN = 2> struct BucketWalk {
 // chebyshev_search, 1: manhatten_search (src/Search.h:794-845).
 // visit(j, dx, accumulated norm, image_linear_index)
 // ---------------------------------------------------------------------------
-template <int D, int LN = 2, typename Visit>
-__device__ inline void search_walk(const Query &q, const double *r, double R, Visit &&visit) {
+template <int D, int LN = 2, bool SC = false, typename Visit>
+__device__ inline void search_walk(const Query &q, const double *r, double R, Visit &&visit, const double *scale = nullptr) {
   const Grid &g = q.g;
   const double R2 = DistHelper<LN>::value(R);
   int img[D];
@@ -233,7 +240,7 @@ __device__ inline void search_walk(const Query &q, const double *r, double R, Vi
     double cur[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) cur[i] = r[i] + (double)img[i] * g.L[i];
-    for (BucketWalk<D, LN> b(g, cur, R2); b.valid; b.increment()) {
+    for (BucketWalk<D, LN, SC> b(g, cur, R2, scale); b.valid; b.increment()) {
       const int cl = local_collapse<D>(g, b.index);
       if (cl < 0) continue; // bucket layer held by another rank (never within reach of an owned row)
       const unsigned c = (unsigned)cl;
@@ -243,6 +250,10 @@ __device__ inline void search_walk(const Query &q, const double *r, double R, Vi
         double acc = 0;
 #pragma unroll
         for (int i = 0; i < D; ++i) dx[i] = q.pos[(size_t)j * D + i] - cur[i];
+        if (SC) { // m_dx = m_transform(p - m_current_point), src/Search.h:443
+#pragma unroll
+          for (int i = 0; i < D; ++i) dx[i] = dx[i] * scale[i];
+        }
 #pragma unroll
         for (int i = 0; i < D; ++i) acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(dx[i]));
         if (!(acc > R2)) visit(j, dx, acc, image_counter);

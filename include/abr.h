@@ -256,6 +256,17 @@ int abr_distance_search_stats(abr_handle h, const double *query_pos, size_t n_qu
                               const double *radius_per_query, int lnorm, uint32_t *count,
                               uint64_t *hash);
 
+/* The same search in a scaled coordinate system: the Transform argument of
+ * distance_search / euclidean_search (src/Search.h:794-845) with a ScaleTransform
+ * (create_scale_transform, src/Transform.h:140-172): dx -> dx * scale per dimension
+ * in the candidate test (src/Search.h:443) and in the bucket / domain distance tests
+ * of the bucket iterator (src/NeighbourSearchBase.h:1790-1799, :1884-1892, :1950-1958).
+ * scale_host: D factors (host).  E.g. tests/neighbours.h:553-561 searches radius 1.0
+ * with scale 1/radius. */
+int abr_distance_search_stats_scaled(abr_handle h, const double *query_pos, size_t n_queries,
+                                     double radius, const double *radius_per_query, int lnorm,
+                                     const double *scale_host, uint32_t *count, uint64_t *hash);
+
 /* Counters of the last abr_sparse_matvec / abr_pair_stats on the tiled path:
  * [0] rows re-done by the exact per-row walk (rounding-sensitive rows),
  * [1] particles whose bucket index overflowed in the last build (forces the

@@ -157,6 +157,9 @@ template <int LN = 2> struct BucketIter {
   bool valid = true;
   int mn[MAXD];
   int index[MAXD];
+  // ScaleTransform (src/Transform.h:140-160): v -> v * scale, box -> (bmax - bmin) * scale;
+  // null = IdentityTransform
+  const double *scale = nullptr;
 
   inline bool ith_quadrant_bit(int i) const { return 1 == ((quadrant >> i) & 1); }
 
@@ -167,6 +170,7 @@ template <int LN = 2> struct BucketIter {
     for (int i = 0; i < D; ++i) {
       const double centre = (bucket[i] + 0.5) * q->side[i] + q->bmin[i];
       dx[i] = centre - query_point[i];
+      if (scale) dx[i] = dx[i] * scale[i]; // m_transform(centre - m_query_point)
     }
     for (int i = 0; i < D; ++i)
       dx[i] = std::max(std::abs(dx[i]) - half_bucket_length[i], 0.0);
@@ -180,7 +184,8 @@ template <int LN = 2> struct BucketIter {
     double dx[MAXD];
     for (int i = 0; i < D; ++i) {
       dx[i] = 0.5 * (q->bmin[i] + q->bmax[i]) - position[i];
-      const double half_domain_side_length = 0.5 * (q->bmax[i] - q->bmin[i]);
+      if (scale) dx[i] = dx[i] * scale[i];
+      const double half_domain_side_length = scale ? 0.5 * ((q->bmax[i] - q->bmin[i]) * scale[i]) : 0.5 * (q->bmax[i] - q->bmin[i]);
       dx[i] = std::max(std::abs(dx[i]) - half_domain_side_length, 0.0);
     }
     double accum = 0;
@@ -225,14 +230,17 @@ template <int LN = 2> struct BucketIter {
   }
 
   // :1779-1804 constructor
-  BucketIter(const Oracle *query, const double *point, double max_distance)
-      : q(query), D(query->D) {
+  BucketIter(const Oracle *query, const double *point, double max_distance, const double *scale_ = nullptr)
+      : q(query), D(query->D), scale(scale_) {
     for (int i = 0; i < D; ++i) query_point[i] = point[i];
     max_distance2 = dist_helper<LN>::value(max_distance); // pow(x,2) -> x*x (§0.5)
     if (outside_domain(point)) {
       valid = false;
     } else {
-      for (int i = 0; i < D; ++i) half_bucket_length[i] = 0.5 * q->side[i];
+      for (int i = 0; i < D; ++i) {
+        // :1790-1799: identity: 0.5 * side; otherwise 0.5 * transform(bbox(-0.5 side, 0.5 side))
+        half_bucket_length[i] = scale ? 0.5 * ((0.5 * q->side[i] - (-0.5 * q->side[i])) * scale[i]) : 0.5 * q->side[i];
+      }
       reset_min_and_index();
     }
   }
@@ -275,7 +283,7 @@ template <int LN = 2> struct BucketIter {
 // ---------------------------------------------------------------------------
 template <int LN, typename Visit>
 inline void distance_search(const Oracle &q, const double *r, double max_distance,
-                            Visit &&visit) {
+                            Visit &&visit, const double *scale = nullptr) {
   const int D = q.D;
   const double max_distance2 = dist_helper<LN>::value(max_distance);
   int start[MAXD], end[MAXD], img[MAXD];
@@ -290,13 +298,15 @@ inline void distance_search(const Oracle &q, const double *r, double max_distanc
     double cur[MAXD];
     for (int i = 0; i < D; ++i)
       cur[i] = r[i] + img[i] * (q.bmax[i] - q.bmin[i]); // Search.h:188-190
-    for (BucketIter<LN> b(&q, cur, max_distance); b.valid; b.increment()) {
+    for (BucketIter<LN> b(&q, cur, max_distance, scale); b.valid; b.increment()) {
       const unsigned c = (unsigned)collapse_index_vector(D, q.size, b.index);
       const unsigned jb = q.bucket_begin[c], je = q.bucket_end[c];
       for (unsigned j = jb; j < je; ++j) {
         double dx[MAXD];
         double accum = 0;
         for (int i = 0; i < D; ++i) dx[i] = q.pos[(size_t)j * D + i] - cur[i];
+        if (scale) // m_dx = m_transform(p - m_current_point), src/Search.h:443
+          for (int i = 0; i < D; ++i) dx[i] = dx[i] * scale[i];
         for (int i = 0; i < D; ++i) accum = dist_helper<LN>::accumulate(accum, dist_helper<LN>::value(dx[i]));
         if (!(accum > max_distance2)) visit(j, dx, image_counter);
       }
@@ -667,8 +677,16 @@ void orc_pair_stats(void *h, const double *row_pos, size_t n_rows, double radius
 // distance_search<LNormNumber> / chebyshev_search / manhatten_search
 // (src/Search.h:794-831): per-row neighbour count and pair-set hash for the
 // norms -1 (Chebyshev), 1 (Manhattan), 2 (Euclidean), 3, 4
+int orc_pair_stats_norm_scaled(void *h, const double *row_pos, size_t n_rows, double radius, int lnorm, const double *scale,
+                               uint32_t *count, uint64_t *hash);
 int orc_pair_stats_norm(void *h, const double *row_pos, size_t n_rows, double radius, int lnorm, uint32_t *count,
                         uint64_t *hash) {
+  return orc_pair_stats_norm_scaled(h, row_pos, n_rows, radius, lnorm, nullptr, count, hash);
+}
+// the same with a ScaleTransform (create_scale_transform, src/Transform.h:140-172; used as
+// euclidean_search(query, centre, 1.0, create_scale_transform(1/radius)) in tests/neighbours.h:553-561)
+int orc_pair_stats_norm_scaled(void *h, const double *row_pos, size_t n_rows, double radius, int lnorm, const double *scale,
+                               uint32_t *count, uint64_t *hash) {
   Oracle *o = static_cast<Oracle *>(h);
   const int D = o->D;
   if (lnorm != -1 && lnorm != 1 && lnorm != 2 && lnorm != 3 && lnorm != 4) return 1;
@@ -681,11 +699,11 @@ int orc_pair_stats_norm(void *h, const double *row_pos, size_t n_rows, double ra
       hs += mix64((uint64_t)j * 81u + (uint64_t)image);
     };
     switch (lnorm) {
-    case -1: distance_search<-1>(*o, row_pos + i * D, radius, visit); break;
-    case 1: distance_search<1>(*o, row_pos + i * D, radius, visit); break;
-    case 3: distance_search<3>(*o, row_pos + i * D, radius, visit); break;
-    case 4: distance_search<4>(*o, row_pos + i * D, radius, visit); break;
-    default: distance_search<2>(*o, row_pos + i * D, radius, visit); break;
+    case -1: distance_search<-1>(*o, row_pos + i * D, radius, visit, scale); break;
+    case 1: distance_search<1>(*o, row_pos + i * D, radius, visit, scale); break;
+    case 3: distance_search<3>(*o, row_pos + i * D, radius, visit, scale); break;
+    case 4: distance_search<4>(*o, row_pos + i * D, radius, visit, scale); break;
+    default: distance_search<2>(*o, row_pos + i * D, radius, visit, scale); break;
     }
     if (count) count[i] = c;
     if (hash) hash[i] = hs;

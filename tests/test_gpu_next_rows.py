@@ -220,3 +220,26 @@ def test_bucket_pair_iterator_parity(D, N, r, periodic):
     assert np.array_equal(cnt, o.fast_bucket_search_counts(r))
     if N <= 5000:
         assert np.array_equal(cnt, orc.brute_force_counts(out["pos"], [-1.0] * D, [1.0] * D, periodic, r))
+
+
+@pytest.mark.parametrize("D,periodic", [(1, True), (2, True), (2, False), (3, True), (3, False)])
+@pytest.mark.parametrize("lnorm", [-1, 1, 2])
+def test_scale_transform_search_parity(D, periodic, lnorm):
+    # distance_search<LN>(query, centre, r, create_scale_transform(scale)) (src/Search.h:794-845,
+    # src/Transform.h:140-172): per-query pair sets equal the oracle's, bit for bit
+    rng = np.random.default_rng(31 * D + lnorm + int(periodic))
+    N = 20000
+    pos = rng.uniform(-1.0, 1.0, size=(N, D))
+    o, out, p = build_both(pos, -1.0, 1.0, periodic)
+    scale = np.array([1.0, 2.5, 0.4])[:D]
+    r = 0.12
+    queries = np.concatenate([out["pos"][:3000], rng.uniform(-1.2, 1.2, size=(2000, D))])
+    cnt, hs = p.distance_search_stats(r, lnorm, queries=queries, scale=scale)
+    ocnt, ohs = o.pair_stats_norm(queries, r, lnorm, scale=scale)
+    assert np.array_equal(cnt.cpu().numpy().view(np.uint32), ocnt)
+    assert np.array_equal(hs.cpu().numpy().view(np.uint64), ohs)
+    assert ocnt.sum() > 0
+    # tests/neighbours.h:553-561: radius 1 with scale 1/r == radius r (same counts up to pairs at exactly r)
+    c_r, _ = p.distance_search_stats(r, 2, queries=queries)
+    c_s, _ = p.distance_search_stats(1.0, 2, queries=queries, scale=1.0 / r)
+    assert abs(int(c_r.sum()) - int(c_s.sum())) <= 2

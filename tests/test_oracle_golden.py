@@ -325,3 +325,36 @@ def test_fast_bucketsearch_vs_brute_force(D, N, r, periodic):
     cnt = o.fast_bucket_search_counts(r)
     bf = orc.brute_force_counts(out["pos"], [-1.0] * D, [1.0] * D, periodic, r)
     assert np.array_equal(cnt, bf)
+
+
+def test_scale_transform_golden():
+    # tests/neighbours.h:553-561: euclidean_search(query, centre, 1.0, create_scale_transform(1/radius))
+    # finds what euclidean_search(query, centre, radius) finds
+    radius = 0.1
+    o = orc.Oracle(3)
+    o.init_neighbour_search([[0.0, 0.0, 0.0]], -1.0, 1.0, True)
+    cnt, _ = o.pair_stats_norm(np.array([[radius / 2, radius / 2, 0.0], [2 * radius, 0.0, 0.0]]), 1.0, 2, scale=1.0 / radius)
+    assert cnt.tolist() == [1, 0]
+    # random cloud, anisotropic scale: against a brute force over the periodic images with the same
+    # transformed distance (the reference's own check, tests/neighbours.h:739-764, applies the transform
+    # to dx before the norm)
+    rng = np.random.default_rng(8)
+    for D, periodic in [(2, True), (3, False), (3, True)]:
+        N = 400
+        pos = rng.uniform(-1.0, 1.0, size=(N, D))
+        scale = np.array([1.0, 2.0, 0.5])[:D]
+        r = 0.3
+        o = orc.Oracle(D)
+        out = o.init_neighbour_search(pos, -1.0, 1.0, periodic, 5)
+        sp = out["pos"]
+        cnt, _ = o.pair_stats_norm(sp, r, 2, scale=scale)
+        images = np.array(np.meshgrid(*[[-1, 0, 1] if periodic else [0]] * D, indexing="ij")).reshape(D, -1).T
+        bf = np.zeros(N, dtype=np.int64)
+        for im in images:
+            d = (sp[None, :, :] - (sp[:, None, :] + im * 2.0)) * scale
+            bf += ((d * d).sum(-1) <= r * r).sum(1)
+        assert np.array_equal(cnt, bf)
+        # identity scale reproduces the untransformed search bit for bit
+        c1, h1 = o.pair_stats_norm(sp, r, 2, scale=1.0)
+        c0, h0 = o.pair_stats_norm(sp, r, 2)
+        assert np.array_equal(c1, c0) and np.array_equal(h1, h0)
