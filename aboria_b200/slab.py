@@ -263,13 +263,20 @@ def run_bench(args, rank, world, dev, metric, unit):
     op = ab.create_sparse_operator(sp.p, sp.p, radius, K.inv_dist(EPS))
     state = {}
 
-    def step():
+    def step(evs=None):
         sp.build(pos_unsorted.clone())
+        if evs is not None:
+            evs.append(torch.cuda.Event(enable_timing=True))
+            evs[-1].record()
         b_local = state.get("b_local")
         if b_local is None or b_local.shape[0] != sp.ex.n_local:
             b_local = state["b_local"] = torch.zeros(sp.ex.n_local, dtype=torch.float64, device=dev)
         b_local[sp.ex.own_begin: sp.ex.own_end].copy_(b_owned)  # owned entries; ghosts come from the neighbours
-        return sp.matvec(op, b_local)
+        y = sp.matvec(op, b_local)
+        if evs is not None:
+            evs.append(torch.cuda.Event(enable_timing=True))
+            evs[-1].record()
+        return y
 
     step()
     cnt, _ = sp.p.pair_stats(radius)
@@ -287,10 +294,12 @@ def run_bench(args, rank, world, dev, metric, unit):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    evs = []
     for _ in range(args.steps):
-        step()
+        step(evs)
     e1.record()
     torch.cuda.synchronize()
+    ms_mv = float(np.mean([evs[2 * k].elapsed_time(evs[2 * k + 1]) for k in range(args.steps)]))  # halo exchange of b + product, this rank
     ms_local = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.barrier()
     dist.all_reduce(ms_local, op=dist.ReduceOp.MAX)  # max over ranks
@@ -329,6 +338,18 @@ def run_bench(args, rank, world, dev, metric, unit):
     halo = torch.tensor([float(sp.ex.n_ghost_lo + sp.ex.n_ghost_hi)], dtype=torch.float64, device=dev)
     dist.all_reduce(halo)
     if rank == 0:
+        from bench import measured_peaks
+
+        hbm_peak, peak_src = measured_peaks()
+        n_loc, n_own = sp.ex.n_local, sp.ex.n_own
+        ncells_loc = int(sp.p.n_buckets)
+        mv_bytes = n_own * (8 * 3 + 8) + n_loc * (8 * 3 + 8) + 8 * ncells_loc  # SURVEY §8d B_mv for this rank's rows / columns
+        pairs_rank = int(sp.owned(cnt).long().sum().item())
+        roofline = {"bound": "hbm", "kernel": "abr::tiled_kernel<3, InvDistFast> on rank 0 (sparse matvec incl. the halo exchange of b)",
+                    "achieved": mv_bytes / (ms_mv * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": mv_bytes / (ms_mv * 1e-3) / 1e9 / hbm_peak,
+                    "traffic": None, "algorithmic_bytes": mv_bytes, "peak_source": peak_src, "ms_matvec_rank0": ms_mv,
+                    "pairs_per_s_matvec_only_rank0": pairs_rank / (ms_mv * 1e-3),
+                    "note": "the product is instruction-issue / fp64 bound, not HBM bound (DESIGN.md §4.2); same kernel as the 1-GPU line"}
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -339,7 +360,7 @@ def run_bench(args, rank, world, dev, metric, unit):
             "e2e": {"value": pairs / e2e_sec, "unit": unit, "h2d_bytes_per_step": int(n_mine * 32 * world), "d2h_bytes_per_step": int(n_mine * 8 * world),
                     "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps},
             "gpu_launches": int(launches) * world, "clocks": clocks,
-            "roofline": None, "cpu_baseline": None,
+            "roofline": roofline, "cpu_baseline": None,
         }
         print(json.dumps(line))
     dist.barrier()
