@@ -249,19 +249,29 @@ template <class F> struct needs_dx<F, decltype((void)F::NEEDS_DX)> { static cons
 #define ABR_QDRAIN 14
 #endif
 #ifndef ABR_TILED_CTAS
-#define ABR_TILED_CTAS 8
+#define ABR_TILED_CTAS 7
 #endif
 constexpr int QDRAIN = ABR_QDRAIN;    // drain when any lane holds this many (a test step adds <= 4)
 constexpr int QCAP = QDRAIN - 1 + 4;  // most accepted pairs a lane can hold
 constexpr int ROW_BITS = 4;
+#ifndef ABR_SKEW_LANES
+#define ABR_SKEW_LANES 1
+#endif
 #ifndef ABR_WQ
 #define ABR_WQ 256
 #endif
 constexpr int WQ = ABR_WQ;            // pairs compacted per drain pass
 constexpr int PCOL = 16;              // columns of the partial-sum table (lanes l and l+16 share one)
 
+// resident CTAs per SM the tiled kernel is compiled for: 7 (72 registers) by default; a
+// functor whose math is light enough for 64 registers declares
+// `static constexpr int TILED_CTAS = 8` (measured: InvDist +2 %, SphDensity -10 % at 8)
+template <class F, class = void> struct tiled_ctas { static constexpr int value = ABR_TILED_CTAS; };
+template <class F> struct tiled_ctas<F, decltype((void)F::TILED_CTAS)> { static constexpr int value = F::TILED_CTAS; };
+
 template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
+  static constexpr int CTAS = NACC == 1 ? tiled_ctas<F>::value : 5;
   // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows); block kernels keep
   // BR partial-sum tables, so they take 8 rows at a time
   static constexpr int RB = NACC == 1 ? (1 << ROW_BITS) : 8;
@@ -519,10 +529,10 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
   }
 }
 
-// occupancy target: 8 CTAs/SM for scalar kernels (6.6 KB of shared memory per warp, 64
-// registers), 5 for D x 1 block kernels
+// occupancy target: TiledCfg::CTAS CTAs/SM (6.4 KB of shared memory per warp): 7 or 8 for
+// scalar kernels, 5 for D x 1 block kernels
 template <int D, class F, bool STATS>
-__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::NACC == 1 ? ABR_TILED_CTAS : 5))
+__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::CTAS))
 tiled_kernel(const abr_matvec_plan p, const F f) {
   constexpr int BR = F::BR;
   constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
@@ -716,7 +726,14 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
             float pj[2][D];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+#if ABR_SKEW_LANES
+              // the second candidate of a lane sits half a run away from the first one: a lane whose
+              // first candidate is in the middle of a run (accepted by most rows) gets a peripheral
+              // second one, which evens out the queue lengths (fewer, fuller drains)
+              const uint32_t k = kb + 32 * h + (h ? ((lane + 16) & 31) : lane);
+#else
               const uint32_t k = kb + 32 * h + lane;
+#endif
               vv[h] = k < total;
               const uint32_t ks = vv[h] ? k : total - 1;
               uint32_t rho = 0;

@@ -66,6 +66,7 @@ namespace functors {
 
 // tests/operators.h:842-847
 struct ConstSum {
+  static constexpr int TILED_CTAS = 8;
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   const double *s1, *s2;
@@ -85,6 +86,7 @@ struct ConstSumDiff {
 };
 // 1/(|dx| + eps)
 struct InvDist {
+  static constexpr int TILED_CTAS = 8;
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   double eps;
@@ -95,6 +97,7 @@ struct InvDist {
 // the same for eps in [1e-100, 1e100] (|dx| + eps is then a normal number far from
 // overflow): branch-free sqrt and reciprocal
 struct InvDistFast {
+  static constexpr int TILED_CTAS = 8;
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   double eps;
