@@ -316,11 +316,13 @@ def run_ours(args):
     build_gbs = build_bytes / (ms_build * 1e-3) / 1e9
     flops_per_pair = 13.0  # 3D-1 distance + sqrt,add,div + 2*BR*BC
     mv_tflops = flops_per_pair * pairs / (ms_mv * 1e-3) / 1e12
-    roofline = {"bound": "hbm", "kernel": "abr::tiled_kernel<3, InvDist> (sparse matvec, dominant kernel of the step)",
+    roofline = {"bound": "hbm", "kernel": "abr::tiled_kernel<3, InvDistFast> (sparse matvec, dominant kernel of the step: 80 % of it)",
                 "achieved": mv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": mv_gbs / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=32M (profiles/r1m_ncu_tiled_kernel_v7_summary.txt)
-                "traffic": 1.590e9 if n == 32_000_000 else None, "algorithmic_bytes": mv_bytes, "peak_source": peak_src,
-                "note": "the matvec is fp64-pipe bound, not HBM bound (SURVEY §8d); see roofline_fp64. algorithmic bytes = N(8D+8BR)+N(8D+8BC)+8C"}
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=32M (profiles/r1y_ncu_tiled_kernel_v9_summary.txt)
+                "traffic": 2.345e9 if n == 32_000_000 else None, "algorithmic_bytes": mv_bytes, "peak_source": peak_src,
+                "note": "the product is instruction-issue bound, not HBM bound (arithmetic intensity >> 6 flop/B, SURVEY §8d; DESIGN.md §4.2): "
+                        "see roofline_fp64 and profiles/r1y_ncu_tiled_kernel_v9_summary.txt. algorithmic bytes = N(8D+8BR)+N(8D+8BC)+8C; "
+                        "achieved uses the product time incl. the 0.3 ms record-packing pass"}
     roofline_fp64 = {"bound": "fp64", "achieved": mv_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": mv_tflops / fp64_peak,
                      "peak_source": "measured here (abr_probe_fp64_peak, DFMA loop)", "flops_per_pair": flops_per_pair,
                      "pairs_per_s_matvec_only": pairs / (ms_mv * 1e-3)}
