@@ -633,16 +633,55 @@ k_gather_phased(const GatherCols cols, const int32_t *__restrict__ order, uint64
 // Final reorder of the two-level build, all columns in one launch: the permutation
 // is read once per particle and every source element sits in the L2-resident bin of
 // its destination.
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 5)
 k_gather_fused(const GatherCols cols, const uint32_t *__restrict__ perm, uint32_t n_out, const uint32_t *__restrict__ n_dev) {
+  // A block moves 256 consecutive output elements of every column.  Columns made of
+  // 8-byte words are gathered WORD-parallel: the W words of an element are read by W
+  // consecutive lanes, so a warp-wide load touches ~32/W records instead of 32 (the L1 tag
+  // stage, one look-up per distinct line per request, is what bounds this kernel:
+  // profiles/r1x_ncu_build_kernels.txt) and the stores are one contiguous span.
+  __shared__ uint32_t s_perm[256];
   if (n_dev) n_out = min(n_out, *n_dev);
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_out) return;
-  const uint32_t o = perm[k];
+  const uint32_t k0 = blockIdx.x * 256;
+  if (k0 >= n_out) return;
+  const uint32_t cnt = min(256u, n_out - k0);
+  const uint32_t tid = threadIdx.x;
+  if (tid < cnt) s_perm[tid] = perm[k0 + tid];
+  __syncthreads();
 #pragma unroll 1
   for (int c = 0; c < cols.ncols; ++c) {
     const uint32_t eb = cols.eb[c];
-    copy_element<4>(cols.src[c] + (uint64_t)o * eb, cols.dst[c] + (uint64_t)k * eb, eb);
+    const uint8_t *src = cols.src[c];
+    uint8_t *dst = cols.dst[c] + (uint64_t)k0 * eb;
+    if ((eb & 7u) == 0 && eb <= 128 && (((uintptr_t)src | (uintptr_t)dst) & 7u) == 0) {
+      const uint32_t W = eb >> 3, total = cnt * W;
+      const uint32_t inv = (65536u + W - 1u) / W; // g / W == (g * inv) >> 16 for g < 4096, W <= 16
+      const uint64_t *s8 = reinterpret_cast<const uint64_t *>(src);
+      uint64_t *t8 = reinterpret_cast<uint64_t *>(dst);
+      constexpr int U = 4;
+      for (uint32_t g0 = tid; g0 < total; g0 += 256 * U) {
+        uint64_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t g = g0 + u * 256;
+          if (g < total) {
+            const uint32_t e = (g * inv) >> 16;
+            v[u] = __ldg(s8 + (uint64_t)s_perm[e] * W + (g - e * W));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t g = g0 + u * 256;
+          if (g < total) t8[g] = v[u];
+        }
+      }
+    } else if (eb == 4 && (((uintptr_t)src | (uintptr_t)dst) & 3u) == 0) {
+      if (tid < cnt) reinterpret_cast<uint32_t *>(dst)[tid] = __ldg(reinterpret_cast<const uint32_t *>(src) + s_perm[tid]);
+    } else if (eb == 1) {
+      if (tid < cnt) dst[tid] = __ldg(src + s_perm[tid]);
+    } else {
+      if (tid < cnt) copy_element<4>(src + (uint64_t)s_perm[tid] * eb, dst + (uint64_t)tid * eb, eb);
+    }
   }
 }
 
