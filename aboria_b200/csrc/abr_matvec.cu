@@ -167,17 +167,17 @@ template <int D> static int dispatch_builtin(Handle *h, const abr_matvec_plan &p
     return launch_checked<D, InvDistAA, false>(h, p, InvDistAA{k->params[0], k->row_vars[0], k->col_vars[0]});
   case ABR_K_WENDLAND_C2:
     if (k->block_rows != 1 || k->block_cols != 1) break;
-    return launch_checked<D, WendlandC2, false>(h, p, WendlandC2{k->params[0]});
+    return launch_checked<D, WendlandC2, false>(h, p, WendlandC2::make(k->params[0]));
   case ABR_K_LJ_FORCE:
     if (k->block_rows != D || k->block_cols != 1) break;
-    return launch_checked<D, LJForce<D>, false>(h, p, LJForce<D>{k->params[0], k->params[1]});
+    return launch_checked<D, LJForce<D>, false>(h, p, LJForce<D>::make(k->params[0], k->params[1]));
   case ABR_K_SPH_DENSITY:
     if (k->block_rows != 1 || k->block_cols != 1) break;
-    return launch_checked<D, SphDensity<D>, false>(h, p, SphDensity<D>{k->params[0], k->params[1], k->params[2]});
+    return launch_checked<D, SphDensity<D>, false>(h, p, SphDensity<D>::make(k->params[0], k->params[1], k->params[2]));
   case ABR_K_SPH_PRESSURE:
     if (k->block_rows != D || k->block_cols != 1) break;
     return launch_checked<D, SphPressure<D>, false>(
-        h, p, SphPressure<D>{k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]});
+        h, p, SphPressure<D>::make(k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]));
   default:
     return set_error(h, ABR_ERR_INVALID, "matvec: unknown kernel_id");
   }
@@ -194,11 +194,11 @@ template <int D> static int dispatch_assemble(Handle *h, const abr_matvec_plan &
   case ABR_K_CONST_SUM_DIFF: e = launch_assemble<D>(p, ConstSumDiff{k->row_vars[0], k->col_vars[0]}, row_ptr, col_idx, values); break;
   case ABR_K_INV_DIST: e = launch_assemble<D>(p, InvDist{k->params[0]}, row_ptr, col_idx, values); break;
   case ABR_K_INV_DIST_AA: e = launch_assemble<D>(p, InvDistAA{k->params[0], k->row_vars[0], k->col_vars[0]}, row_ptr, col_idx, values); break;
-  case ABR_K_WENDLAND_C2: e = launch_assemble<D>(p, WendlandC2{k->params[0]}, row_ptr, col_idx, values); break;
-  case ABR_K_LJ_FORCE: e = launch_assemble<D>(p, LJForce<D>{k->params[0], k->params[1]}, row_ptr, col_idx, values); break;
-  case ABR_K_SPH_DENSITY: e = launch_assemble<D>(p, SphDensity<D>{k->params[0], k->params[1], k->params[2]}, row_ptr, col_idx, values); break;
+  case ABR_K_WENDLAND_C2: e = launch_assemble<D>(p, WendlandC2::make(k->params[0]), row_ptr, col_idx, values); break;
+  case ABR_K_LJ_FORCE: e = launch_assemble<D>(p, LJForce<D>::make(k->params[0], k->params[1]), row_ptr, col_idx, values); break;
+  case ABR_K_SPH_DENSITY: e = launch_assemble<D>(p, SphDensity<D>::make(k->params[0], k->params[1], k->params[2]), row_ptr, col_idx, values); break;
   case ABR_K_SPH_PRESSURE:
-    e = launch_assemble<D>(p, SphPressure<D>{k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]}, row_ptr, col_idx, values);
+    e = launch_assemble<D>(p, SphPressure<D>::make(k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]), row_ptr, col_idx, values);
     break;
   default: return set_error(h, ABR_ERR_INVALID, "assemble: unknown kernel_id");
   }
@@ -217,11 +217,11 @@ template <int D> static int dispatch_coeff(Handle *h, const abr_matvec_plan &p, 
   case ABR_K_CONST_SUM_DIFF: e = launch_coeff<D>(p, ConstSumDiff{k->row_vars[0], k->col_vars[0]}, ii, jj, m, out); break;
   case ABR_K_INV_DIST: e = launch_coeff<D>(p, InvDist{k->params[0]}, ii, jj, m, out); break;
   case ABR_K_INV_DIST_AA: e = launch_coeff<D>(p, InvDistAA{k->params[0], k->row_vars[0], k->col_vars[0]}, ii, jj, m, out); break;
-  case ABR_K_WENDLAND_C2: e = launch_coeff<D>(p, WendlandC2{k->params[0]}, ii, jj, m, out); break;
-  case ABR_K_LJ_FORCE: e = launch_coeff<D>(p, LJForce<D>{k->params[0], k->params[1]}, ii, jj, m, out); break;
-  case ABR_K_SPH_DENSITY: e = launch_coeff<D>(p, SphDensity<D>{k->params[0], k->params[1], k->params[2]}, ii, jj, m, out); break;
+  case ABR_K_WENDLAND_C2: e = launch_coeff<D>(p, WendlandC2::make(k->params[0]), ii, jj, m, out); break;
+  case ABR_K_LJ_FORCE: e = launch_coeff<D>(p, LJForce<D>::make(k->params[0], k->params[1]), ii, jj, m, out); break;
+  case ABR_K_SPH_DENSITY: e = launch_coeff<D>(p, SphDensity<D>::make(k->params[0], k->params[1], k->params[2]), ii, jj, m, out); break;
   case ABR_K_SPH_PRESSURE:
-    e = launch_coeff<D>(p, SphPressure<D>{k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]}, ii, jj, m, out);
+    e = launch_coeff<D>(p, SphPressure<D>::make(k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]), ii, jj, m, out);
     break;
   default: return set_error(h, ABR_ERR_INVALID, "coeff: unknown kernel_id");
   }

@@ -272,9 +272,13 @@ template <class F> struct tiled_ctas<F, decltype((void)F::TILED_CTAS)> { static 
 template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
   static constexpr int CTAS = NACC == 1 ? tiled_ctas<F>::value : 5;
-  // rows per batch (buckets hold ~n_particles_in_leaf = 10 rows); block kernels keep
-  // BR partial-sum tables, so they take 8 rows at a time
-  static constexpr int RB = NACC == 1 ? (1 << ROW_BITS) : 8;
+  // rows per batch: 16 (buckets hold ~n_particles_in_leaf = 10 rows, so one sweep over the
+  // candidates serves the whole bucket); block kernels keep BR partial-sum tables of
+  // RB x 16 doubles each (ABR_BLOCK_RB=8 restores the smaller tables)
+#ifndef ABR_BLOCK_RB
+#define ABR_BLOCK_RB 16
+#endif
+  static constexpr int RB = NACC == 1 ? (1 << ROW_BITS) : ABR_BLOCK_RB;
 };
 
 // per-warp shared memory (a warp works on one target bucket at a time and never

@@ -115,33 +115,44 @@ struct InvDistAA {
     blk[0] = (ai[i] * aj[j]) * __drcp_rn(sqrt_d2(d2) + eps);
   }
 };
+// The functors below keep loop-invariant scalars (1/h, 1/h^D * wcon * mass, sigma^2 ...) as
+// members computed once on the host by make(): inside the drain a division costs ~20
+// instructions with a divergent slow path, a multiplication one.  Their values differ from
+// the reference's expression order by a few ulp (inside the 1e-12 budget); cut-offs inside a
+// kernel function (q <= 2) sit where the function is continuous and zero.
+//
 // tests/rbf_interpolation.h:310-313: pow(2 - r/h, 4) * (1 + 2 r/h)
 struct WendlandC2 {
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
-  double h;
+  double inv_h;
+  static WendlandC2 make(double h) { return WendlandC2{1.0 / h}; }
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
-    const double r = sqrt_d2(d2);
-    const double t = 2.0 - r / h;
+    const double q = sqrt_d2_fast(d2) * inv_h;
+    const double t = 2.0 - q;
     const double t2 = t * t;
-    blk[0] = (t2 * t2) * (1.0 + 2.0 * r / h);
+    blk[0] = (t2 * t2) * (1.0 + 2.0 * q);
   }
 };
-// SURVEY §8d c3 (tests/md.h:166-174 pattern): Lennard-Jones force, D x 1 block
+// SURVEY §8d c3 (tests/md.h:166-174 pattern): Lennard-Jones force, D x 1 block:
+// 24 eps (2 (s/r)^12 - (s/r)^6) / r^2 * dx needs 1/r^2 only — no square root
 template <int D> struct LJForce {
   static constexpr int BR = D, BC = 1;
-  double sigma, eps;
+  double sigma2, eps24;
+  static LJForce make(double sigma, double eps) { return LJForce{sigma * sigma, 24.0 * eps}; }
   __device__ void operator()(const double *dx, double d2, uint32_t, uint32_t, double *blk) const {
-    if (d2 == 0) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) blk[d] = 0.0;
-      return;
+    const bool regular = d2 > 1e-280; // d2 == 0: the self pair, force 0
+    double fmag = 0.0;
+    if (regular) {
+      const double inv = rcp_fast(d2);
+      const double sr2 = sigma2 * inv;
+      const double sr6 = sr2 * sr2 * sr2;
+      fmag = eps24 * (2.0 * sr6 * sr6 - sr6) * inv;
+    } else if (d2 != 0) { // closer than 1e-140: the plain expression (overflows like the reference's)
+      const double sr2 = sigma2 / d2;
+      const double sr6 = sr2 * sr2 * sr2;
+      fmag = eps24 * (2.0 * sr6 * sr6 - sr6) / d2;
     }
-    const double r = sqrt_d2(d2);
-    const double sr = sigma / r;
-    const double sr2 = sr * sr;
-    const double sr6 = sr2 * sr2 * sr2;
-    const double fmag = 24.0 * eps * (2.0 * sr6 * sr6 - sr6) / (r * r);
 #pragma unroll
     for (int d = 0; d < D; ++d) blk[d] = fmag * dx[d];
   }
@@ -150,41 +161,37 @@ template <int D> struct LJForce {
 template <int D> struct SphDensity {
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
-  double h, mass, wcon;
+  double inv_h, pref; // pref = (1 / h^D) * wcon * mass
+  static SphDensity make(double h, double mass, double wcon) {
+    double hD = h;
+    for (int d = 1; d < D; ++d) hD *= h;
+    return SphDensity{1.0 / h, mass * ((1 / hD) * wcon)};
+  }
   __device__ void operator()(const double *, double d2, uint32_t, uint32_t, double *blk) const {
-    const double q = sqrt_d2(d2) / h;
-    double W = 0.0;
-    if (q <= 2.0) {
-      double hD = h;
-#pragma unroll
-      for (int d = 1; d < D; ++d) hD *= h;
-      const double t = 2.0 - q;
-      const double t2 = t * t;
-      W = (1 / hD) * wcon * (t2 * t2) * (1.0 + 2.0 * q);
-    }
-    blk[0] = mass * W;
+    const double q = sqrt_d2_fast(d2) * inv_h;
+    const double t = 2.0 - q;
+    const double t2 = t * t;
+    const double W = pref * (t2 * t2) * (1.0 + 2.0 * q);
+    blk[0] = q <= 2.0 ? W : 0.0;
   }
 };
 // tests/sph.h:140-152 F_fun and the pressure term of :333-339, D x 1 block
 template <int D> struct SphPressure {
   static constexpr int BR = D, BC = 1;
-  double h, mass, wcon;
+  double inv_h, pref; // pref = mass * (1 / h^(D+2)) * wcon
   const double *pdr2_i, *pdr2_j;
+  static SphPressure make(double h, double mass, double wcon, const double *pi, const double *pj) {
+    double hD2 = h * h;
+    for (int d = 0; d < D; ++d) hD2 *= h;
+    return SphPressure{1.0 / h, mass * ((1 / hD2) * wcon), pi, pj};
+  }
   __device__ void operator()(const double *dx, double d2, uint32_t i, uint32_t j, double *blk) const {
-    double Fv = 0.0;
-    const double r = sqrt_d2(d2);
-    if (r != 0) {
-      const double q = r / h;
-      if (q <= 2.0) {
-        double hD2 = h * h;
-#pragma unroll
-        for (int d = 0; d < D; ++d) hD2 *= h;
-        const double t = 2.0 - q;
-        const double t3 = t * t * t;
-        Fv = (1 / hD2) * wcon * (-4 * t3 * (1 + 2 * q) + 2 * (t3 * t)) / q;
-      }
-    }
-    const double c = mass * (pdr2_i[i] + pdr2_j[j]) * Fv;
+    const bool regular = d2 > 1e-280; // r == 0: F_fun returns 0
+    const double q = sqrt_d2_fast(d2) * inv_h;
+    const double t = 2.0 - q;
+    const double t3 = t * t * t;
+    const double Fv = pref * (-4 * t3 * (1 + 2 * q) + 2 * (t3 * t)) * rcp_fast(regular ? q : 1.0);
+    const double c = (regular && q <= 2.0) ? (pdr2_i[i] + pdr2_j[j]) * Fv : 0.0;
 #pragma unroll
     for (int d = 0; d < D; ++d) blk[d] = c * dx[d];
   }
