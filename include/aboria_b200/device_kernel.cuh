@@ -123,6 +123,7 @@ struct InvDistAA {
 //
 // tests/rbf_interpolation.h:310-313: pow(2 - r/h, 4) * (1 + 2 r/h)
 struct WendlandC2 {
+  static constexpr int TILED_CTAS = 8;
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   double inv_h;
