@@ -267,7 +267,11 @@ constexpr int PCOL = 16;              // columns of the partial-sum table (lanes
 // functor whose math is light enough for 64 registers declares
 // `static constexpr int TILED_CTAS = 8` (measured: InvDist +2 %, SphDensity -10 % at 8)
 template <class F, class = void> struct tiled_ctas { static constexpr int value = ABR_TILED_CTAS; };
+#ifdef ABR_FORCE_CTAS
+template <class F> struct tiled_ctas<F, decltype((void)F::TILED_CTAS)> { static constexpr int value = ABR_FORCE_CTAS; };
+#else
 template <class F> struct tiled_ctas<F, decltype((void)F::TILED_CTAS)> { static constexpr int value = F::TILED_CTAS; };
+#endif
 
 template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int NACC = STATS ? 2 : F::BR;
@@ -894,6 +898,13 @@ template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_pl
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILED_THREADS, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
+    {
+      // ask for no more shared memory than the resident CTAs need: what is left of the
+      // 256 KB array serves as L1 for the drain's gathers
+      int pct = (int)((100.0 * per_sm * (smem + 1024)) / (228.0 * 1024.0)) + 1;
+      if (pct > 100) pct = 100;
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     const unsigned max_chunks = (p.q.g.ncells + p.grab * TILED_WARPS - 1) / (p.grab * TILED_WARPS);
     unsigned grid = (unsigned)(p.sm_count * per_sm);
     if (grid > max_chunks) grid = max_chunks;
