@@ -59,6 +59,7 @@ SIGNATURES = {
     "abr_pair_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "abr_distance_search_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "abr_distance_search_stats_scaled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "abr_distance_search_stats_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "abr_last_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64 * 4)]),
     "abr_sparse_matvec_custom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "abr_probe_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

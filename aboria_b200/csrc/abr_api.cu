@@ -445,7 +445,16 @@ int abr_distance_search_stats_scaled(abr_handle hh, const double *row_pos, size_
   if (!h) return ABR_ERR_INVALID;
   ABR_CUDA(h, cudaSetDevice(h->device));
   abr::MatvecCall c{row_pos, n_rows, 0, radius, radius_per_row, nullptr, nullptr, count, hash, 1};
-  return abr::run_norm_stats(h, c, lnorm, scale_host);
+  return abr::run_norm_stats(h, c, lnorm, scale_host ? 1 : 0, scale_host);
+}
+
+int abr_distance_search_stats_linear(abr_handle hh, const double *row_pos, size_t n_rows, double radius, const double *radius_per_row, int lnorm,
+                                     const double *matrix_host, uint32_t *count, uint64_t *hash) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::MatvecCall c{row_pos, n_rows, 0, radius, radius_per_row, nullptr, nullptr, count, hash, 1};
+  return abr::run_norm_stats(h, c, lnorm, 2, matrix_host);
 }
 
 int abr_last_counters(abr_handle hh, uint64_t counters[4]) {

@@ -133,7 +133,7 @@ struct MatvecCall {
 };
 int run_builtin_matvec(Handle *h, const MatvecCall &c, const abr_kernel_desc *k);
 int run_pair_stats(Handle *h, const MatvecCall &c);
-int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm, const double *scale_host = nullptr);
+int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm, int transform_kind = 0, const double *t_host = nullptr);
 int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint32_t *row_ptr, int32_t *col_idx, double *values,
                  size_t capacity, uint64_t *nnz_host);
 int run_coeff(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, const uint64_t *ii, const uint64_t *jj, size_t m, double *out);

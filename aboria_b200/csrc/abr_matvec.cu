@@ -322,25 +322,12 @@ int run_pair_stats(Handle *h, const MatvecCall &c) {
   }
 }
 
-template <int D> static int launch_norm_stats(Handle *h, const abr_matvec_plan &p, int lnorm, const double *scale_host) {
+template <int D, int TK> static int launch_norm_stats_t(Handle *h, const abr_matvec_plan &p, int lnorm, const Xform &xf) {
   const unsigned grid = (unsigned)((p.n_rows + 127) / 128);
-  if (scale_host) { // ScaleTransform (src/Transform.h:140-160)
-    ScaleArg sc;
-    for (int d = 0; d < MAXD; ++d) sc.s[d] = d < D ? scale_host[d] : 1.0;
-    switch (lnorm) {
-    case -1: norm_stats_kernel<D, -1, true><<<grid, 128, 0, p.stream>>>(p, sc); break;
-    case 1: norm_stats_kernel<D, 1, true><<<grid, 128, 0, p.stream>>>(p, sc); break;
-    case 2: norm_stats_kernel<D, 2, true><<<grid, 128, 0, p.stream>>>(p, sc); break;
-    default: return set_error(h, ABR_ERR_UNSUPPORTED, "distance_search: norm must be -1 (Chebyshev), 1 (Manhattan) or 2 (Euclidean)");
-    }
-    h->launches += 1;
-    ABR_CUDA(h, cudaGetLastError());
-    return ABR_OK;
-  }
   switch (lnorm) {
-  case -1: norm_stats_kernel<D, -1><<<grid, 128, 0, p.stream>>>(p); break;
-  case 1: norm_stats_kernel<D, 1><<<grid, 128, 0, p.stream>>>(p); break;
-  case 2: norm_stats_kernel<D, 2><<<grid, 128, 0, p.stream>>>(p); break;
+  case -1: norm_stats_kernel<D, -1, TK><<<grid, 128, 0, p.stream>>>(p, xf); break;
+  case 1: norm_stats_kernel<D, 1, TK><<<grid, 128, 0, p.stream>>>(p, xf); break;
+  case 2: norm_stats_kernel<D, 2, TK><<<grid, 128, 0, p.stream>>>(p, xf); break;
   default: return set_error(h, ABR_ERR_UNSUPPORTED, "distance_search: norm must be -1 (Chebyshev), 1 (Manhattan) or 2 (Euclidean)");
   }
   h->launches += 1;
@@ -348,7 +335,41 @@ template <int D> static int launch_norm_stats(Handle *h, const abr_matvec_plan &
   return ABR_OK;
 }
 
-int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm, const double *scale_host) {
+// transform_kind: 0 identity, 1 ScaleTransform (D factors), 2 LinearTransform (D x D matrix, row major)
+template <int D> static int launch_norm_stats(Handle *h, const abr_matvec_plan &p, int lnorm, int transform_kind, const double *t_host) {
+  Xform xf;
+  memset(&xf, 0, sizeof(xf));
+  if (transform_kind == 1) {
+    for (int d = 0; d < D; ++d) xf.s[d] = t_host[d];
+    return launch_norm_stats_t<D, 1>(h, p, lnorm, xf);
+  }
+  if (transform_kind == 2) {
+    for (int e = 0; e < D * D; ++e) xf.m[e] = t_host[e];
+    // LinearTransform constructor (src/Transform.h:82-99): the vertex of [-1,1]^D whose image is
+    // longest, lattice order (last dimension fastest), strict '>'
+    double best = 0;
+    for (int code = 0; code < (1 << D); ++code) {
+      double pt[D], q[D];
+      int bits[D];
+      for (int j = 0; j < D; ++j) {
+        bits[j] = (code >> (D - 1 - j)) & 1;
+        pt[j] = bits[j] ? 1.0 : -1.0;
+      }
+      xform_point<D, 2>(xf, pt, q);
+      double n2 = 0;
+      for (int j = 0; j < D; ++j) n2 += q[j] * q[j];
+      if (n2 > best) {
+        for (int j = 0; j < D; ++j) xf.eig[j] = bits[j];
+        best = n2;
+      }
+    }
+    return launch_norm_stats_t<D, 2>(h, p, lnorm, xf);
+  }
+  return launch_norm_stats_t<D, 0>(h, p, lnorm, xf);
+}
+
+int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm, int transform_kind, const double *t_host) {
+  if (transform_kind != 0 && !t_host) return set_error(h, ABR_ERR_INVALID, "distance_search: null transform");
   if (c.n_rows == 0) return ABR_OK;
   if (!c.row_pos) return set_error(h, ABR_ERR_INVALID, "distance_search: null pointer");
   abr_matvec_plan p;
@@ -357,9 +378,9 @@ int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm, const double *scal
   int rc = make_plan(h, w, 1, &p);
   if (rc) return rc;
   switch (h->D) {
-  case 1: return launch_norm_stats<1>(h, p, lnorm, scale_host);
-  case 2: return launch_norm_stats<2>(h, p, lnorm, scale_host);
-  default: return launch_norm_stats<3>(h, p, lnorm, scale_host);
+  case 1: return launch_norm_stats<1>(h, p, lnorm, transform_kind, t_host);
+  case 2: return launch_norm_stats<2>(h, p, lnorm, transform_kind, t_host);
+  default: return launch_norm_stats<3>(h, p, lnorm, transform_kind, t_host);
   }
 }
 

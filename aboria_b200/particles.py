@@ -300,7 +300,7 @@ class Particles:
         """tuning knobs of the library (no effect on results), see abr_set_option"""
         check(self._h, self._lib.abr_set_option(self._h, name.encode(), float(value)))
 
-    def distance_search_stats(self, radius, lnorm, queries=None, scale=None):
+    def distance_search_stats(self, radius, lnorm, queries=None, scale=None, linear=None):
         """distance_search<lnorm> / chebyshev_search (-1) / manhatten_search (1) /
         euclidean_search (2) from `queries` (default: the particles themselves):
         per query the neighbour count and pair-set hash."""
@@ -309,6 +309,10 @@ class Particles:
         n = qp.shape[0]
         cnt = torch.zeros(n, dtype=torch.int32, device=self.device)
         hs = torch.zeros(n, dtype=torch.int64, device=self.device)
+        if linear is not None:  # create_linear_transform<D>(functor) with a linear functor given as its matrix (src/Transform.h:61-137)
+            mat = np.ascontiguousarray(np.asarray(linear, dtype=np.float64).reshape(self.D, self.D))
+            check(self._h, self._lib.abr_distance_search_stats_linear(self._h, _ptr(qp), n, float(radius), None, int(lnorm), mat.ctypes.data, _ptr(cnt), _ptr(hs)))
+            return cnt, hs
         if scale is not None:  # create_scale_transform(scale) (src/Transform.h:140-172)
             sc = np.ascontiguousarray(np.broadcast_to(np.asarray(scale, dtype=np.float64), (self.D,)))
             check(self._h, self._lib.abr_distance_search_stats_scaled(self._h, _ptr(qp), n, float(radius), None, int(lnorm), sc.ctypes.data, _ptr(cnt), _ptr(hs)))

@@ -101,11 +101,67 @@ template <int LN> struct DistHelper {
 // lattice_iterator_within_distance<Query,LNormNumber,IdentityTransform>
 // (src/NeighbourSearchBase.h:1720-2009), restated for the device.
 // ---------------------------------------------------------------------------
-// SC = true: ScaleTransform (src/Transform.h:140-160; v -> v * scale, a box's extent ->
-// (bmax - bmin) * scale) applied wherever the reference applies m_transform.
-template <int D, int LN = 2, bool SC = false> struct BucketWalk {
+// The Transform argument of the search iterators (src/Transform.h), by-value kernel argument.
+//   TK = 0  IdentityTransform (no code at all)
+//   TK = 1  ScaleTransform (:140-160): v -> v * s; a box's extent -> (bmax - bmin) * s
+//   TK = 2  LinearTransform (:61-137) over a linear functor given as its D x D matrix (row
+//           major, zero entries skipped, a 1.0 entry is a plain copy) with the "eigen vertex"
+//           the constructor finds (:82-99, computed on the host)
+struct Xform {
+  double s[MAXD];
+  double m[MAXD * MAXD];
+  int eig[MAXD];
+};
+template <int D, int TK> __host__ __device__ inline void xform_point(const Xform &x, const double *v, double *out) {
+  if (TK == 1) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) out[i] = v[i] * x.s[i];
+  } else if (TK == 2) {
+    double tmp[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      bool first = true;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double c = x.m[i * D + j];
+        if (c == 0.0) continue;
+        const double t = c == 1.0 ? v[j] : c * v[j];
+        acc = first ? t : acc + t;
+        first = false;
+      }
+      tmp[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) out[i] = tmp[i];
+  }
+}
+// extent of the axis-aligned box bounding the transformed box [bmin, bmax]
+template <int D, int TK> __host__ __device__ inline void xform_box(const Xform &x, const double *bmin, const double *bmax, double *out) {
+  if (TK == 1) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) out[i] = (bmax[i] - bmin[i]) * x.s[i];
+  } else if (TK == 2) {
+    double mx[D], mn[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double centre = 0.5 * (bmax[i] + bmin[i]);
+      mx[i] = (x.eig[i] ? bmax[i] : bmin[i]) - centre;
+      mn[i] = (x.eig[i] ? bmin[i] : bmax[i]) - centre;
+    }
+    xform_point<D, TK>(x, mx, mx);
+    xform_point<D, TK>(x, mn, mn);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double hi = fmax(mx[i], mn[i]), lo = fmin(mx[i], mn[i]);
+      out[i] = hi - lo;
+    }
+  }
+}
+
+template <int D, int LN = 2, int TK = 0> struct BucketWalk {
   const Grid &g;
-  const double *sc;
+  const Xform *xf;
   double qp[D];
   double half[D];
   double r2;
@@ -119,12 +175,16 @@ template <int D, int LN = 2, bool SC = false> struct BucketWalk {
   // :1884-1892 with find_bucket_centre = (v + 0.5) * side + bmin
   __device__ inline double min_dist2(const int *b) const {
     double acc = 0;
+    double dx[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const double centre = ((double)b[i] + 0.5) * g.side[i] + g.bmin[i];
-      double dxi = centre - qp[i];
-      if (SC) dxi = dxi * sc[i];
-      const double t = fmax(fabs(dxi) - half[i], 0.0);
+      dx[i] = centre - qp[i];
+    }
+    if (TK) xform_point<D, TK>(*xf, dx, dx); // m_transform(centre - m_query_point)
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double t = fmax(fabs(dx[i]) - half[i], 0.0);
       acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(t));
     }
     return acc;
@@ -132,12 +192,19 @@ template <int D, int LN = 2, bool SC = false> struct BucketWalk {
   // :1950-1958
   __device__ inline bool outside_domain() const {
     double acc = 0;
+    double dx[D], ext[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      double dx = 0.5 * (g.bmin[i] + g.bmax[i]) - qp[i];
-      if (SC) dx = dx * sc[i];
-      const double hl = SC ? 0.5 * ((g.bmax[i] - g.bmin[i]) * sc[i]) : 0.5 * (g.bmax[i] - g.bmin[i]);
-      const double t = fmax(fabs(dx) - hl, 0.0);
+      dx[i] = 0.5 * (g.bmin[i] + g.bmax[i]) - qp[i];
+      ext[i] = g.bmax[i] - g.bmin[i];
+    }
+    if (TK) {
+      xform_point<D, TK>(*xf, dx, dx);
+      xform_box<D, TK>(*xf, g.bmin, g.bmax, ext);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double t = fmax(fabs(dx[i]) - 0.5 * ext[i], 0.0);
       acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(t));
     }
     return acc > r2;
@@ -180,16 +247,26 @@ template <int D, int LN = 2, bool SC = false> struct BucketWalk {
     }
   }
   // :1779-1804
-  __device__ inline BucketWalk(const Grid &grid, const double *point, double R2, const double *scale = nullptr)
-      : g(grid), sc(scale), r2(R2), quadrant(0), valid(true) {
+  __device__ inline BucketWalk(const Grid &grid, const double *point, double R2, const Xform *xform = nullptr)
+      : g(grid), xf(xform), r2(R2), quadrant(0), valid(true) {
 #pragma unroll
     for (int i = 0; i < D; ++i) qp[i] = point[i];
     if (outside_domain()) {
       valid = false;
     } else {
 #pragma unroll
-      for (int i = 0; i < D; ++i) // :1790-1799
-        half[i] = SC ? 0.5 * ((0.5 * g.side[i] - (-0.5 * g.side[i])) * sc[i]) : 0.5 * g.side[i];
+      for (int i = 0; i < D; ++i) half[i] = 0.5 * g.side[i];
+      if (TK) { // :1790-1799: 0.5 * m_transform(bbox(-0.5 side, 0.5 side))
+        double lo[D], hi[D], ext[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          lo[i] = -0.5 * g.side[i];
+          hi[i] = 0.5 * g.side[i];
+        }
+        xform_box<D, TK>(*xf, lo, hi, ext);
+#pragma unroll
+        for (int i = 0; i < D; ++i) half[i] = 0.5 * ext[i];
+      }
       reset_min_and_index();
     }
   }
@@ -228,8 +305,8 @@ template <int D, int LN = 2, bool SC = false> struct BucketWalk {
 // chebyshev_search, 1: manhatten_search (src/Search.h:794-845).
 // visit(j, dx, accumulated norm, image_linear_index)
 // ---------------------------------------------------------------------------
-template <int D, int LN = 2, bool SC = false, typename Visit>
-__device__ inline void search_walk(const Query &q, const double *r, double R, Visit &&visit, const double *scale = nullptr) {
+template <int D, int LN = 2, int TK = 0, typename Visit>
+__device__ inline void search_walk(const Query &q, const double *r, double R, Visit &&visit, const Xform *xform = nullptr) {
   const Grid &g = q.g;
   const double R2 = DistHelper<LN>::value(R);
   int img[D];
@@ -240,7 +317,7 @@ __device__ inline void search_walk(const Query &q, const double *r, double R, Vi
     double cur[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) cur[i] = r[i] + (double)img[i] * g.L[i];
-    for (BucketWalk<D, LN, SC> b(g, cur, R2, scale); b.valid; b.increment()) {
+    for (BucketWalk<D, LN, TK> b(g, cur, R2, xform); b.valid; b.increment()) {
       const int cl = local_collapse<D>(g, b.index);
       if (cl < 0) continue; // bucket layer held by another rank (never within reach of an owned row)
       const unsigned c = (unsigned)cl;
@@ -250,10 +327,7 @@ __device__ inline void search_walk(const Query &q, const double *r, double R, Vi
         double acc = 0;
 #pragma unroll
         for (int i = 0; i < D; ++i) dx[i] = q.pos[(size_t)j * D + i] - cur[i];
-        if (SC) { // m_dx = m_transform(p - m_current_point), src/Search.h:443
-#pragma unroll
-          for (int i = 0; i < D; ++i) dx[i] = dx[i] * scale[i];
-        }
+        if (TK) xform_point<D, TK>(*xform, dx, dx); // m_dx = m_transform(p - m_current_point), src/Search.h:443
 #pragma unroll
         for (int i = 0; i < D; ++i) acc = DistHelper<LN>::accumulate(acc, DistHelper<LN>::value(dx[i]));
         if (!(acc > R2)) visit(j, dx, acc, image_counter);

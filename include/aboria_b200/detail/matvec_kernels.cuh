@@ -132,11 +132,8 @@ __global__ void __launch_bounds__(128) walk_kernel(const abr_matvec_plan p, cons
 // norm_stats_kernel: distance_search<LN> / chebyshev_search / manhatten_search
 // (src/Search.h:794-831) — per-row neighbour count and pair-set hash
 // ---------------------------------------------------------------------------
-struct ScaleArg {
-  double s[MAXD];
-};
-template <int D, int LN, bool SC = false>
-__global__ void __launch_bounds__(128) norm_stats_kernel(const abr_matvec_plan p, const ScaleArg scale = ScaleArg()) {
+template <int D, int LN, int TK = 0>
+__global__ void __launch_bounds__(128) norm_stats_kernel(const abr_matvec_plan p, const Xform xform = Xform()) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n_rows; i += gridDim.x * blockDim.x) {
     double r[D];
 #pragma unroll
@@ -144,10 +141,10 @@ __global__ void __launch_bounds__(128) norm_stats_kernel(const abr_matvec_plan p
     const double R = p.radius_per_row ? p.radius_per_row[i] : p.radius;
     uint32_t cnt = 0;
     uint64_t hs = 0;
-    search_walk<D, LN, SC>(p.q, r, R, [&](unsigned j, const double *, double, int image) {
+    search_walk<D, LN, TK>(p.q, r, R, [&](unsigned j, const double *, double, int image) {
       ++cnt;
       hs += mix64((uint64_t)j * 81u + (uint64_t)image);
-    }, scale.s);
+    }, &xform);
     if (p.stat_count) p.stat_count[i] = cnt;
     if (p.stat_hash) p.stat_hash[i] = hs;
   }

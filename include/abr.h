@@ -267,6 +267,15 @@ int abr_distance_search_stats_scaled(abr_handle h, const double *query_pos, size
                                      double radius, const double *radius_per_query, int lnorm,
                                      const double *scale_host, uint32_t *count, uint64_t *hash);
 
+/* ... and with a LinearTransform (create_linear_transform<D>(functor), src/Transform.h:61-137,
+ * :162-166) whose functor is linear, given as its D x D matrix (row major, host): the
+ * point transform is the matrix product (zero entries skipped, so the reference tests'
+ * SkewTransform `v[0] + 0.3 v[1]`, tests/neighbours.h:1262-1267, is reproduced operation for
+ * operation); the box transform uses the constructor's "eigen vertex" (:82-99, :112-136). */
+int abr_distance_search_stats_linear(abr_handle h, const double *query_pos, size_t n_queries,
+                                     double radius, const double *radius_per_query, int lnorm,
+                                     const double *matrix_host, uint32_t *count, uint64_t *hash);
+
 /* Counters of the last abr_sparse_matvec / abr_pair_stats on the tiled path:
  * [0] rows re-done by the exact per-row walk (rounding-sensitive rows),
  * [1] particles whose bucket index overflowed in the last build (forces the

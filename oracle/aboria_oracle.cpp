@@ -147,6 +147,89 @@ template <int LN> struct dist_helper {
 // LNormNumber,IdentityTransform>; enumerates buckets near a point exactly as the
 // reference does (quadrant by quadrant, row-wise with early exit).
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// src/Transform.h: the Transform argument of the search iterators.
+//   kind 1  ScaleTransform (:140-160): v -> v * scale; box -> (bmax - bmin) * scale
+//   kind 2  LinearTransform (:61-137) over a LINEAR user functor, given here as its matrix
+//           (row major; zero entries are skipped so that e.g. the reference tests'
+//           SkewTransform `v[0] + 0.3 * v[1]`, tests/neighbours.h:1262-1267, is reproduced
+//           operation for operation); the box transform uses the "eigen vertex" found by the
+//           constructor (:82-99).
+// ---------------------------------------------------------------------------
+struct Xform {
+  int kind = 0;
+  int D = 0;
+  double s[MAXD];
+  double m[MAXD * MAXD];
+  bool eig[MAXD];
+  inline void point(const double *v, double *out) const {
+    if (kind == 1) {
+      for (int i = 0; i < D; ++i) out[i] = v[i] * s[i];
+    } else {
+      double tmp[MAXD];
+      for (int i = 0; i < D; ++i) {
+        bool first = true;
+        double acc = 0.0;
+        for (int j = 0; j < D; ++j) {
+          const double c = m[i * D + j];
+          if (c == 0.0) continue;
+          const double t = c == 1.0 ? v[j] : c * v[j];
+          acc = first ? t : acc + t;
+          first = false;
+        }
+        tmp[i] = acc;
+      }
+      for (int i = 0; i < D; ++i) out[i] = tmp[i];
+    }
+  }
+  // side lengths of the axis-aligned box bounding the transformed box
+  inline void box(const double *bmin, const double *bmax, double *out) const {
+    if (kind == 1) {
+      for (int i = 0; i < D; ++i) out[i] = (bmax[i] - bmin[i]) * s[i];
+      return;
+    }
+    double mx[MAXD], mn[MAXD]; // :112-136
+    for (int i = 0; i < D; ++i) {
+      const double centre = 0.5 * (bmax[i] + bmin[i]);
+      if (eig[i]) {
+        mx[i] = bmax[i] - centre;
+        mn[i] = bmin[i] - centre;
+      } else {
+        mx[i] = bmin[i] - centre;
+        mn[i] = bmax[i] - centre;
+      }
+    }
+    point(mx, mx);
+    point(mn, mn);
+    for (int i = 0; i < D; ++i) {
+      const double tmp = std::max(mx[i], mn[i]);
+      mn[i] = std::min(mx[i], mn[i]);
+      mx[i] = tmp;
+      out[i] = mx[i] - mn[i];
+    }
+  }
+  // LinearTransform constructor (:82-99): the vertex of [-1,1]^D whose image is longest
+  void find_eigen_vertices() {
+    double best = 0;
+    for (int i = 0; i < D; ++i) eig[i] = false;
+    for (int code = 0; code < (1 << D); ++code) { // lattice_iterator over {0,1}^D, last dimension fastest
+      double pt[MAXD], q[MAXD];
+      bool bits[MAXD];
+      for (int j = 0; j < D; ++j) {
+        bits[j] = (code >> (D - 1 - j)) & 1;
+        pt[j] = bits[j] ? 1.0 : -1.0;
+      }
+      point(pt, q);
+      double n2 = 0;
+      for (int j = 0; j < D; ++j) n2 += q[j] * q[j];
+      if (n2 > best) {
+        for (int j = 0; j < D; ++j) eig[j] = bits[j];
+        best = n2;
+      }
+    }
+  }
+};
+
 template <int LN = 2> struct BucketIter {
   const Oracle *q;
   int D;
@@ -157,9 +240,7 @@ template <int LN = 2> struct BucketIter {
   bool valid = true;
   int mn[MAXD];
   int index[MAXD];
-  // ScaleTransform (src/Transform.h:140-160): v -> v * scale, box -> (bmax - bmin) * scale;
-  // null = IdentityTransform
-  const double *scale = nullptr;
+  const Xform *xf = nullptr; // null = IdentityTransform
 
   inline bool ith_quadrant_bit(int i) const { return 1 == ((quadrant >> i) & 1); }
 
@@ -170,8 +251,8 @@ template <int LN = 2> struct BucketIter {
     for (int i = 0; i < D; ++i) {
       const double centre = (bucket[i] + 0.5) * q->side[i] + q->bmin[i];
       dx[i] = centre - query_point[i];
-      if (scale) dx[i] = dx[i] * scale[i]; // m_transform(centre - m_query_point)
     }
+    if (xf) xf->point(dx, dx); // m_transform(centre - m_query_point)
     for (int i = 0; i < D; ++i)
       dx[i] = std::max(std::abs(dx[i]) - half_bucket_length[i], 0.0);
     double accum = 0; // src/detail/Distance.h:131-138
@@ -181,11 +262,17 @@ template <int LN = 2> struct BucketIter {
 
   // :1950-1958 outside_domain
   inline bool outside_domain(const double *position) const {
-    double dx[MAXD];
+    double dx[MAXD], ext[MAXD];
     for (int i = 0; i < D; ++i) {
       dx[i] = 0.5 * (q->bmin[i] + q->bmax[i]) - position[i];
-      if (scale) dx[i] = dx[i] * scale[i];
-      const double half_domain_side_length = scale ? 0.5 * ((q->bmax[i] - q->bmin[i]) * scale[i]) : 0.5 * (q->bmax[i] - q->bmin[i]);
+      ext[i] = q->bmax[i] - q->bmin[i];
+    }
+    if (xf) {
+      xf->point(dx, dx);
+      xf->box(q->bmin, q->bmax, ext);
+    }
+    for (int i = 0; i < D; ++i) {
+      const double half_domain_side_length = 0.5 * ext[i];
       dx[i] = std::max(std::abs(dx[i]) - half_domain_side_length, 0.0);
     }
     double accum = 0;
@@ -230,16 +317,24 @@ template <int LN = 2> struct BucketIter {
   }
 
   // :1779-1804 constructor
-  BucketIter(const Oracle *query, const double *point, double max_distance, const double *scale_ = nullptr)
-      : q(query), D(query->D), scale(scale_) {
+  BucketIter(const Oracle *query, const double *point, double max_distance, const Xform *xf_ = nullptr)
+      : q(query), D(query->D), xf(xf_) {
     for (int i = 0; i < D; ++i) query_point[i] = point[i];
     max_distance2 = dist_helper<LN>::value(max_distance); // pow(x,2) -> x*x (§0.5)
     if (outside_domain(point)) {
       valid = false;
     } else {
-      for (int i = 0; i < D; ++i) {
-        // :1790-1799: identity: 0.5 * side; otherwise 0.5 * transform(bbox(-0.5 side, 0.5 side))
-        half_bucket_length[i] = scale ? 0.5 * ((0.5 * q->side[i] - (-0.5 * q->side[i])) * scale[i]) : 0.5 * q->side[i];
+      // :1790-1799: identity: 0.5 * side; otherwise 0.5 * transform(bbox(-0.5 side, 0.5 side))
+      if (xf) {
+        double lo[MAXD], hi[MAXD], ext[MAXD];
+        for (int i = 0; i < D; ++i) {
+          lo[i] = -0.5 * q->side[i];
+          hi[i] = 0.5 * q->side[i];
+        }
+        xf->box(lo, hi, ext);
+        for (int i = 0; i < D; ++i) half_bucket_length[i] = 0.5 * ext[i];
+      } else {
+        for (int i = 0; i < D; ++i) half_bucket_length[i] = 0.5 * q->side[i];
       }
       reset_min_and_index();
     }
@@ -283,7 +378,7 @@ template <int LN = 2> struct BucketIter {
 // ---------------------------------------------------------------------------
 template <int LN, typename Visit>
 inline void distance_search(const Oracle &q, const double *r, double max_distance,
-                            Visit &&visit, const double *scale = nullptr) {
+                            Visit &&visit, const Xform *xf = nullptr) {
   const int D = q.D;
   const double max_distance2 = dist_helper<LN>::value(max_distance);
   int start[MAXD], end[MAXD], img[MAXD];
@@ -298,15 +393,14 @@ inline void distance_search(const Oracle &q, const double *r, double max_distanc
     double cur[MAXD];
     for (int i = 0; i < D; ++i)
       cur[i] = r[i] + img[i] * (q.bmax[i] - q.bmin[i]); // Search.h:188-190
-    for (BucketIter<LN> b(&q, cur, max_distance, scale); b.valid; b.increment()) {
+    for (BucketIter<LN> b(&q, cur, max_distance, xf); b.valid; b.increment()) {
       const unsigned c = (unsigned)collapse_index_vector(D, q.size, b.index);
       const unsigned jb = q.bucket_begin[c], je = q.bucket_end[c];
       for (unsigned j = jb; j < je; ++j) {
         double dx[MAXD];
         double accum = 0;
         for (int i = 0; i < D; ++i) dx[i] = q.pos[(size_t)j * D + i] - cur[i];
-        if (scale) // m_dx = m_transform(p - m_current_point), src/Search.h:443
-          for (int i = 0; i < D; ++i) dx[i] = dx[i] * scale[i];
+        if (xf) xf->point(dx, dx); // m_dx = m_transform(p - m_current_point), src/Search.h:443
         for (int i = 0; i < D; ++i) accum = dist_helper<LN>::accumulate(accum, dist_helper<LN>::value(dx[i]));
         if (!(accum > max_distance2)) visit(j, dx, image_counter);
       }
@@ -685,8 +779,31 @@ int orc_pair_stats_norm(void *h, const double *row_pos, size_t n_rows, double ra
 }
 // the same with a ScaleTransform (create_scale_transform, src/Transform.h:140-172; used as
 // euclidean_search(query, centre, 1.0, create_scale_transform(1/radius)) in tests/neighbours.h:553-561)
+int orc_pair_stats_norm_xform(void *h, const double *row_pos, size_t n_rows, double radius, int lnorm, const Xform *xf, uint32_t *count,
+                              uint64_t *hash);
 int orc_pair_stats_norm_scaled(void *h, const double *row_pos, size_t n_rows, double radius, int lnorm, const double *scale,
                                uint32_t *count, uint64_t *hash) {
+  Oracle *o = static_cast<Oracle *>(h);
+  Xform xf;
+  xf.kind = 1;
+  xf.D = o->D;
+  if (scale)
+    for (int d = 0; d < o->D; ++d) xf.s[d] = scale[d];
+  return orc_pair_stats_norm_xform(h, row_pos, n_rows, radius, lnorm, scale ? &xf : nullptr, count, hash);
+}
+// create_linear_transform<D>(functor) for a linear functor given as its D x D matrix (row major)
+int orc_pair_stats_norm_linear(void *h, const double *row_pos, size_t n_rows, double radius, int lnorm, const double *matrix,
+                               uint32_t *count, uint64_t *hash) {
+  Oracle *o = static_cast<Oracle *>(h);
+  Xform xf;
+  xf.kind = 2;
+  xf.D = o->D;
+  for (int e = 0; e < o->D * o->D; ++e) xf.m[e] = matrix[e];
+  xf.find_eigen_vertices();
+  return orc_pair_stats_norm_xform(h, row_pos, n_rows, radius, lnorm, &xf, count, hash);
+}
+int orc_pair_stats_norm_xform(void *h, const double *row_pos, size_t n_rows, double radius, int lnorm, const Xform *scale, uint32_t *count,
+                              uint64_t *hash) {
   Oracle *o = static_cast<Oracle *>(h);
   const int D = o->D;
   if (lnorm != -1 && lnorm != 1 && lnorm != 2 && lnorm != 3 && lnorm != 4) return 1;

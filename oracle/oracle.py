@@ -58,6 +58,8 @@ def lib():
         L.orc_pair_stats_norm.argtypes = [vp, dp, C.c_size_t, C.c_double, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_pair_stats_norm_scaled.restype = C.c_int
         L.orc_pair_stats_norm_scaled.argtypes = [vp, dp, C.c_size_t, C.c_double, C.c_int, dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_pair_stats_norm_linear.restype = C.c_int
+        L.orc_pair_stats_norm_linear.argtypes = [vp, dp, C.c_size_t, C.c_double, C.c_int, dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_sparse_matvec.restype = C.c_uint64
         L.orc_sparse_matvec.argtypes = [vp, dp, C.c_size_t, C.c_int, dp, C.POINTER(dp), C.POINTER(dp), C.c_double, dp, C.c_int, C.c_int, dp, dp, C.c_int]
         L.orc_sparse_assemble.restype = C.c_uint64
@@ -210,13 +212,20 @@ class Oracle:
         lib().orc_pair_stats(self.h, _dp(row_pos), n, float(radius), _dp(rpr), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), hs.ctypes.data_as(C.POINTER(C.c_uint64)))
         return cnt, hs
 
-    def pair_stats_norm(self, row_pos, radius, lnorm, scale=None):
+    def pair_stats_norm(self, row_pos, radius, lnorm, scale=None, linear=None):
         """distance_search<lnorm> (src/Search.h:794-831): count and pair-set hash per row;
-        scale: ScaleTransform factors (src/Transform.h:140-160), None = IdentityTransform"""
+        scale: ScaleTransform factors (src/Transform.h:140-160); linear: D x D matrix of a
+        LinearTransform (:61-137); neither = IdentityTransform"""
         row_pos = _f64(row_pos)
         n = row_pos.shape[0]
         cnt = np.zeros(n, dtype=np.uint32)
         hs = np.zeros(n, dtype=np.uint64)
+        if linear is not None:
+            mat = _f64(np.asarray(linear, dtype=np.float64).reshape(self.D, self.D))
+            rc = lib().orc_pair_stats_norm_linear(self.h, _dp(row_pos), n, float(radius), int(lnorm), _dp(mat), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), hs.ctypes.data_as(C.POINTER(C.c_uint64)))
+            if rc:
+                raise ValueError("unsupported norm")
+            return cnt, hs
         sc = _f64(np.broadcast_to(scale, (self.D,))) if scale is not None else None
         rc = lib().orc_pair_stats_norm_scaled(self.h, _dp(row_pos), n, float(radius), int(lnorm), _dp(sc), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), hs.ctypes.data_as(C.POINTER(C.c_uint64)))
         if rc:

@@ -243,3 +243,21 @@ def test_scale_transform_search_parity(D, periodic, lnorm):
     c_r, _ = p.distance_search_stats(r, 2, queries=queries)
     c_s, _ = p.distance_search_stats(1.0, 2, queries=queries, scale=1.0 / r)
     assert abs(int(c_r.sum()) - int(c_s.sum())) <= 2
+
+
+@pytest.mark.parametrize("D,N,r,nn,periodic", [(1, 14, 0.1, 1, False), (1, 1000, 0.1, 10, True), (2, 1000, 0.5, 10, True), (2, 1000, 0.5, 10, False),
+                                                (2, 1000, 0.2, 10, True), (2, 50000, 0.05, 10, True), (3, 20000, 0.1, 10, True)])
+@pytest.mark.parametrize("lnorm", [2, -1])
+def test_linear_transform_search_parity(D, N, r, nn, periodic, lnorm):
+    # distance_search with create_linear_transform<D>(SkewTransform()) (tests/neighbours.h:1262-1309):
+    # per-query pair sets equal the oracle's bit for bit
+    rng = np.random.default_rng(D * 100 + N)
+    pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+    T = {1: np.array([[0.7]]), 2: np.array([[1.0, 0.3], [0.0, 1.0]]), 3: np.array([[1.0, 0.3, 0.0], [0.0, 1.0, -0.2], [0.1, 0.0, 0.9]])}[D]
+    o, out, p = build_both(pos, -1.0, 1.0, periodic, nn)
+    queries = np.concatenate([out["pos"][: min(N, 3000)], rng.uniform(-1.2, 1.2, size=(500, D))])
+    cnt, hs = p.distance_search_stats(r, lnorm, queries=queries, linear=T)
+    ocnt, ohs = o.pair_stats_norm(queries, r, lnorm, linear=T)
+    assert np.array_equal(cnt.cpu().numpy().view(np.uint32), ocnt)
+    assert np.array_equal(hs.cpu().numpy().view(np.uint64), ohs)
+    assert ocnt.sum() > 0

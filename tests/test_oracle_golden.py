@@ -358,3 +358,31 @@ def test_scale_transform_golden():
         c1, h1 = o.pair_stats_norm(sp, r, 2, scale=1.0)
         c0, h0 = o.pair_stats_norm(sp, r, 2)
         assert np.array_equal(c1, c0) and np.array_equal(h1, h0)
+
+
+SKEW_CASES = [(1, 14, 0.1, 1, False), (1, 14, 0.1, 1, True), (1, 1000, 0.1, 10, True), (1, 1000, 0.1, 10, False),
+              (2, 1000, 0.5, 10, True), (2, 1000, 0.5, 10, False), (2, 1000, 0.2, 10, True), (2, 1000, 0.2, 10, False)]
+
+
+def _skew(D):
+    # tests/neighbours.h:1262-1267 SkewTransform: 1-D 0.7 v; 2-D (v0 + 0.3 v1, v1)
+    return np.array([[0.7]]) if D == 1 else np.array([[1.0, 0.3], [0.0, 1.0]])
+
+
+@pytest.mark.parametrize("D,N,r,nn,periodic", SKEW_CASES)
+def test_linear_transform_vs_brute_force(D, N, r, nn, periodic):
+    # helper_d_random(..., skew) (tests/neighbours.h:968-1147, cases :1274-1309): the search with a
+    # LinearTransform finds what the transform-aware brute force of :739-764 finds
+    rng = np.random.default_rng(D * 100 + N)
+    pos = rng.uniform(-1.0, 1.0, size=(N, D)).astype(np.float32).astype(np.float64)
+    T = _skew(D)
+    o = orc.Oracle(D)
+    out = o.init_neighbour_search(pos, -1.0, 1.0, periodic, nn)
+    sp = out["pos"]
+    cnt, _ = o.pair_stats_norm(sp, r, 2, linear=T)
+    images = np.array(np.meshgrid(*[[-1, 0, 1] if periodic else [0]] * D, indexing="ij")).reshape(D, -1).T
+    bf = np.zeros(N, dtype=np.int64)
+    for im in images:
+        d = (sp[None, :, :] - sp[:, None, :] - im * 2.0) @ T.T
+        bf += ((d * d).sum(-1) <= r * r).sum(1)
+    assert np.array_equal(cnt, bf)
