@@ -36,6 +36,29 @@ EPS = 0.1
 N_LEAF = 10.0
 
 
+# The driver reads ONE JSON line from stdout.  Libraries (NCCL's version banner, for one)
+# write to file descriptor 1 behind Python's back, so while the bench runs fd 1 points at
+# stderr and the result line goes to the saved original.
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -165,7 +188,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------
@@ -192,7 +215,7 @@ def run_ours(args):
         from aboria_b200 import slab
 
         dist.init_process_group("nccl", device_id=dev)
-        return slab.run_bench(args, rank, world, dev, METRIC, UNIT)
+        return slab.run_bench(args, rank, world, dev, METRIC, UNIT, emit)
 
     n = args.n_per_gpu
     side, size = grid_side(n)
@@ -352,7 +375,7 @@ def run_ours(args):
         "roofline": roofline, "roofline_fp64": roofline_fp64, "roofline_build": roofline_build,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -365,6 +388,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("ABR_BENCH_CPU_N", 2_000_000)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    guard_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
