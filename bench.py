@@ -349,6 +349,17 @@ def run_ours(args):
     roofline_fp64 = {"bound": "fp64", "achieved": mv_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": mv_tflops / fp64_peak,
                      "peak_source": "measured here (abr_probe_fp64_peak, DFMA loop)", "flops_per_pair": flops_per_pair,
                      "pairs_per_s_matvec_only": pairs / (ms_mv * 1e-3)}
+    # what actually binds the product: warp-instruction issue.  Instruction count of one launch
+    # from ncu (smsp__inst_executed.sum, profiles/r1y_ncu_tiled_kernel_v9_summary.txt; a property of
+    # kernel + workload), issue peak = SMs x 4 schedulers x SM clock
+    roofline_issue = None
+    if n == 32_000_000 and clocks.get("sm_mhz"):
+        inst = 11.514e9
+        peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+        ms_kernel = ms_mv - 0.40  # product time minus record packing, y zeroing and the exact-walk launch (profiles/r1y_launch_summary.txt)
+        roofline_issue = {"bound": "issue", "achieved": inst / (ms_kernel * 1e-3) / 1e12, "peak": peak_issue / 1e12, "unit": "T warp-inst/s",
+                          "frac": inst / (ms_kernel * 1e-3) / peak_issue, "warp_inst_per_pair": inst / pairs,
+                          "source": "ncu smsp__inst_executed.sum of one launch (static for this workload) / live kernel time"}
     roofline_build = {"bound": "hbm", "kernel": "cell-list build (k_enforce_key + radix sort + bounds + gather of position,id,alive)",
                       "achieved": build_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak,
                       "mparticles_per_s": n / (ms_build * 1e-3) / 1e6, "ms": ms_build}
@@ -372,7 +383,7 @@ def run_ours(args):
                    "l2": "inputs (0.77 GB positions) exceed the 126 MB L2; no flush needed", "rows_recomputed_by_exact_walk": walk_rows},
         "ms_build": ms_build, "ms_matvec": ms_mv, "build_mparticles_per_s": n / (ms_build * 1e-3) / 1e6,
         "ms_build_min_max": [float(np.min(t_build)), float(np.max(t_build))], "host_enqueue_ms_per_step": float(np.median(host_t)),
-        "roofline": roofline, "roofline_fp64": roofline_fp64, "roofline_build": roofline_build,
+        "roofline": roofline, "roofline_fp64": roofline_fp64, "roofline_issue": roofline_issue, "roofline_build": roofline_build,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     emit(line)
