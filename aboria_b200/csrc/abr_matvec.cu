@@ -171,6 +171,9 @@ template <int D> static int dispatch_builtin(Handle *h, const abr_matvec_plan &p
   case ABR_K_LJ_FORCE:
     if (k->block_rows != D || k->block_cols != 1) break;
     return launch_checked<D, LJForce<D>, false>(h, p, LJForce<D>::make(k->params[0], k->params[1]));
+  case ABR_K_LINEAR_SPRING:
+    if (k->block_rows != D || k->block_cols != 1) break;
+    return launch_checked<D, LinearSpring<D>, false>(h, p, LinearSpring<D>::make(k->params[0], k->params[1]));
   case ABR_K_SPH_DENSITY:
     if (k->block_rows != 1 || k->block_cols != 1) break;
     return launch_checked<D, SphDensity<D>, false>(h, p, SphDensity<D>::make(k->params[0], k->params[1], k->params[2]));
@@ -196,6 +199,7 @@ template <int D> static int dispatch_assemble(Handle *h, const abr_matvec_plan &
   case ABR_K_INV_DIST_AA: e = launch_assemble<D>(p, InvDistAA{k->params[0], k->row_vars[0], k->col_vars[0]}, row_ptr, col_idx, values); break;
   case ABR_K_WENDLAND_C2: e = launch_assemble<D>(p, WendlandC2::make(k->params[0]), row_ptr, col_idx, values); break;
   case ABR_K_LJ_FORCE: e = launch_assemble<D>(p, LJForce<D>::make(k->params[0], k->params[1]), row_ptr, col_idx, values); break;
+  case ABR_K_LINEAR_SPRING: e = launch_assemble<D>(p, LinearSpring<D>::make(k->params[0], k->params[1]), row_ptr, col_idx, values); break;
   case ABR_K_SPH_DENSITY: e = launch_assemble<D>(p, SphDensity<D>::make(k->params[0], k->params[1], k->params[2]), row_ptr, col_idx, values); break;
   case ABR_K_SPH_PRESSURE:
     e = launch_assemble<D>(p, SphPressure<D>::make(k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]), row_ptr, col_idx, values);
@@ -219,6 +223,7 @@ template <int D> static int dispatch_coeff(Handle *h, const abr_matvec_plan &p, 
   case ABR_K_INV_DIST_AA: e = launch_coeff<D>(p, InvDistAA{k->params[0], k->row_vars[0], k->col_vars[0]}, ii, jj, m, out); break;
   case ABR_K_WENDLAND_C2: e = launch_coeff<D>(p, WendlandC2::make(k->params[0]), ii, jj, m, out); break;
   case ABR_K_LJ_FORCE: e = launch_coeff<D>(p, LJForce<D>::make(k->params[0], k->params[1]), ii, jj, m, out); break;
+  case ABR_K_LINEAR_SPRING: e = launch_coeff<D>(p, LinearSpring<D>::make(k->params[0], k->params[1]), ii, jj, m, out); break;
   case ABR_K_SPH_DENSITY: e = launch_coeff<D>(p, SphDensity<D>::make(k->params[0], k->params[1], k->params[2]), ii, jj, m, out); break;
   case ABR_K_SPH_PRESSURE:
     e = launch_coeff<D>(p, SphPressure<D>::make(k->params[0], k->params[1], k->params[2], k->row_vars[0], k->col_vars[0]), ii, jj, m, out);

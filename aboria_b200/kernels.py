@@ -7,6 +7,7 @@ references to the particle sets, src/Kernels.h:133-134)."""
 
 K_CONST_SUM, K_CONST_SUM_DIFF, K_INV_DIST, K_INV_DIST_AA = 0, 1, 2, 3
 K_WENDLAND_C2, K_LJ_FORCE, K_SPH_DENSITY, K_SPH_PRESSURE = 4, 5, 6, 7
+K_LINEAR_SPRING = 8
 
 
 class Kernel:
@@ -57,3 +58,8 @@ def sph_density(h, mass, wcon):
 def sph_pressure(D, h, mass, wcon, pdr2):
     """D x 1: mass (pdr2_a + pdr2_b) F(|dx|,h) dx  (tests/sph.h:140-152, :333-339)"""
     return Kernel(K_SPH_PRESSURE, D, 1, (h, mass, wcon), (pdr2,), (pdr2,))
+
+
+def linear_spring(D, k, diameter):
+    """D x 1 linear spring force -k (diameter/|dx| - 1) dx, 0 at |dx| = 0 (tests/md.h:166-174)"""
+    return Kernel(K_LINEAR_SPRING, D, 1, (k, diameter))

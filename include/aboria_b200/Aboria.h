@@ -402,6 +402,54 @@ struct wendland_c2 : desc_base {
   }
   template <typename R, typename Cc> void bind(const R &, const Cc &) {}
 };
+// D x 1 Lennard-Jones force 24 eps (2 (sigma/r)^12 - (sigma/r)^6) / r^2 dx   (tests/md.h pattern)
+template <unsigned int D> struct lj_force : desc_base {
+  lj_force(double sigma, double eps) {
+    d.kernel_id = ABR_K_LJ_FORCE;
+    d.block_rows = D;
+    d.block_cols = 1;
+    d.params[0] = sigma;
+    d.params[1] = eps;
+  }
+  template <typename R, typename Cc> void bind(const R &, const Cc &) {}
+};
+// D x 1 linear spring -k (diameter/|dx| - 1) dx, 0 at |dx| = 0   (tests/md.h:166-174)
+template <unsigned int D> struct linear_spring : desc_base {
+  linear_spring(double k, double diameter) {
+    d.kernel_id = ABR_K_LINEAR_SPRING;
+    d.block_rows = D;
+    d.block_cols = 1;
+    d.params[0] = k;
+    d.params[1] = diameter;
+  }
+  template <typename R, typename Cc> void bind(const R &, const Cc &) {}
+};
+// mass * W(|dx|, h)   (tests/sph.h:154-165)
+struct sph_density : desc_base {
+  sph_density(double h, double mass, double wcon) {
+    d.kernel_id = ABR_K_SPH_DENSITY;
+    d.block_rows = d.block_cols = 1;
+    d.params[0] = h;
+    d.params[1] = mass;
+    d.params[2] = wcon;
+  }
+  template <typename R, typename Cc> void bind(const R &, const Cc &) {}
+};
+// D x 1: mass (get<P>(a) + get<P>(b)) F(|dx|, h) dx, P = pressure / density^2   (tests/sph.h:140-152, :333-339)
+template <unsigned int D, typename P> struct sph_pressure : desc_base {
+  sph_pressure(double h, double mass, double wcon) {
+    d.kernel_id = ABR_K_SPH_PRESSURE;
+    d.block_rows = D;
+    d.block_cols = 1;
+    d.params[0] = h;
+    d.params[1] = mass;
+    d.params[2] = wcon;
+  }
+  template <typename R, typename Cc> void bind(const R &rows, const Cc &cols) {
+    d.row_vars[0] = static_cast<const double *>(rows.template device_column<P>());
+    d.col_vars[0] = static_cast<const double *>(cols.template device_column<P>());
+  }
+};
 } // namespace kernels
 
 // ---- sparse operator ------------------------------------------------------------

@@ -158,6 +158,20 @@ template <int D> struct LJForce {
     for (int d = 0; d < D; ++d) blk[d] = fmag * dx[d];
   }
 };
+// tests/md.h:166-174: linear spring between overlapping discs/spheres, D x 1 block:
+// -k (diameter / r - 1) dx for r != 0
+template <int D> struct LinearSpring {
+  static constexpr int BR = D, BC = 1;
+  double k, diameter;
+  static LinearSpring make(double k, double diameter) { return LinearSpring{k, diameter}; }
+  __device__ void operator()(const double *dx, double d2, uint32_t, uint32_t, double *blk) const {
+    const bool regular = d2 > 1e-280;
+    const double r = sqrt_d2_fast(d2);
+    const double f = regular ? -k * (diameter * rcp_fast(regular ? r : 1.0) - 1.0) : 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) blk[d] = f * dx[d];
+  }
+};
 // tests/sph.h:154-165 W_fun (Wendland), times the particle mass
 template <int D> struct SphDensity {
   static constexpr bool NEEDS_DX = false;

@@ -54,7 +54,8 @@ enum abr_kernel_id {
   ABR_K_LJ_FORCE = 5,       /* Dx1: 24 p1 (2(p0/r)^12-(p0/r)^6)/r^2 dx  tests/md.h:166-174 pattern */
   ABR_K_SPH_DENSITY = 6,    /* p1 * W(|dx|, p0), p2 = WCON tests/sph.h:154-165 */
   ABR_K_SPH_PRESSURE = 7,   /* Dx1: p1 (rv0_i + cv0_j) F(|dx|,p0) dx    tests/sph.h:140-152, :333-339 */
-  ABR_K_COUNT_ = 8
+  ABR_K_LINEAR_SPRING = 8,  /* Dx1: -p0 (p1/|dx| - 1) dx, 0 at |dx| = 0   tests/md.h:166-174 (k = p0, diameter = p1) */
+  ABR_K_COUNT_ = 9
 };
 
 /* Describes the kernel function of one sparse operator block

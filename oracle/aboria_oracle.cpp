@@ -436,6 +436,7 @@ enum {
   K_LJ_FORCE = 5,       // SURVEY §8d c3 (md.h pattern tests/md.h:166-174) Dx1
   K_SPH_DENSITY = 6,    // tests/sph.h:154-165 W_fun, times mass
   K_SPH_PRESSURE = 7,   // tests/sph.h:140-152 F_fun; m(Pa/ra^2+Pb/rb^2) F dx, Dx1
+  K_LINEAR_SPRING = 8,  // tests/md.h:166-174  -k (diameter/r - 1) dx for r != 0, Dx1
 };
 
 struct KernelCtx {
@@ -487,6 +488,13 @@ inline void eval_kernel(const KernelCtx &k, const double *dx, size_t i, size_t j
       const double f = 24.0 * eps * (2.0 * sr6 * sr6 - sr6) / (r * r);
       for (int d = 0; d < D; ++d) blk[d] = f * dx[d];
     }
+    break;
+  }
+  case K_LINEAR_SPRING: {
+    // params: k, diameter.  tests/md.h:166-174: if (r != 0) sum += -k * (diameter / r - 1.0) * dx
+    const double kk = k.params[0], diameter = k.params[1];
+    const double r = norm_of(dx, D);
+    for (int d = 0; d < D; ++d) blk[d] = (r != 0) ? -kk * (diameter / r - 1.0) * dx[d] : 0.0;
     break;
   }
   case K_SPH_DENSITY: {

@@ -15,6 +15,7 @@ _LIB = None
 
 K_CONST_SUM, K_CONST_SUM_DIFF, K_INV_DIST, K_INV_DIST_AA = 0, 1, 2, 3
 K_WENDLAND_C2, K_LJ_FORCE, K_SPH_DENSITY, K_SPH_PRESSURE = 4, 5, 6, 7
+K_LINEAR_SPRING = 8
 
 SORT_STD, SORT_STABLE = 0, 1
 

@@ -257,7 +257,41 @@ static void test_id_search() {
   for (size_t want = 0; want < N; want += 7) TS_ASSERT_EQUALS(get<id>(particles)[particles.get_query().find(want)], want);
 }
 
+static void test_md_force_block_kernel() {
+  // tests/md.h:166-174: sum over neighbours of -k (diameter / r - 1) dx as a D x 1 block operator times ones
+  typedef Particles<std::tuple<>, 2> P;
+  typedef position_d<2> position;
+  const size_t N = 400;
+  const double diameter = 0.08, k = 10.0;
+  P particles(N);
+  std::default_random_engine gen(5);
+  std::uniform_real_distribution<double> uniform(0, 1);
+  for (size_t i = 0; i < N; ++i) get<position>(particles)[i] = vdouble2(uniform(gen), uniform(gen));
+  particles.init_neighbour_search(vdouble2(0, 0), vdouble2(1, 1), vbool2(false, false));
+  auto F = create_sparse_operator(particles, particles, diameter, kernels::linear_spring<2>(k, diameter));
+  vector_type ones(N, 1.0);
+  vector_type f = F * ones;
+  TS_ASSERT_EQUALS(f.size(), 2 * N);
+  double err2 = 0, nrm2 = 0;
+  for (size_t i = 0; i < N; ++i) {
+    double sx = 0, sy = 0;
+    for (size_t j = 0; j < N; ++j) {
+      const vdouble2 dx = get<position>(particles)[j] - get<position>(particles)[i];
+      const double r = dx.norm();
+      if (dx.squaredNorm() <= diameter * diameter && r != 0) {
+        sx += -k * (diameter / r - 1.0) * dx[0];
+        sy += -k * (diameter / r - 1.0) * dx[1];
+      }
+    }
+    err2 += (sx - f[2 * i]) * (sx - f[2 * i]) + (sy - f[2 * i + 1]) * (sy - f[2 * i + 1]);
+    nrm2 += sx * sx + sy * sy;
+  }
+  TS_ASSERT(nrm2 > 0);
+  TS_ASSERT(std::sqrt(err2 / nrm2) <= 1e-12);
+}
+
 int main() {
+  test_md_force_block_kernel();
   test_sparse_operator();
   test_block_operator();
   test_id_search();
