@@ -201,3 +201,36 @@ def test_md_linear_spring_steps():
     assert np.abs(gvel - vel[oo]).max() < 1e-9
     # the discs did interact
     assert np.abs(gvel - vel0).max() > 1e-3
+
+
+def test_host_pipeline_matches_step_by_step():
+    # aboria_b200.pipeline.HostPipeline: overlapped host-buffer steps give, for every step, exactly
+    # what the plain sequence (upload, init_neighbour_search, K * b, download) gives
+    from aboria_b200.pipeline import HostPipeline
+
+    N, steps = 50000, 7
+    rng = np.random.default_rng(21)
+    side = (10.0 / N) ** (1.0 / 3.0)
+    r = 1.3 * side
+    kern = K.inv_dist(0.1)
+    pos_h = [torch.from_numpy(rng.random((N, 3))).pin_memory() for _ in range(steps)]
+    b_h = [torch.from_numpy(rng.random(N)).pin_memory() for _ in range(steps)]
+    y_h = [torch.empty(N, dtype=torch.float64).pin_memory() for _ in range(steps)]
+    pipe = HostPipeline(3, N, 0.0, 1.0, True, r, kern)
+    for k in range(steps):
+        pipe.submit(pos_h[k], b_h[k], y_h[k])
+    pipe.wait()
+    p = ab.Particles(3, N)
+    op = ab.create_sparse_operator(p, p, r, kern)
+    for k in range(steps):
+        p.resize_from_positions(pos_h[k])
+        p.init_neighbour_search(0.0, 1.0, True)
+        y = op.matvec(b_h[k].to(p.device)).cpu()
+        assert torch.equal(y, y_h[k]), k
+    # a step in which a particle leaves a non-periodic domain is reported, not multiplied
+    pipe2 = HostPipeline(3, N, 0.0, 1.0, False, r, kern)
+    bad = pos_h[0].clone()
+    bad[17, 1] = 1.5
+    pipe2.submit(bad.pin_memory(), b_h[0], y_h[0])
+    with pytest.raises(ab.AbrError):
+        pipe2.wait()
