@@ -430,9 +430,9 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
         double s[BR];
   #pragma unroll
         for (int a2 = 0; a2 < BR; ++a2) {
-          s[a2] = 0;
+          s[a2] = blk[a2 * BC] * bj[0];
   #pragma unroll
-          for (int c = 0; c < BC; ++c) s[a2] += blk[a2 * BC + c] * bj[c];
+          for (int c = 1; c < BC; ++c) s[a2] += blk[a2 * BC + c] * bj[c];
         }
   #pragma unroll
         for (int half = 0; half < 2; ++half) {
