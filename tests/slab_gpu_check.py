@@ -66,9 +66,19 @@ def main():
         cnt, _ = sp.p.pair_stats(radius)
         cnt1, _ = p1.pair_stats(radius)
         same_cnt = np.array_equal(sp.owned(cnt).cpu().numpy(), cnt1.cpu().numpy()[sel])
-        ok = same_order and same_pos and same_cnt and err <= 1e-12
+        # host-buffer steps through SlabHostPipeline: every step equals the device-resident step
+        pos_h = torch.from_numpy(pos[mine].copy()).pin_memory()
+        b_owned_sorted = sp.owned(b_check).clone()
+        b_h = b_owned_sorted.cpu().pin_memory()  # b is indexed by post-reorder position; the order is the same every step
+        y_h = [torch.empty(len(mine), dtype=torch.float64).pin_memory() for _ in range(3)]
+        pipe = slab.SlabHostPipeline(sp, op, len(mine), dev)
+        for k in range(3):
+            pipe.submit(pos_h, b_h, y_h[k])
+        pipe.wait()
+        same_pipe = all(torch.equal(yh, sp.owned(y).cpu()) for yh in y_h)
+        ok = same_order and same_pos and same_cnt and err <= 1e-12 and same_pipe
         print(f"[rank {rank}] N={N} periodic={periodic} r={rfac}*side w={sp.w} layers={sp.lo_layer}..{sp.hi_layer} own={len(own_ids)} "
-              f"ghost={sp.ex.n_ghost_lo}+{sp.ex.n_ghost_hi} order={same_order} pos={same_pos} counts={same_cnt} rel_l2={err:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+              f"ghost={sp.ex.n_ghost_lo}+{sp.ex.n_ghost_hi} order={same_order} pos={same_pos} counts={same_cnt} pipeline={same_pipe} rel_l2={err:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
         ok_all = ok_all and ok
     flag = torch.tensor([1 if ok_all else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
