@@ -27,12 +27,10 @@ namespace abr {
 // particle; the position / alive flag are written back only when they changed
 // (same memory image as the reference's unconditional store, fewer bytes).
 // ---------------------------------------------------------------------------
+// the per-particle part: returns the bucket key (key_bound for a dead particle)
 template <int D, bool WINDOWED>
-__global__ void __launch_bounds__(256)
-k_enforce_key(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t n, Grid g,
-              uint32_t *__restrict__ keys, DevScalars *sc) {
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+__device__ __forceinline__ uint32_t enforce_one(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t p, const Grid &g,
+                                                DevScalars *sc) {
   double r[D], r0[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) r0[d] = r[d] = pos[(size_t)p * D + d];
@@ -84,7 +82,35 @@ k_enforce_key(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t n,
       if (key >= g.key_bound) key = g.key_bound - 1; // cannot happen (v[d] <= size[d]); keeps the sort in range
     }
   }
-  keys[p] = key;
+  return key;
+}
+
+constexpr int EK_THREADS = 256;
+constexpr int EK_TILE = 4096; // == RS_TILE: one block per radix tile, so the block can hand over the tile's first histogram
+
+// hist != nullptr: also writes the tile's digit histogram of (key >> hist_shift) & 255 in the
+// digit-major layout of k_radix_hist (hist[digit * num_tiles + tile]) — the first pass of the
+// sort then needs no histogram kernel of its own.
+template <int D, bool WINDOWED>
+__global__ void __launch_bounds__(EK_THREADS)
+k_enforce_key(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t n, Grid g,
+              uint32_t *__restrict__ keys, DevScalars *sc, uint32_t *__restrict__ hist, int hist_shift, uint32_t num_tiles) {
+  __shared__ uint32_t s_hist[256];
+  const uint32_t tile = blockIdx.x;
+  if (hist) s_hist[threadIdx.x] = 0;
+  if (hist) __syncthreads();
+#pragma unroll 4
+  for (int j = 0; j < EK_TILE / EK_THREADS; ++j) {
+    const uint32_t p = tile * EK_TILE + j * EK_THREADS + threadIdx.x;
+    if (p >= n) break;
+    const uint32_t key = enforce_one<D, WINDOWED>(pos, alive, p, g, sc);
+    keys[p] = key;
+    if (hist) atomicAdd(&s_hist[(key >> hist_shift) & 255u], 1u);
+  }
+  if (hist) {
+    __syncthreads();
+    hist[(size_t)threadIdx.x * num_tiles + tile] = s_hist[threadIdx.x];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -941,27 +967,32 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
 
     uint32_t *keys0 = h->keys[0].as<uint32_t>();
     const unsigned gb = grid_for(n, 256);
+    // LSD radix sort over the bits of key_bound; the key kernel also produces the tile
+    // histograms of the first pass (two-level: of the most significant digit)
+    int bits = 1;
+    while (bits < 32 && (g.key_bound >> bits) != 0) ++bits;
+    const int passes = presorted ? 0 : (bits + 7) / 8; // adopt_sorted: keys only, no permutation
+    const bool two_level = reorder && !presorted && passes >= 2 && n >= h->two_level_min_n && reorder->ncols <= GP_MAXC - 1;
+    uint32_t *hist = h->tile_hist.as<uint32_t>();
+    uint32_t *first_hist = passes > 0 ? hist : nullptr;
+    const int first_shift = two_level ? 8 * (passes - 1) : 0;
+    static_assert(EK_TILE == RS_TILE, "k_enforce_key hands its histogram to the radix tiles");
     if (h->windowed) {
       switch (D) {
-      case 2: k_enforce_key<2, true><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
-      default: k_enforce_key<3, true><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+      case 2: k_enforce_key<2, true><<<num_tiles, EK_THREADS, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars, first_hist, first_shift, num_tiles); break;
+      default: k_enforce_key<3, true><<<num_tiles, EK_THREADS, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars, first_hist, first_shift, num_tiles); break;
       }
     } else {
       switch (D) {
-      case 1: k_enforce_key<1, false><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
-      case 2: k_enforce_key<2, false><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
-      default: k_enforce_key<3, false><<<gb, 256, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars); break;
+      case 1: k_enforce_key<1, false><<<num_tiles, EK_THREADS, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars, first_hist, first_shift, num_tiles); break;
+      case 2: k_enforce_key<2, false><<<num_tiles, EK_THREADS, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars, first_hist, first_shift, num_tiles); break;
+      default: k_enforce_key<3, false><<<num_tiles, EK_THREADS, 0, h->stream>>>(pos, alive, n32, g, keys0, h->d_scalars, first_hist, first_shift, num_tiles); break;
       }
     }
     h->launches += 1;
 
-    // LSD radix sort over the bits of key_bound
     ABR_CUDA(h, cudaFuncSetAttribute(k_radix_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixScatterSmem)));
-    int bits = 1;
-    while (bits < 32 && (g.key_bound >> bits) != 0) ++bits;
-    const int passes = presorted ? 0 : (bits + 7) / 8; // adopt_sorted: keys only, no permutation
     int cur = 0;
-    uint32_t *hist = h->tile_hist.as<uint32_t>();
     const TileTab dense{nullptr, nullptr, nullptr, nullptr, nullptr};
     GatherCols no_cols;
     no_cols.ncols = 0;
@@ -969,7 +1000,6 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     const uint32_t *orig_tmp = nullptr;  // two-level: binned position -> original index
     GatherCols tmp_cols;                 // two-level: the binned copy of every column
     tmp_cols.ncols = 0;
-    const bool two_level = reorder && !presorted && passes >= 2 && n >= h->two_level_min_n && reorder->ncols <= GP_MAXC - 1;
     if (two_level) {
       // ---- level 1: stable partition of whole records by the most significant digit ----
       const int top_shift = 8 * (passes - 1);
@@ -996,7 +1026,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
       }
       uint32_t *keys1 = h->keys[1].as<uint32_t>();
       uint32_t *orig = h->idx[1].as<uint32_t>();
-      k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(keys0, n32, top_shift, num_tiles, hist, dense);
+      // (the histogram of the top digit came with the keys)
       cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
       if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
       ABR_CUDA(h, cudaFuncSetAttribute(k_radix_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixScatterSmem)));
@@ -1007,7 +1037,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
       TileTabW tw{tb, tb + t_bound, tb + 2 * t_bound, tb + 3 * t_bound, tb + 4 * t_bound, tb + 4 * t_bound + 8};
       k_tiletab_bins<<<1, RADIX, 0, h->stream>>>(hist, num_tiles, n32, tw);
       const TileTab seg{tw.start, tw.count, tw.hbase, tw.hstride, tw.total};
-      h->launches += 3;
+      h->launches += 2;
       // ---- level 2: LSD passes over the remaining digits, segmented by bin; they
       //      permute (key, binned position) pairs inside 1/256th of the array ----
       uint32_t *shist = h->seg_hist.as<uint32_t>();
@@ -1040,12 +1070,12 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
         uint32_t *kout = h->keys[cur ^ 1].as<uint32_t>();
         uint32_t *iout = (pass == passes - 1) ? reinterpret_cast<uint32_t *>(order_out)
                                               : h->idx[cur ^ 1].as<uint32_t>();
-        k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, n32, shift, num_tiles, hist, dense);
+        if (pass > 0) k_radix_hist<<<num_tiles, RS_THREADS, 0, h->stream>>>(kin, n32, shift, num_tiles, hist, dense); // pass 0: came with the keys
         cudaError_t e = device_scan<OpSum, false, 0>(h, hist, (uint64_t)RADIX * num_tiles, hist, nullptr);
         if (e != cudaSuccess) return check_cuda(h, e, "radix scan");
         k_radix_scatter<false><<<num_tiles, RS_THREADS, sizeof(RadixScatterSmem), h->stream>>>(kin, iin, kout, iout, hist, shift, n32, num_tiles,
                                                                                                 dense, no_cols);
-        h->launches += 2;
+        h->launches += pass > 0 ? 2 : 1;
         cur ^= 1;
       }
       h->sorted_keys = h->keys[cur].as<uint32_t>();
