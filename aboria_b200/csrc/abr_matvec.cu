@@ -116,7 +116,7 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
     // small grids: hand out single buckets so that every resident warp gets work
     const uint64_t warps = (uint64_t)h->sm_count * 32;
     uint64_t gsz = p->q.g.ncells / (4 * warps);
-    p->grab = (uint32_t)(gsz < 1 ? 1 : (gsz > 8 ? 8 : gsz));
+    p->grab = (uint32_t)(gsz < 1 ? 1 : (gsz > TILED_GRAB ? TILED_GRAB : gsz));
   }
   if (tiled) {
     ABR_CUDA(h, h->danger_list.reserve((size_t)c.n_rows * sizeof(uint32_t)));

@@ -304,7 +304,10 @@ template <int D, class F, bool STATS> struct WarpSmem {
   uint32_t pad_[3];
 };
 
-constexpr uint32_t TILED_GRAB = 8; // most consecutive buckets a warp claims per scheduler step (plan.grab)
+#ifndef ABR_TILED_GRAB
+#define ABR_TILED_GRAB 8
+#endif
+constexpr uint32_t TILED_GRAB = ABR_TILED_GRAB; // most consecutive buckets a warp claims per scheduler step (plan.grab)
 
 // Stencil trimming.  A neighbour bucket at offset o (in buckets) from the target
 // bucket is at least max(|o|-1, 0) * side away from every point of the target
