@@ -1,4 +1,5 @@
 // C-ABI entry points of libabr.so (declared in include/abr.h).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,41 @@ int check_cuda(Handle *h, cudaError_t e, const char *what) {
 void host_set_domain_impl(Handle *h, size_t n);
 int probe_fp64_peak(Handle *h, double *tflops);
 
+} // namespace abr
+
+namespace abr {
+__global__ void __launch_bounds__(256) k_sum_u32(const uint32_t *__restrict__ v, uint64_t n, unsigned long long *__restrict__ out) {
+  unsigned long long acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+// accepted (i, j, image) pairs of a product: a separate stats pass (diagnostic, not part of
+// the product path), reduced on the device
+static int count_pairs(Handle *h, const double *row_pos, size_t n_rows, int rows_are_cols, double radius, const double *radius_per_row,
+                       uint64_t *n_pairs_host) {
+  *n_pairs_host = 0;
+  if (n_rows == 0) return ABR_OK;
+  uint32_t *cnt = nullptr;
+  ABR_CUDA(h, cudaMalloc(&cnt, (n_rows + 3) * sizeof(uint32_t)));
+  unsigned long long *total = reinterpret_cast<unsigned long long *>(cnt + ((n_rows + 1) & ~(size_t)1));
+  cudaMemsetAsync(total, 0, sizeof(unsigned long long), h->stream);
+  MatvecCall s{row_pos, n_rows, rows_are_cols, radius, radius_per_row, nullptr, nullptr, cnt, nullptr, -1};
+  int rc = run_pair_stats(h, s);
+  if (!rc) {
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_rows + 255) / 256, (uint64_t)h->sm_count * 8);
+    k_sum_u32<<<grid, 256, 0, h->stream>>>(cnt, n_rows, total);
+    h->launches += 1;
+    unsigned long long t = 0;
+    cudaMemcpyAsync(&t, total, sizeof(t), cudaMemcpyDeviceToHost, h->stream);
+    rc = check_cuda(h, cudaStreamSynchronize(h->stream), "pair count");
+    *n_pairs_host = t;
+  }
+  cudaFree(cnt);
+  return rc;
+}
 } // namespace abr
 
 using abr::Handle;
@@ -341,25 +377,7 @@ int abr_sparse_matvec(abr_handle hh, const double *row_pos, size_t n_rows, int r
   abr::MatvecCall c{row_pos, n_rows, rows_are_cols, radius, radius_per_row, b, y, nullptr, nullptr, -1};
   int rc = abr::run_builtin_matvec(h, c, k);
   if (rc) return rc;
-  if (n_pairs_host) {
-    // diagnostic: counted by a separate stats pass (not part of the product path)
-    uint32_t *cnt = nullptr;
-    ABR_CUDA(h, cudaMalloc(&cnt, (n_rows + 1) * sizeof(uint32_t)));
-    abr::MatvecCall s{row_pos, n_rows, rows_are_cols, radius, radius_per_row, nullptr, nullptr, cnt, nullptr, -1};
-    rc = abr::run_pair_stats(h, s);
-    uint64_t total = 0;
-    if (!rc) {
-      std::string tmp;
-      uint32_t *hc = new uint32_t[n_rows];
-      cudaMemcpyAsync(hc, cnt, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream);
-      cudaStreamSynchronize(h->stream);
-      for (size_t i = 0; i < n_rows; ++i) total += hc[i];
-      delete[] hc;
-    }
-    cudaFree(cnt);
-    *n_pairs_host = total;
-    if (rc) return rc;
-  }
+  if (n_pairs_host) return abr::count_pairs(h, row_pos, n_rows, rows_are_cols, radius, radius_per_row, n_pairs_host);
   return ABR_OK;
 }
 
@@ -478,7 +496,7 @@ int abr_sparse_matvec_custom(abr_handle hh, const double *row_pos, size_t n_rows
   abr::MatvecCall c{row_pos, n_rows, rows_are_cols, radius, radius_per_row, b, y, nullptr, nullptr, -1};
   int rc = abr::run_custom_matvec(h, c, launch, functor, BR, BC);
   if (rc) return rc;
-  if (n_pairs_host) *n_pairs_host = 0;
+  if (n_pairs_host) return abr::count_pairs(h, row_pos, n_rows, rows_are_cols, radius, radius_per_row, n_pairs_host);
   return ABR_OK;
 }
 

@@ -1224,4 +1224,15 @@ int orc_max_threads() {
 #endif
 }
 
+// Sets the OpenMP team size for every later parallel region of the oracle.  bench.py calls
+// it with the number of host cores it may use: launchers such as torchrun export
+// OMP_NUM_THREADS=1, which would silently turn the timed CPU arm into a single-thread run.
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 } // extern "C"

@@ -74,6 +74,7 @@ def lib():
         L.orc_bucket_pairs.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int8), C.c_uint64]
         L.orc_fast_bucket_search_counts.argtypes = [vp, C.c_double, C.POINTER(C.c_uint32)]
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -358,3 +359,16 @@ def id_find(key, value, query):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def set_num_threads(n):
+    """OpenMP team size of the oracle from here on (overrides OMP_NUM_THREADS)"""
+    lib().orc_set_num_threads(int(n))
+
+
+def host_cores():
+    """cores this process may run on (the affinity mask, not OMP_NUM_THREADS)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1

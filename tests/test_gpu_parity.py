@@ -346,6 +346,46 @@ def test_c3_lj_4m_newton_third_law_and_sampled_oracle():
     assert rel_l2(y_g, y_o) <= TOL
 
 
+def test_c5_32m_sampled_oracle():
+    # configs[4] / the bench workload itself: 3-D periodic unit cube, uniform, N = 32M per GPU,
+    # r = bucket side, 1/(|dx|+0.1).  The oracle re-sorts the GPU's sorted positions (identity:
+    # the stable build is idempotent, so order and bucket ranges are checked at full size) and
+    # evaluates 1-in-4001 rows; pair counts and pair-set hashes of those rows are compared too,
+    # and the total pair count against the analytic expectation of a uniform cloud.
+    N = 32_000_000
+    dev = torch.device("cuda:0")
+    pos = synth.torch_uniform_positions(N, 3, 0.0, 1.0, synth.SEED, 0, dev)
+    p = ab.Particles(3, 0)
+    p.resize_from_positions(pos)
+    del pos
+    p.init_neighbour_search(0.0, 1.0, True)
+    size, side, nb = p.grid()
+    assert list(size) == [147, 147, 147]
+    r = float(side[0])
+    b = torch.from_numpy(synth.vector(N)).to(dev)
+    op = ab.create_sparse_operator(p, p, r, K.inv_dist(0.1))
+    y = op * b
+    cnt, hs = p.pair_stats(r, path=0)
+    total = int(cnt.long().sum())
+    expect = N * (1.0 + 4.0 / 3.0 * np.pi * r**3 * N)
+    assert abs(total - expect) / expect < 1e-3
+    ps = p.get("position").cpu().numpy()
+    o = orc.Oracle(3)
+    o.set_domain(0.0, 1.0, True, 10.0)
+    out = o.update_positions(ps.copy())
+    assert np.array_equal(out["order"], np.arange(N, dtype=np.int32))
+    q = p.get_query()
+    assert np.array_equal(q.bucket_begin.cpu().numpy().view(np.uint32), out["bucket_begin"])
+    assert np.array_equal(q.bucket_end.cpu().numpy().view(np.uint32), out["bucket_end"])
+    o.update_iterators(ps)
+    sub = np.arange(0, N, 4001)
+    y_o, _ = o.sparse_matvec(ps[sub], orc.K_INV_DIST, [0.1], r, b.cpu().numpy())
+    assert rel_l2(y.cpu().numpy()[sub], y_o) <= TOL
+    cnt_o, hs_o = o.pair_stats(ps[sub], r)
+    assert np.array_equal(cnt.cpu().numpy().view(np.uint32)[sub], cnt_o)
+    assert np.array_equal(hs.cpu().numpy().view(np.uint64)[sub], hs_o)
+
+
 def test_c4_sph_clustered_16m_properties():
     # configs[3]: SPH density sum, N=16M clustered cloud (64 Gaussian blobs + 10 % background),
     # periodic (1,1,0).  Oracle too slow at this size: tiled == exact walk on sampled rows,
