@@ -93,6 +93,8 @@ int abr_create(abr_handle *out, int device, void *stream) {
   }
   cudaMemset(h->d_scalars, 0, sizeof(abr::DevScalars));
   if (const char *e = getenv("ABR_PHASED_GATHER")) h->phased_gather = (e[0] != '0');
+  if (const char *e = getenv("ABR_MATVEC_VARIANT")) h->matvec_variant = atoi(e);
+  if (const char *e = getenv("ABR_SYMMETRIC")) h->symmetric = (e[0] != '0');
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
   for (int d = 0; d < abr::MAXD; ++d) {
@@ -124,6 +126,8 @@ int abr_destroy(abr_handle hh) {
   h->bucket_begin.release();
   h->bucket_end.release();
   h->danger_list.release();
+  h->ytmp.release();
+  h->row_bits.release();
   h->posb.release();
   for (int i = 0; i < 2; ++i) {
     h->idm_k[i].release();
@@ -155,8 +159,14 @@ int abr_set_option(abr_handle hh, const char *name, double value) {
   const std::string k(name);
   if (k == "two_level_min_n") {
     h->two_level_min_n = value < 0 ? 0 : (size_t)value;
+  } else if (k == "counting_min_n") {
+    h->counting_min_n = value < 0 ? 0 : (value > 1e18 ? (size_t)-1 : (size_t)value);
   } else if (k == "phased_gather") {
     h->phased_gather = value != 0;
+  } else if (k == "symmetric") {
+    h->symmetric = value != 0;
+  } else if (k == "matvec_variant") {
+    h->matvec_variant = (int)value;
   } else {
     return abr::set_error(h, ABR_ERR_INVALID, "set_option: unknown option " + k);
   }

@@ -18,6 +18,7 @@
 #include <cmath>
 
 #include "abr_internal.h"
+#include "abr_enforce.cuh"
 
 namespace abr {
 
@@ -27,64 +28,6 @@ namespace abr {
 // particle; the position / alive flag are written back only when they changed
 // (same memory image as the reference's unconditional store, fewer bytes).
 // ---------------------------------------------------------------------------
-// the per-particle part: returns the bucket key (key_bound for a dead particle)
-template <int D, bool WINDOWED>
-__device__ __forceinline__ uint32_t enforce_one(double *__restrict__ pos, uint8_t *__restrict__ alive, uint32_t p, const Grid &g,
-                                                DevScalars *sc) {
-  double r[D], r0[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) r0[d] = r[d] = pos[(size_t)p * D + d];
-  const uint8_t a0 = alive[p];
-  uint8_t a = a0;
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    if (!isfinite(r[d])) {
-      a = 0;
-    } else if (g.periodic[d]) {
-      // The reference loops without bound (and never terminates once |r|/L
-      // exceeds 2^53).  A GPU kernel must not hang: after 2^20 steps the
-      // particle is killed like a non-finite one (documented deviation).
-      int guard = 0;
-      while (r[d] < g.bmin[d] && ++guard < (1 << 20)) r[d] += (g.bmax[d] - g.bmin[d]);
-      while (r[d] >= g.bmax[d] && ++guard < (1 << 20)) r[d] -= (g.bmax[d] - g.bmin[d]);
-      if (guard >= (1 << 20)) {
-        a = 0;
-        r[d] = r0[d];
-      }
-    } else {
-      if ((r[d] < g.bmin[d]) || (r[d] >= g.bmax[d])) a = 0;
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < D; ++d)
-    if (__double_as_longlong(r[d]) != __double_as_longlong(r0[d])) pos[(size_t)p * D + d] = r[d];
-  if (a != a0) alive[p] = a;
-  uint32_t key = g.key_bound;
-  if (a) {
-    int v[D];
-    bool overflow = false;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      v[d] = (int)floor((r[d] - g.bmin[d]) * g.inv_side[d]);
-      overflow |= (v[d] >= g.size[d]) | (v[d] < 0);
-    }
-    if (WINDOWED) {
-      const int cl = overflow ? -1 : local_collapse<D>(g, v);
-      if (cl < 0) {
-        atomicAdd(&sc->n_outside, 1u); // not this rank's particle: reported as an error by the host
-        key = g.key_bound;
-      } else {
-        key = (uint32_t)cl;
-      }
-    } else {
-      key = (uint32_t)collapse_index<D>(g, v);
-      if (overflow) atomicAdd(&sc->n_aliased, 1u);
-      if (key >= g.key_bound) key = g.key_bound - 1; // cannot happen (v[d] <= size[d]); keeps the sort in range
-    }
-  }
-  return key;
-}
-
 constexpr int EK_THREADS = 256;
 constexpr int EK_TILE = 4096; // == RS_TILE: one block per radix tile, so the block can hand over the tile's first histogram
 
@@ -124,7 +67,6 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RADIX = 256;
 
 // a set of columns (device pointers + element sizes) passed to kernels by value
-constexpr int GP_MAXC = 8;
 struct GatherCols {
   int ncols;
   const uint8_t *src[GP_MAXC];
@@ -965,14 +907,25 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     k_set_scalars<<<1, 1, 0, h->stream>>>(h->d_scalars, init);
     h->launches += 1;
 
-    uint32_t *keys0 = h->keys[0].as<uint32_t>();
     const unsigned gb = grid_for(n, 256);
-    // LSD radix sort over the bits of key_bound; the key kernel also produces the tile
-    // histograms of the first pass (two-level: of the most significant digit)
     int bits = 1;
     while (bits < 32 && (g.key_bound >> bits) != 0) ++bits;
+    // large sets: counting-sort build (abr_build2.cu) — keys, bucket ranges and the reorder of every column in three kernels
+    const bool counting = !presorted && counting_build_applicable(h, n, bits, reorder, alive);
+    bool two_level = false;
+    const uint32_t *perm = nullptr;      // two-level: final position -> position in the binned copy
+    const uint32_t *orig_tmp = nullptr;  // two-level: binned position -> original index
+    GatherCols tmp_cols;                 // two-level: the binned copy of every column
+    tmp_cols.ncols = 0;
+    if (counting) {
+      const int rc = build_counting(h, pos, alive, n32, g, bits, reorder, order_out);
+      if (rc) return rc;
+    } else {
+    uint32_t *keys0 = h->keys[0].as<uint32_t>();
+    // LSD radix sort over the bits of key_bound; the key kernel also produces the tile
+    // histograms of the first pass (two-level: of the most significant digit)
     const int passes = presorted ? 0 : (bits + 7) / 8; // adopt_sorted: keys only, no permutation
-    const bool two_level = reorder && !presorted && passes >= 2 && n >= h->two_level_min_n && reorder->ncols <= GP_MAXC - 1;
+    two_level = reorder && !presorted && passes >= 2 && n >= h->two_level_min_n && reorder->ncols <= GP_MAXC - 1;
     uint32_t *hist = h->tile_hist.as<uint32_t>();
     uint32_t *first_hist = passes > 0 ? hist : nullptr;
     const int first_shift = two_level ? 8 * (passes - 1) : 0;
@@ -996,10 +949,6 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     const TileTab dense{nullptr, nullptr, nullptr, nullptr, nullptr};
     GatherCols no_cols;
     no_cols.ncols = 0;
-    const uint32_t *perm = nullptr;      // two-level: final position -> position in the binned copy
-    const uint32_t *orig_tmp = nullptr;  // two-level: binned position -> original index
-    GatherCols tmp_cols;                 // two-level: the binned copy of every column
-    tmp_cols.ncols = 0;
     if (two_level) {
       // ---- level 1: stable partition of whole records by the most significant digit ----
       const int top_shift = 8 * (passes - 1);
@@ -1091,8 +1040,10 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     cudaError_t e = device_scan<OpMin, true, 1>(h, bb, prod, bb, be);
     if (e != cudaSuccess) return check_cuda(h, e, "bucket fill");
 
+    } // radix builds
+
     publish_scalars(h);
-    if (reorder) {
+    if (reorder && !counting) {
       // Particles::reorder enqueued behind the build, bounded by the device-side
       // alive count: the only host round trip of update_positions is the final one
       int rc;

@@ -70,12 +70,17 @@ struct Handle {
   // --- device state ---------------------------------------------------------
   DevBuf keys[2], idx[2], tile_hist, scan_tmp;
   DevBuf idx2, tmp_cols, tile_tab, seg_hist; // two-level build
+  DevBuf cs_ko, cs_scratch, cs_scratch2, cs_bins; // counting-sort build (abr_build2.cu)
+  size_t counting_min_n = (size_t)-1;             // counting-sort build (abr_build2.cu) from this many particles; off by default: measured slower
+                                                  // than the two-level radix build on B200 (3.4 vs 2.7 ms at 32 M, profiles/r2f_counting_build.txt)
   size_t two_level_min_n = (size_t)1 << 20;  // use the two-level build from this many particles (abr_set_option)
   DevBuf bucket_begin, bucket_end;
   DevBuf danger_list;
   DevBuf scan_tmp2, pair_i, pair_j, pair_q; // bucket-pair traversal (abr_pairs.cu)
   DevBuf idm_k[2], idm_i[2], idm_max, id_map_key, id_map_value; // id map (m_id_map_key / m_id_map_value) + sort scratch
   size_t id_map_n = 0;
+  DevBuf ytmp, row_bits; // symmetric product: accumulation scratch, exact-walk flags
+  bool symmetric = false; // abr_set_option("symmetric"): evaluate each unordered pair once for functors that declare SYMMETRY
   DevBuf posb; // packed (x, y, z, b) records of the column particles for the tiled product
   DevScalars *d_scalars = nullptr;
   DevScalars *h_scalars = nullptr; // pinned read-back mirror, written by k_publish_scalars
@@ -91,6 +96,7 @@ struct Handle {
 
   uint64_t counters[4] = {0, 0, 0, 0};
   uint64_t launches = 0; // kernels launched since abr_create
+  int matvec_variant = 0; // tiled product: 0 = gathers from L2 (tiled_kernel), 1 = bulk-copy staging (staged_kernel); abr_set_option("matvec_variant")
   bool phased_gather = false; // L2-windowed reorder for column sets larger than L2 (measured SLOWER on B200: 5.8 vs 3.0 ms build; ABR_PHASED_GATHER=1 enables)
   uint64_t gather_src_n = 0; // source length of the gather in flight (0: unknown, use n_out)
 
@@ -99,6 +105,8 @@ struct Handle {
 
 int set_error(Handle *h, int code, const std::string &msg);
 int check_cuda(Handle *h, cudaError_t e, const char *what);
+
+constexpr int GP_MAXC = 8; // columns a reorder kernel takes by value
 
 // abr_build.cu
 struct ReorderSpec {
@@ -109,6 +117,9 @@ struct ReorderSpec {
 };
 int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *order_out,
                    size_t *n_alive_host, const ReorderSpec *reorder, bool presorted = false);
+// abr_build2.cu
+bool counting_build_applicable(const Handle *h, size_t n, int bits, const ReorderSpec *reorder, const uint8_t *alive);
+int build_counting(Handle *h, double *pos, uint8_t *alive, uint32_t n, const Grid &g, int bits, const ReorderSpec *reorder, int32_t *order_out);
 int gather_columns(Handle *h, int ncols, const void *const *src, void *const *dst,
                    const size_t *elem_bytes, const int32_t *order, size_t n_out, const uint32_t *n_dev);
 

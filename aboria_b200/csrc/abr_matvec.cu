@@ -112,6 +112,18 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
       return set_error(h, ABR_ERR_INVALID, "tiled path not applicable for this radius / grid");
   }
   p->use_tiled = tiled ? 1 : 0;
+  p->variant = h->matvec_variant;
+  if (tiled && h->symmetric && c.b && c.y && !c.count && !c.hash) {
+    // symmetric product (functors that declare SYMMETRY): zeroed accumulation scratch + one flag bit per row
+    const size_t ny = (size_t)c.n_rows * (size_t)(BR > 0 ? BR : 1);
+    ABR_CUDA(h, h->ytmp.reserve(ny * sizeof(double)));
+    ABR_CUDA(h, h->row_bits.reserve(((size_t)c.n_rows / 32 + 2) * sizeof(uint32_t)));
+    fill_u32(h, h->ytmp.as<uint32_t>(), 0u, ny * 2);
+    fill_u32(h, h->row_bits.as<uint32_t>(), 0u, (uint64_t)c.n_rows / 32 + 2);
+    p->symmetric = 1;
+    p->ytmp = h->ytmp.as<double>();
+    p->row_bits = h->row_bits.as<uint32_t>();
+  }
   {
     // small grids: hand out single buckets so that every resident warp gets work
     const uint64_t warps = (uint64_t)h->sm_count * 32;
@@ -144,7 +156,8 @@ template <int D, class F, bool STATS>
 static int launch_checked(Handle *h, const abr_matvec_plan &p, const F &f) {
   const int e = launch_plan<D, F, STATS>(p, f);
   if (e != 0) return check_cuda(h, (cudaError_t)e, "matvec launch");
-  h->counters[2] = p.use_tiled ? 2 : 1;
+  const bool sym = !STATS && symmetry<F>::value != 0 && p.symmetric && p.ytmp && p.row_bits;
+  h->counters[2] = p.use_tiled ? (sym ? 3 : 2) : 1;
   h->launches += h->counters[2];
   return ABR_OK;
 }

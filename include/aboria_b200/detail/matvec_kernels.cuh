@@ -63,6 +63,10 @@ struct abr_matvec_plan {
   cudaStream_t stream;
   int sm_count;
   int walk_only_list; // walk kernel processes danger_list instead of all rows
+  int symmetric;      // tiled path: half stencil + y[j] scatter for functors that declare SYMMETRY (see tiled_kernel)
+  double *ytmp;       //   zeroed scratch the symmetric kernel accumulates into (n_rows * BR)
+  uint32_t *row_bits; //   one bit per row: result comes from the exact walk, not from ytmp
+  int variant;        // tiled path: 0 = tiled_kernel (gathers from L2), 1 = staged_kernel (bulk-copy staging in shared memory)
 };
 
 namespace abr {
@@ -242,6 +246,15 @@ template <int D, class F> inline int launch_coeff(const abr_matvec_plan &p, cons
 template <class F, class = void> struct needs_dx { static constexpr bool value = true; };
 template <class F> struct needs_dx<F, decltype((void)F::NEEDS_DX)> { static constexpr bool value = F::NEEDS_DX; };
 
+// Symmetry of the kernel function under exchange of the two particles, declared by the functor:
+//   static constexpr int SYMMETRY = +1   block(-dx, b, a) == +block(dx, a, b)   (1/(r+eps), Wendland, SPH density ...)
+//   static constexpr int SYMMETRY = -1   block(-dx, b, a) == -block(dx, a, b)   (central forces: LJ, linear spring)
+// default 0: no assumption.  With a symmetric functor and rows == columns the product can evaluate every
+// unordered pair ONCE (half stencil, "fast cell-list search" of tests/neighbours.h:281-300 /
+// src/Search.h:498-764) and add the result to both rows.
+template <class F, class = void> struct symmetry { static constexpr int value = 0; };
+template <class F> struct symmetry<F, decltype((void)F::SYMMETRY)> { static constexpr int value = F::SYMMETRY; };
+
 #ifndef ABR_QDRAIN
 #define ABR_QDRAIN 14
 #endif
@@ -282,6 +295,16 @@ template <int D, class F, bool STATS> struct TiledCfg {
   static constexpr int RB = NACC == 1 ? (1 << ROW_BITS) : ABR_BLOCK_RB;
 };
 
+// what the symmetric kernel's drain needs besides DrainCtx; kept in the warp's shared memory (a by-value
+// argument of this size would travel through local memory at every call of the non-inlined drain)
+struct SymCtx {
+  double *ytmp;
+  uint32_t *row_bits, *danger_count, *danger_list;
+  uint32_t danger_capacity;
+  uint32_t own_p0, own_p1; // rows this rank owns: [own_p0, own_p1)
+  uint32_t pad_;
+};
+
 // per-warp shared memory (a warp works on one target bucket at a time and never
 // synchronises with the other warps of its CTA)
 template <int D, class F, bool STATS> struct WarpSmem {
@@ -301,7 +324,10 @@ template <int D, class F, bool STATS> struct WarpSmem {
   uint32_t run_pref[32];                  // candidate-run directory: inclusive prefix of run lengths
   uint32_t run_delta[32];                 //   j = k + run_delta[run]
   uint32_t danger;
-  uint32_t pad_[3];
+  uint32_t danger_pre;                    // rows flagged before the candidates are seen (symmetric kernel: their partners are flagged too)
+  uint32_t pad_[2];
+  double rowsb[F::BC][RB];                // b of the rows (symmetric kernel only: y[j] += K(j,i) b[i])
+  SymCtx sym;
 };
 
 #ifndef ABR_TILED_GRAB
@@ -349,6 +375,18 @@ struct DrainCtx {
   double r2lo;
   double r2;
 };
+// symmetric kernel: bit 31 of the drain's image_id argument marks the primary image, where a pair
+// (i, j > i) counts for both rows; periodic-image runs are one-sided (every pair, row i only)
+constexpr uint32_t TWO_SIDED = 0x80000000u;
+// symmetric kernel: row j's result must come from the exact walk (first flagging appends it to the list)
+__device__ __forceinline__ void flag_row(const SymCtx &p, uint32_t j) {
+  const uint32_t bit = 1u << (j & 31u);
+  const uint32_t old = atomicOr(&p.row_bits[j >> 5], bit);
+  if (!(old & bit)) {
+    const uint32_t slot = atomicAdd(p.danger_count, 1u);
+    if (slot < p.danger_capacity) p.danger_list[slot] = j;
+  }
+}
 
 // Drain the lane-private queues.  The queued (j, row) pairs of all lanes are
 // first compacted into one warp-wide list (an exclusive scan of the queue
@@ -357,7 +395,7 @@ struct DrainCtx {
 // lane utilisation instead of on the ~15 % of lanes that pass the cut-off test.
 // dx and |dx|^2 are recomputed here in fp64 with the reference's operations in
 // the reference's order.
-template <int D, class F, bool STATS, class SM>
+template <int D, class F, bool STATS, int SYM, class SM>
 __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, int lane, uint32_t cnt, uint32_t r0,
                                           const double (*rowp)[SM::RB], uint32_t image_id) {
   constexpr int BR = F::BR, BC = F::BC;
@@ -411,7 +449,20 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
       }
       // the queue holds the survivors of the conservative fp32 pre-filter; this is
       // the reference's exact predicate (src/Search.h:438-446)
-      const bool ok = live && !(d2 > p.r2);
+      bool ok = live && !(d2 > p.r2);
+      bool both = false; // symmetric kernel: this pair also counts for row j
+      if (SYM != 0) {
+        // primary image: every unordered pair of the half stencil once (j > i; the self pair j == i one-sided);
+        // j < i only occurs inside the target bucket itself and is the pair (j, i) seen from row j
+        const uint32_t gi = r0 + i;
+        if (image_id & TWO_SIDED) {
+          const uint32_t o0 = sm.sym.own_p0, o1 = sm.sym.own_p1;
+          ok = ok && j >= gi;
+          both = ok && j > gi && j >= o0 && j < o1;
+          ok = ok && gi >= o0 && gi < o1; // a ghost row (slab ranks) only serves its owned partners
+        }
+        if (both && (d2 > p.r2lo || ((sm.danger_pre >> i) & 1u))) flag_row(sm.sym, j);
+      }
       if (ok && d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
       // lanes l and l+16 share a column of the partial-sum table: the two halves of
       // the warp update it one after the other
@@ -436,6 +487,18 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
           s[a2] = blk[a2 * BC] * bj[0];
   #pragma unroll
           for (int c = 1; c < BC; ++c) s[a2] += blk[a2 * BC + c] * bj[c];
+        }
+        if (SYM != 0) {
+          // y[j] += K(j, i) b[i] with K(j, i) = SYM * K(i, j): one fp64 reduction per block row (RED.E.ADD.F64)
+          if (both) {
+  #pragma unroll
+            for (int a2 = 0; a2 < BR; ++a2) {
+              double t = blk[a2 * BC] * sm.rowsb[0][i];
+  #pragma unroll
+              for (int c = 1; c < BC; ++c) t += blk[a2 * BC + c] * sm.rowsb[c][i];
+              atomicAdd(&sm.sym.ytmp[(size_t)j * BR + a2], SYM > 0 ? t : -t);
+            }
+          }
         }
   #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -490,7 +553,7 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 // pointer bump; the exact un-fused fp64 predicate is applied to them in
 // drain_queues.  (6.45 candidates are tested per accepted pair, so this loop is
 // kept off the fp64 pipe altogether.)
-template <int D, class F, bool STATS, class SM>
+template <int D, class F, bool STATS, int SYM, class SM>
 __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_r2, const F &f, int lane,
                                           const float *pA, const float *pB, uint32_t jA, uint32_t jB, bool vA, bool vB,
                                           int nr, const double (*rowp)[SM::RB], uint32_t image_id, uint32_t r0,
@@ -531,7 +594,7 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
     eA += 2u;
     eB += 2u;
     if (__any_sync(0xFFFFFFFFu, qa >= q0 + QDRAIN * 128u)) {
-      drain_queues<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 7, r0, rowp, image_id);
+      drain_queues<D, F, STATS, SYM>(sm, dc, f, lane, (qa - q0) >> 7, r0, rowp, image_id);
       qa = q0;
     }
   }
@@ -539,8 +602,21 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
 
 // occupancy target: TiledCfg::CTAS CTAs/SM (6.4 KB of shared memory per warp): 7 or 8 for
 // scalar kernels, 5 for D x 1 block kernels
-template <int D, class F, bool STATS>
-__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::CTAS))
+//
+// SYM != 0 (functor-declared symmetry, rows == columns): the symmetric form.  A target bucket is tested
+// against the FORWARD half of its stencil only (itself and the neighbours after it in bucket order); an
+// accepted pair (i, j > i) is evaluated once and added to both rows — row i through the warp's partial-sum
+// table, row j with one fp64 reduction (RED.E.ADD.F64) per block row.  All sums go to the zeroed scratch
+// `ytmp` (k_sym_combine adds it to y afterwards) because a row flagged for the exact walk — by its own
+// bucket or by a partner — must not keep partial sums.  Periodic-image runs stay one-sided (cur = r +
+// image * L is not antisymmetric under exchange in floating point).  On slab ranks the lower ghost layers
+// are targets too (their forward neighbours are owned rows); only owned rows receive sums.
+// Results differ from the ordered form by summation order only (fp64 atomics are not ordered).
+#ifndef ABR_SYM_CTAS_LESS
+#define ABR_SYM_CTAS_LESS 1 // the symmetric form keeps a little more state: one resident CTA less per SM
+#endif
+template <int D, class F, bool STATS, int SYM = 0>
+__global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::CTAS - (SYM != 0 && TiledCfg<D, F, STATS>::CTAS > 5 ? ABR_SYM_CTAS_LESS : 0)))
 tiled_kernel(const abr_matvec_plan p, const F f) {
   constexpr int BR = F::BR;
   constexpr int NACC = TiledCfg<D, F, STATS>::NACC;
@@ -562,14 +638,26 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
   int img0[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) img0[d] = 0;
-  const uint32_t image_id0 = STATS ? (uint32_t)image_linear_index<D>(g, img0) : 0u;
+  const uint32_t image_id0 = STATS ? (uint32_t)image_linear_index<D>(g, img0) : (SYM != 0 ? TWO_SIDED : 0u);
   // buckets of the bucket layers this rank owns (all of them on a single GPU)
   uint32_t per_layer = 1;
 #pragma unroll
   for (int d = 1; d < D; ++d) per_layer *= (uint32_t)g.size[d];
   const uint32_t first_cell = (D > 1 ? (uint32_t)g.own_lo * per_layer : 0u);
   const uint32_t own_cells = (D > 1 ? (uint32_t)g.own_n * per_layer : g.ncells);
+  // target buckets: the owned ones; the symmetric kernel also visits the lower ghost layers of a slab rank
+  const uint32_t tfirst = SYM != 0 ? 0u : first_cell;
+  const uint32_t tcount = first_cell + own_cells - tfirst;
+  uint32_t own_p0 = 0, own_p1 = 0xFFFFFFFFu;
+  if (SYM != 0 && own_cells > 0) {
+    own_p0 = bbeg[first_cell];
+    own_p1 = bend[first_cell + own_cells - 1];
+  }
   const DrainCtx dc{p.posb, p.b, p.r2lo, p.r2};
+  if (SYM != 0) {
+    if (lane == 0) sm.sym = SymCtx{p.ytmp, p.row_bits, p.danger_count, p.danger_list, p.danger_capacity, own_p0, own_p1, 0u};
+    __syncwarp();
+  }
   const double *__restrict__ posb = p.posb;
   const float pre_r2 = p.pre_r2;
   const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
@@ -600,14 +688,14 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
     uint32_t grab = 0;
     if (lane == 0) grab = atomicAdd(p.work_counter, p.grab);
     grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
-    if (grab >= own_cells) break;
-    const uint32_t grab_end = min(grab + p.grab, own_cells);
+    if (grab >= tcount) break;
+    const uint32_t grab_end = min(grab + p.grab, tcount);
 
     // bucket coordinates of the first bucket of the grab (inverse of collapse_index);
     // the following ones are reached by counting up, last dimension fastest
     int tc[D];
     {
-      const uint32_t cell = first_cell + grab;
+      const uint32_t cell = tfirst + grab;
       uint32_t rem = cell;
 #pragma unroll
       for (int d = D - 1; d >= 0; --d) {
@@ -623,7 +711,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
     }
     --tc[L]; // the loop advances before it works
 
-    for (uint32_t cell = first_cell + grab; cell < first_cell + grab_end; ++cell) {
+    for (uint32_t cell = tfirst + grab; cell < tfirst + grab_end; ++cell) {
       // advance the bucket coordinates to `cell`
       if (++tc[L] == S) {
         if (D > 1) {
@@ -640,6 +728,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
       }
       const uint32_t rb = bbeg[cell], re = bend[cell];
       if (rb == re) continue;
+      const bool owned_target = SYM == 0 || first_cell == 0u || cell >= first_cell; // else: a lower ghost layer (symmetric kernel on a slab rank)
       const int zlo = tc[L] - p.w[L], zhi = tc[L] + p.w[L];
       // does any neighbour of this bucket lie across a periodic boundary / outside?
       bool boundary = (zlo < 0) | (zhi >= S);
@@ -668,6 +757,14 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
           }
         }
         if (lane == 0) sm.danger = 0;
+        if (SYM != 0) {
+          if (lane < nr) {
+#pragma unroll
+            for (int c = 0; c < F::BC; ++c) sm.rowsb[c][lane] = p.b[(size_t)(r0 + lane) * F::BC + c];
+          }
+          const uint32_t pre = __ballot_sync(0xFFFFFFFFu, my_danger);
+          if (lane == 0) sm.danger_pre = pre;
+        }
         __syncwarp();
         if (lane < RB + 2) {
           // fp32 copy relative to the stencil origin (lower corner of the first neighbour
@@ -706,7 +803,18 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
               ok &= (u >= 0) & (u < g.size[d]);
               nc[d] = u;
             }
-            const int a = max(tc[L] - wz, 0), bnd = min(tc[L] + wz, S - 1);
+            int zfirst = tc[L] - wz;
+            if (SYM != 0) {
+              // forward half of the stencil: runs after the target's own run in bucket order, and of the
+              // own run the part from the target bucket on
+              int sgn = 0;
+#pragma unroll
+              for (int d = 0; d < D - 1; ++d)
+                if (sgn == 0 && od[d] != 0) sgn = od[d] > 0 ? 1 : -1;
+              ok &= sgn >= 0;
+              if (sgn == 0) zfirst = tc[L];
+            }
+            const int a = max(zfirst, 0), bnd = min(tc[L] + wz, S - 1);
             if (ok && wz >= 0 && a <= bnd) {
               nc[L] = a;
               const int c_lo = local_collapse<D>(g, nc);
@@ -754,16 +862,16 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
 #pragma unroll
               for (int d = 0; d < D; ++d) pj[h][d] = (float)(rec[d] - origin[d]);
             }
-            test_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
-                                   image_id0, r0, qa);
+            test_rows<D, F, STATS, SYM>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
+                                        image_id0, r0, qa);
           }
         }
         // pairs queued so far belong to the primary image
         if (__any_sync(0xFFFFFFFFu, qa != q0)) {
-          drain_queues<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rows0, image_id0);
+          drain_queues<D, F, STATS, SYM>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rows0, image_id0);
           qa = q0;
         }
-        if (boundary) {
+        if (boundary && owned_target) {
           // ---- phase 2 (buckets at a periodic boundary only): runs reached through
           //      a periodic image; cur = r + image * L exactly as src/Search.h:188-190 ----
           int o[DS];
@@ -825,17 +933,653 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) pj[h][d] = (float)((rec[d] - (double)img[d] * g.L[d]) - origin[d]);
                   }
-                  test_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
-                                         image_id, r0, qa);
+                  test_rows<D, F, STATS, SYM>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
+                                              image_id, r0, qa);
                 }
                 // leave no pair of this image in the queues (rowsS is reused)
                 if (__any_sync(0xFFFFFFFFu, qa != q0)) {
-                  drain_queues<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rowsS, image_id);
+                  drain_queues<D, F, STATS, SYM>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rowsS, image_id);
                   qa = q0;
                 }
               }
             }
             // next offset tuple in the slow dimensions (odometer)
+            more = false;
+#pragma unroll
+            for (int d = D - 2; d >= 0; --d) {
+              if (!more) {
+                if (++o[d] <= p.w[d]) {
+                  more = true;
+                } else {
+                  o[d] = -p.w[d];
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+
+        // ---- reduce part[row][*] in a fixed (skewed, conflict-free) order ----
+        const uint32_t dmask = sm.danger | __ballot_sync(0xFFFFFFFFu, my_danger);
+        if (lane < nr && owned_target) {
+          const bool dangerous = (dmask >> lane) & 1u;
+          if (dangerous) {
+            if (SYM != 0) {
+              flag_row(sm.sym, r0 + lane); // a partner's drain may have flagged it already
+            } else {
+              const uint32_t slot = atomicAdd(p.danger_count, 1u);
+              if (slot < p.danger_capacity) p.danger_list[slot] = r0 + lane;
+            }
+          } else if (STATS) {
+            unsigned long long c = 0, hsum = 0;
+#pragma unroll
+            for (int k = 0; k < PCOL; ++k) {
+              c += sm.part[0][lane][(k + lane) & (PCOL - 1)];
+              hsum += sm.part[1][lane][(k + lane) & (PCOL - 1)];
+            }
+            if (p.stat_count) p.stat_count[r0 + lane] = (uint32_t)c;
+            if (p.stat_hash) p.stat_hash[r0 + lane] = hsum;
+          } else {
+#pragma unroll
+            for (int a2 = 0; a2 < NACC; ++a2) {
+              double s = 0;
+#pragma unroll
+              for (int k = 0; k < PCOL; ++k) s += *reinterpret_cast<double *>(&sm.part[a2][lane][(k + lane) & (PCOL - 1)]);
+              if (SYM != 0)
+                atomicAdd(&p.ytmp[(size_t)(r0 + lane) * BR + a2], s); // partners add to the same entry concurrently
+              else
+                p.y[(size_t)(r0 + lane) * BR + a2] += s;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// staged_kernel — the cell-tiled product with the candidate records staged in
+// shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, SASS UBLKCP /
+// SYNCS): "stages the neighbouring cells' sorted positions and b values into shared
+// memory with TMA" (north_star).
+//
+// Same decomposition as tiled_kernel (one warp per target bucket, candidates = the
+// contiguous particle runs of the neighbouring buckets, conservative fp32 pre-filter,
+// exact fp64 predicate + F in a compacted drain), but the unit of work is a CHUNK of 64
+// consecutive candidates of the concatenated runs:
+//   * the lanes that own a run (lane = run) each issue ONE bulk copy for the piece of
+//     their run that falls into the chunk — 32-byte (x, y, z, b) records, contiguous in
+//     the sorted array — into a per-warp double buffer; lane 0 arms the buffer's mbarrier
+//     with the byte count.  Chunk c+1 is in flight while chunk c is tested and drained;
+//   * a lane's two candidates are slots `lane` and `32 + (lane+16)%32` of the buffer: no
+//     run lookup (the binary search of tiled_kernel is gone), no global gather;
+//   * queue entries are (slot << 4 | row): the drain runs at the end of every chunk (and
+//     whenever a lane's queue fills) and reads the candidate records from shared memory
+//     instead of re-gathering them from L2;
+//   * the column index j is reconstructed (a few shuffles per chunk) only for functors
+//     that read it (uses_j), for block columns (BC > 1) and for the pair-set hashes.
+// Periodic-image runs (boundary buckets only) are staged by plain loads into the same
+// buffers, so test and drain code is shared.
+// ---------------------------------------------------------------------------
+template <class F, class = void> struct uses_j { static constexpr bool value = true; };
+template <class F> struct uses_j<F, decltype((void)F::USES_J)> { static constexpr bool value = F::USES_J; };
+
+constexpr int CHUNK = 64;
+#ifndef ABR_STAGED_PCOL
+#define ABR_STAGED_PCOL 16
+#endif
+#ifndef ABR_STAGED_CTAS
+#define ABR_STAGED_CTAS 6
+#endif
+constexpr int SPCOL = ABR_STAGED_PCOL; // columns of the partial-sum table: 16 (two half-warp passes) or 32 (one pass)
+
+template <int D, class F, bool STATS> struct StagedCfg {
+  static constexpr int NACC = STATS ? 2 : F::BR;
+  static constexpr int RB = TiledCfg<D, F, STATS>::RB;
+  static constexpr bool NEEDJ = STATS || uses_j<F>::value || F::BC != 1;
+  static constexpr int CTAS = NACC == 1 ? ABR_STAGED_CTAS : (NACC == 2 ? 5 : 4);
+};
+
+template <int D, class F, bool STATS> struct alignas(128) StagedSmem {
+  static constexpr int NACC = StagedCfg<D, F, STATS>::NACC;
+  static constexpr int RB = StagedCfg<D, F, STATS>::RB;
+  double stage[2][CHUNK][4];               // candidate records (x, y, z, b) of two chunks
+  unsigned long long mbar[2];              // one mbarrier per buffer
+  double rows0[MAXD][RB];
+  double rowsS[MAXD][RB];
+  unsigned long long rowsf2[RB / 2 + 1][4];
+  unsigned long long part[NACC][RB][SPCOL];
+  uint16_t lq[QCAP][32];                   // lane-private queues, slot major: (slot << ROW_BITS) | row
+  uint16_t wq[WQ];                         // compacted for the drain
+  uint32_t sj[CHUNK];                      // column index of each slot (NEEDJ only)
+  uint32_t danger;
+  uint32_t pad_[3];
+};
+
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!done && ++spins > (1 << 22)) __trap(); // a lost copy must fail loudly, never hang the GPU
+  }
+}
+// global -> shared bulk copy, completion reported to an mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+
+struct SDrainCtx {
+  const double *b;   // b column (BC > 1 only)
+  double r2lo;
+  double r2;
+  uint32_t stage;    // shared-window address of the chunk's records
+};
+
+template <int D, class F, bool STATS, class SM>
+__device__ __noinline__ void sdrain(SM &sm, const SDrainCtx p, const F f, int lane, uint32_t cnt, uint32_t r0, const double (*rowp)[SM::RB],
+                                    uint32_t image_id) {
+  constexpr int BR = F::BR, BC = F::BC;
+  constexpr bool NEEDJ = StagedCfg<D, F, STATS>::NEEDJ;
+  uint32_t pin = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pin, o);
+    if (lane >= o) pin += t;
+  }
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, pin, 31);
+  const uint32_t excl = pin - cnt;
+  const uint32_t lq0 = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
+  const uint32_t wq0 = (uint32_t)__cvta_generic_to_shared(&sm.wq[0]);
+  for (uint32_t wbase = 0; wbase < total; wbase += WQ) {
+    {
+      const uint32_t lo = max(excl, wbase), hi = min(pin, wbase + WQ);
+      for (uint32_t k = lo; k < hi; ++k) sts16(wq0 + (k - wbase) * 2u, lds16(lq0 + (k - excl) * 64u));
+    }
+    __syncwarp();
+    const uint32_t wtotal = min(total - wbase, (uint32_t)WQ);
+    for (uint32_t base = 0; base < wtotal; base += 32) {
+      const uint32_t k = base + lane;
+      const bool live = k < wtotal;
+      const uint32_t ent = sm.wq[live ? k : 0u];
+      const uint32_t slot = ent >> ROW_BITS;
+      const uint32_t i = ent & ((1u << ROW_BITS) - 1u);
+      double pj[3], bj[BC];
+      uint32_t j = 0;
+      {
+        double rx, ry, rz, rb;
+        const uint32_t a = p.stage + slot * 32u;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rx), "=d"(ry) : "r"(a));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rz), "=d"(rb) : "r"(a + 16u));
+        pj[0] = rx;
+        pj[1] = ry;
+        pj[2] = rz;
+        if (NEEDJ) j = sm.sj[slot];
+        if (!STATS) {
+          if (BC == 1) {
+            bj[0] = rb;
+          } else {
+#pragma unroll
+            for (int c = 0; c < BC; ++c) bj[c] = p.b[(size_t)j * BC + c];
+          }
+        }
+      }
+      double dx[D];
+      double d2 = 0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        dx[d] = pj[d] - rowp[d][i];
+        d2 = d2 + dx[d] * dx[d];
+      }
+      // the reference's exact predicate (src/Search.h:438-446) on the survivors of the pre-filter
+      const bool ok = live && !(d2 > p.r2);
+      if (ok && d2 > p.r2lo) atomicOr(&sm.danger, 1u << i);
+      if (STATS) {
+        const unsigned long long hv = mix64((uint64_t)j * 81u + (uint64_t)image_id);
+        if (SPCOL == 32) {
+          if (ok) {
+            sm.part[0][i][lane & (SPCOL - 1)] += 1ull;
+            sm.part[1][i][lane & (SPCOL - 1)] += hv;
+          }
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (ok && (lane >> 4) == half) {
+              sm.part[0][i][lane & (SPCOL - 1)] += 1ull;
+              sm.part[1][i][lane & (SPCOL - 1)] += hv;
+            }
+            __syncwarp();
+          }
+        }
+      } else {
+        double blk[BR * BC];
+        f(dx, d2, r0 + i, j, blk);
+        double s[BR];
+#pragma unroll
+        for (int a2 = 0; a2 < BR; ++a2) {
+          s[a2] = blk[a2 * BC] * bj[0];
+#pragma unroll
+          for (int c = 1; c < BC; ++c) s[a2] += blk[a2 * BC + c] * bj[c];
+        }
+        if (SPCOL == 32) {
+          if (ok) {
+#pragma unroll
+            for (int a2 = 0; a2 < BR; ++a2) {
+              double *cell = reinterpret_cast<double *>(&sm.part[a2][i][lane & (SPCOL - 1)]);
+              *cell += s[a2];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (ok && (lane >> 4) == half) {
+#pragma unroll
+              for (int a2 = 0; a2 < BR; ++a2) {
+                double *cell = reinterpret_cast<double *>(&sm.part[a2][i][lane & (SPCOL - 1)]);
+                *cell += s[a2];
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// pre-filter of one chunk: this lane's two candidates (slots sA, sB of the staged buffer)
+// against the nr rows of the batch, two rows per packed instruction — see test_rows
+template <int D, class F, bool STATS, class SM>
+__device__ __forceinline__ void stest_rows(SM &sm, const SDrainCtx &dc, float pre_r2, const F &f, int lane, const float *pA, const float *pB,
+                                           uint32_t sA, uint32_t sB, bool vA, bool vB, int nr, const double (*rowp)[SM::RB], uint32_t image_id,
+                                           uint32_t r0, uint32_t &qa) {
+  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
+  unsigned long long a[D], b[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float av = vA ? pA[d] : -3.0e18f, bv = vB ? pB[d] : -3.0e18f;
+    a[d] = pack2(av, av);
+    b[d] = pack2(bv, bv);
+  }
+  uint32_t eA = sA << ROW_BITS, eB = sB << ROW_BITS;
+  const int npairs = (nr + 1) >> 1;
+  for (int pr = 0; pr < npairs; ++pr) {
+    unsigned long long accA, accB;
+    {
+      const unsigned long long r = sm.rowsf2[pr][0];
+      const unsigned long long ta = sub2(a[0], r), tb = sub2(b[0], r);
+      accA = mul2(ta, ta);
+      accB = mul2(tb, tb);
+    }
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      const unsigned long long r = sm.rowsf2[pr][d];
+      const unsigned long long ta = sub2(a[d], r), tb = sub2(b[d], r);
+      accA = fma2(ta, ta, accA);
+      accB = fma2(tb, tb, accB);
+    }
+    float a0, a1, b0, b1;
+    unpack2(accA, a0, a1);
+    unpack2(accB, b0, b1);
+    if (a0 <= pre_r2) { sts16(qa, eA); qa += 64u; }
+    if (a1 <= pre_r2) { sts16(qa, eA + 1u); qa += 64u; }
+    if (b0 <= pre_r2) { sts16(qa, eB); qa += 64u; }
+    if (b1 <= pre_r2) { sts16(qa, eB + 1u); qa += 64u; }
+    eA += 2u;
+    eB += 2u;
+    if (__any_sync(0xFFFFFFFFu, qa >= q0 + QDRAIN * 64u)) {
+      sdrain<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 6, r0, rowp, image_id);
+      qa = q0;
+    }
+  }
+}
+
+template <int D, class F, bool STATS>
+__global__ void __launch_bounds__(TILED_THREADS, (StagedCfg<D, F, STATS>::CTAS))
+staged_kernel(const abr_matvec_plan p, const F f) {
+  constexpr int BR = F::BR;
+  constexpr int NACC = StagedCfg<D, F, STATS>::NACC;
+  constexpr int RB = StagedCfg<D, F, STATS>::RB;
+  constexpr bool NEEDJ = StagedCfg<D, F, STATS>::NEEDJ;
+  using WS = StagedSmem<D, F, STATS>;
+  extern __shared__ __align__(16) unsigned char smem_raw[]; // no static shared memory in this kernel: the window starts 1024-byte aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WS &sm = reinterpret_cast<WS *>(smem_raw)[warp];
+  const Grid &g = p.q.g;
+  const double *__restrict__ pos = p.q.pos;
+  const uint32_t *__restrict__ bbeg = p.q.bucket_begin;
+  const uint32_t *__restrict__ bend = p.q.bucket_end;
+  constexpr int L = D - 1;
+  constexpr int DS = D > 1 ? D - 1 : 1;
+  int nslow = 1;
+#pragma unroll
+  for (int d = 0; d < D - 1; ++d) nslow *= 2 * p.w[d] + 1;
+  int img0[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) img0[d] = 0;
+  const uint32_t image_id0 = STATS ? (uint32_t)image_linear_index<D>(g, img0) : 0u;
+  uint32_t per_layer = 1;
+#pragma unroll
+  for (int d = 1; d < D; ++d) per_layer *= (uint32_t)g.size[d];
+  const uint32_t first_cell = (D > 1 ? (uint32_t)g.own_lo * per_layer : 0u);
+  const uint32_t own_cells = (D > 1 ? (uint32_t)g.own_n * per_layer : g.ncells);
+  const char *__restrict__ posb = reinterpret_cast<const char *>(p.posb);
+  const float pre_r2 = p.pre_r2;
+  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(&sm.lq[0][lane]);
+  const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(&sm.stage[0][0][0]);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&sm.mbar[0]);
+  const int S = g.size[L];
+  // this lane's two slots of a chunk (the second one half a run away from the first: evens out the queue lengths)
+  const uint32_t sA = (uint32_t)lane, sB = 32u + (uint32_t)((lane + 16) & 31);
+
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t n_issued = 0, n_waited = 0; // chunk k uses buffer k & 1, completes phase (k >> 1) & 1 of its barrier
+  bool generic_dirty = false;          // a buffer was written by plain stores since the last bulk copy
+
+  auto decode_run = [&](int rid, int *od, int &wz) {
+    int rem = rid;
+    double gap2 = 0.0;
+#pragma unroll
+    for (int d = D - 2; d >= 0; --d) {
+      const int span = 2 * p.w[d] + 1;
+      od[d] = (rem % span) - p.w[d];
+      rem /= span;
+      const double gap = (double)max(abs(od[d]) - 1, 0) * g.side[d];
+      gap2 += gap * gap;
+    }
+    wz = p.trim ? reach_last_dim(p.r2, gap2, g.side[L], p.w[L]) : p.w[L];
+  };
+  int od_first[DS], wz_first;
+  od_first[0] = 0;
+  decode_run(lane, od_first, wz_first);
+
+  while (true) {
+    uint32_t grab = 0;
+    if (lane == 0) grab = atomicAdd(p.work_counter, p.grab);
+    grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
+    if (grab >= own_cells) break;
+    const uint32_t grab_end = min(grab + p.grab, own_cells);
+    int tc[D];
+    {
+      const uint32_t cell = first_cell + grab;
+      uint32_t rem = cell;
+#pragma unroll
+      for (int d = D - 1; d >= 0; --d) {
+        tc[d] = (int)(rem % (uint32_t)g.size[d]);
+        rem /= (uint32_t)g.size[d];
+      }
+      if (D > 1) {
+        int gl = g.win_lo + (int)(cell / per_layer);
+        if (gl < 0) gl += g.size[0];
+        if (gl >= g.size[0]) gl -= g.size[0];
+        tc[0] = gl;
+      }
+    }
+    --tc[L];
+
+    for (uint32_t cell = first_cell + grab; cell < first_cell + grab_end; ++cell) {
+      if (++tc[L] == S) {
+        if (D > 1) {
+          tc[L] = 0;
+          if (D > 2) {
+            if (++tc[D > 2 ? 1 : 0] == g.size[D > 2 ? 1 : 0]) {
+              tc[D > 2 ? 1 : 0] = 0;
+              if (++tc[0] >= g.size[0]) tc[0] -= g.size[0];
+            }
+          } else {
+            if (++tc[0] >= g.size[0]) tc[0] -= g.size[0];
+          }
+        }
+      }
+      const uint32_t rb = bbeg[cell], re = bend[cell];
+      if (rb == re) continue;
+      const int zlo = tc[L] - p.w[L], zhi = tc[L] + p.w[L];
+      bool boundary = (zlo < 0) | (zhi >= S);
+#pragma unroll
+      for (int d = 0; d < D - 1; ++d) boundary |= (tc[d] - p.w[d] < 0) | (tc[d] + p.w[d] >= g.size[d]);
+      double origin[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) origin[d] = g.bmin[d] + (double)(tc[d] - p.w[d]) * g.side[d];
+
+      for (uint32_t r0 = rb; r0 < re; r0 += RB) {
+        const int nr = (int)min((uint32_t)RB, re - r0);
+        // ---- phase 1: candidate runs of the primary image, 32 runs per directory batch ----
+        bool rows_ready = false;
+        bool my_danger = false;
+        uint32_t qa = q0;
+        for (int rbase = 0; rbase < nslow; rbase += 32) {
+          uint32_t len = 0, jb = 0;
+          const int rid = rbase + lane;
+          if (rid < nslow) {
+            int od[DS], wz;
+            if (rbase == 0) {
+#pragma unroll
+              for (int d = 0; d < DS; ++d) od[d] = od_first[d];
+              wz = wz_first;
+            } else {
+              decode_run(rid, od, wz);
+            }
+            int nc[D];
+            bool ok = true;
+#pragma unroll
+            for (int d = 0; d < D - 1; ++d) {
+              const int u = tc[d] + od[d];
+              ok &= (u >= 0) & (u < g.size[d]);
+              nc[d] = u;
+            }
+            const int a = max(tc[L] - wz, 0), bnd = min(tc[L] + wz, S - 1);
+            if (ok && wz >= 0 && a <= bnd) {
+              nc[L] = a;
+              const int c_lo = local_collapse<D>(g, nc);
+              if (c_lo >= 0) {
+                jb = bbeg[c_lo];
+                len = bend[c_lo + (bnd - a)] - jb;
+              }
+            }
+          }
+          uint32_t pin = len;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pin, o);
+            if (lane >= o) pin += t;
+          }
+          const uint32_t total = __shfl_sync(0xFFFFFFFFu, pin, 31);
+          const uint32_t excl = pin - len;              // this lane's run = candidates excl .. pin-1 of the batch
+          const uint32_t jdelta = jb - excl;            // j = k + jdelta inside the run
+          const uint32_t nchunks = (total + CHUNK - 1) / CHUNK;
+
+          // chunk c of this batch -> buffer n_issued & 1
+          auto issue = [&](uint32_t c) {
+            __syncwarp(); // every lane is done with the buffer's previous contents
+            const uint32_t buf = n_issued & 1u;
+            const uint32_t k0 = c * CHUNK;
+            const uint32_t lo = max(excl, k0), hi = min(pin, k0 + CHUNK);
+            if (generic_dirty) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              generic_dirty = false;
+            }
+            if (lane == 0) mbar_arrive_expect_tx(bar0 + buf * 8u, min((uint32_t)CHUNK, total - k0) * 32u);
+            if (lo < hi) bulk_g2s(stage0 + buf * (CHUNK * 32u) + (lo - k0) * 32u, posb + (size_t)(lo + jdelta) * 32u, (hi - lo) * 32u, bar0 + buf * 8u);
+            ++n_issued;
+          };
+          if (nchunks > 0) issue(0);
+
+          if (!rows_ready) {
+            // ---- rows of this batch (while the first chunk is in flight) ----
+            rows_ready = true;
+            if (lane < nr) {
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                const double r = pos[(size_t)(r0 + lane) * D + d];
+                sm.rows0[d][lane] = r;
+                const double fl = (r - g.bmin[d]) * g.inv_side[d];
+                const double fr = fl - floor(fl);
+                my_danger |= ((int)floor(fl) != tc[d]) | (fr < p.tolf[d]) | (fr > 1.0 - p.tolf[d]) | (fabs(fr - 0.5) < p.tolf[d]);
+              }
+            }
+            if (lane == 0) sm.danger = 0;
+            __syncwarp();
+            if (lane < RB + 2) {
+              float *rf = reinterpret_cast<float *>(&sm.rowsf2[0][0]);
+#pragma unroll
+              for (int d = 0; d < D; ++d)
+                rf[(((lane >> 1) * 4) + d) * 2 + (lane & 1)] = lane < nr ? (float)(sm.rows0[d][lane] - origin[d]) : 3.0e18f;
+            }
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+              for (int e = lane; e < nr * SPCOL; e += 32) (&sm.part[a][0][0])[e] = 0ull;
+            __syncwarp();
+          }
+
+          for (uint32_t c = 0; c < nchunks; ++c) {
+            if (c + 1 < nchunks) issue(c + 1);
+            const uint32_t buf = n_waited & 1u;
+            mbar_wait(bar0 + buf * 8u, (n_waited >> 1) & 1u);
+            ++n_waited;
+            const uint32_t k0 = c * CHUNK;
+            const uint32_t nvalid = min((uint32_t)CHUNK, total - k0);
+            const uint32_t stg = stage0 + buf * (CHUNK * 32u);
+            if (NEEDJ) {
+              // column index of each slot: pieces of the runs that intersect this chunk
+              const uint32_t lo = max(excl, k0), hi = min(pin, k0 + CHUNK);
+              uint32_t pm = __ballot_sync(0xFFFFFFFFu, lo < hi);
+              uint32_t dA = 0, dB = 0;
+              while (pm) {
+                const int r = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t plo = __shfl_sync(0xFFFFFFFFu, lo, r) - k0;
+                const uint32_t pd = __shfl_sync(0xFFFFFFFFu, jdelta, r) + k0;
+                if (sA >= plo) dA = pd;
+                if (sB >= plo) dB = pd;
+              }
+              sm.sj[sA] = sA + dA;
+              sm.sj[sB] = sB + dB;
+              __syncwarp();
+            }
+            float pj[2][D];
+            const bool vA = sA < nvalid, vB = sB < nvalid;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t a = stg + (h ? sB : sA) * 32u;
+              double rx, ry, rz = 0.0;
+              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rx), "=d"(ry) : "r"(a));
+              if (D > 2) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rz) : "r"(a + 16u));
+              const double rec[3] = {rx, ry, rz};
+#pragma unroll
+              for (int d = 0; d < D; ++d) pj[h][d] = (float)(rec[d] - origin[d]);
+            }
+            const SDrainCtx dc{p.b, p.r2lo, p.r2, stg};
+            stest_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], sA, sB, vA, vB, nr, sm.rows0, image_id0, r0, qa);
+            // the records of this chunk leave the buffer with the next bulk copy: drain now
+            if (__any_sync(0xFFFFFFFFu, qa != q0)) {
+              sdrain<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 6, r0, sm.rows0, image_id0);
+              qa = q0;
+            }
+          }
+        }
+        if (boundary) {
+          // ---- phase 2 (buckets at a periodic boundary only): runs reached through a periodic
+          //      image, cur = r + image * L exactly as src/Search.h:188-190; staged by plain loads ----
+          int o[DS];
+#pragma unroll
+          for (int d = 0; d < D - 1; ++d) o[d] = -p.w[d];
+          bool more = true;
+          while (more) {
+            int nc[D], img[D];
+            bool ok_slow = true, slow_shifted = false;
+            double gap2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < D - 1; ++d) {
+              const double gap = (double)max(abs(o[d]) - 1, 0) * g.side[d];
+              gap2 += gap * gap;
+              int u = tc[d] + o[d];
+              img[d] = 0;
+              if (u < 0) {
+                u += g.size[d];
+                img[d] = 1;
+              } else if (u >= g.size[d]) {
+                u -= g.size[d];
+                img[d] = -1;
+              }
+              ok_slow &= (u >= 0) & (u < g.size[d]) & (img[d] == 0 || g.periodic[d]);
+              slow_shifted |= (img[d] != 0);
+              nc[d] = u;
+            }
+            const int wz = p.trim ? reach_last_dim(p.r2, gap2, g.side[L], p.w[L]) : p.w[L];
+            if (ok_slow && wz >= 0) {
+              for (int m = (g.periodic[L] ? -1 : 0); m <= (g.periodic[L] ? 1 : 0); ++m) {
+                if (m == 0 && !slow_shifted) continue;
+                const int a = max(tc[L] - wz, m * S), bnd = min(tc[L] + wz, m * S + S - 1);
+                if (a > bnd) continue;
+                img[L] = -m;
+                nc[L] = a - m * S;
+                const int c_lo = local_collapse<D>(g, nc);
+                if (c_lo < 0) continue;
+                const uint32_t jb = bbeg[c_lo], je = bend[c_lo + (bnd - a)];
+                if (jb >= je) continue;
+                __syncwarp();
+                if (lane < nr) {
+#pragma unroll
+                  for (int d = 0; d < D; ++d) sm.rowsS[d][lane] = sm.rows0[d][lane] + (double)img[d] * g.L[d];
+                }
+                __syncwarp();
+                const uint32_t image_id = STATS ? (uint32_t)image_linear_index<D>(g, img) : 0u;
+                const SDrainCtx dc{p.b, p.r2lo, p.r2, stage0};
+                generic_dirty = true;
+                for (uint32_t cb = jb; cb < je; cb += CHUNK) {
+                  float pj[2][D];
+                  const uint32_t nvalid = min((uint32_t)CHUNK, je - cb);
+                  const bool vA = sA < nvalid, vB = sB < nvalid;
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const uint32_t sl = h ? sB : sA;
+                    const uint32_t jx = min(cb + sl, je - 1);
+                    double rec[4];
+                    ld_rec(p.posb, jx, rec[0], rec[1], rec[2], rec[3]);
+                    const uint32_t a = stage0 + sl * 32u;
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(rec[0]), "d"(rec[1]) : "memory");
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16u), "d"(rec[2]), "d"(rec[3]) : "memory");
+                    if (NEEDJ) sm.sj[sl] = jx;
+                    // pre-filter only: move the candidate by -image*L instead of the row by +image*L
+#pragma unroll
+                    for (int d = 0; d < D; ++d) pj[h][d] = (float)((rec[d] - (double)img[d] * g.L[d]) - origin[d]);
+                  }
+                  __syncwarp();
+                  stest_rows<D, F, STATS>(sm, dc, pre_r2, f, lane, pj[0], pj[1], sA, sB, vA, vB, nr, sm.rowsS, image_id, r0, qa);
+                  if (__any_sync(0xFFFFFFFFu, qa != q0)) {
+                    sdrain<D, F, STATS>(sm, dc, f, lane, (qa - q0) >> 6, r0, sm.rowsS, image_id);
+                    qa = q0;
+                  }
+                  __syncwarp();
+                }
+              }
+            }
             more = false;
 #pragma unroll
             for (int d = D - 2; d >= 0; --d) {
@@ -861,9 +1605,9 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
           } else if (STATS) {
             unsigned long long c = 0, hsum = 0;
 #pragma unroll
-            for (int k = 0; k < PCOL; ++k) {
-              c += sm.part[0][lane][(k + lane) & (PCOL - 1)];
-              hsum += sm.part[1][lane][(k + lane) & (PCOL - 1)];
+            for (int k = 0; k < SPCOL; ++k) {
+              c += sm.part[0][lane][(k + lane) & (SPCOL - 1)];
+              hsum += sm.part[1][lane][(k + lane) & (SPCOL - 1)];
             }
             if (p.stat_count) p.stat_count[r0 + lane] = (uint32_t)c;
             if (p.stat_hash) p.stat_hash[r0 + lane] = hsum;
@@ -872,7 +1616,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
             for (int a2 = 0; a2 < NACC; ++a2) {
               double s = 0;
 #pragma unroll
-              for (int k = 0; k < PCOL; ++k) s += *reinterpret_cast<double *>(&sm.part[a2][lane][(k + lane) & (PCOL - 1)]);
+              for (int k = 0; k < SPCOL; ++k) s += *reinterpret_cast<double *>(&sm.part[a2][lane][(k + lane) & (SPCOL - 1)]);
               p.y[(size_t)(r0 + lane) * BR + a2] += s;
             }
           }
@@ -887,11 +1631,34 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
 // launcher, instantiated per (D, Functor) — in libabr.so for the built-in
 // functors, in the user's nvcc-compiled TU for custom ones.
 // ---------------------------------------------------------------------------
+// symmetric kernel, second step: y += ytmp for the owned rows that keep their tiled result
+// (flagged rows are recomputed from y by the exact walk that follows)
+__global__ void __launch_bounds__(256) k_sym_combine(const abr_matvec_plan p, int BR) {
+  const Grid &g = p.q.g;
+  uint32_t per_layer = 1;
+  for (int d = 1; d < g.D; ++d) per_layer *= (uint32_t)g.size[d];
+  const uint32_t first_cell = g.D > 1 ? (uint32_t)g.own_lo * per_layer : 0u;
+  const uint32_t own_cells = g.D > 1 ? (uint32_t)g.own_n * per_layer : g.ncells;
+  if (own_cells == 0) return;
+  const uint32_t p0 = p.q.bucket_begin[first_cell], p1 = p.q.bucket_end[first_cell + own_cells - 1];
+  const uint64_t total = (uint64_t)(p1 - p0) * BR;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t i = p0 + (uint32_t)(e / BR);
+    if (!((p.row_bits[i >> 5] >> (i & 31u)) & 1u)) {
+      const uint64_t idx = (uint64_t)p0 * BR + e;
+      p.y[idx] += p.ytmp[idx];
+    }
+  }
+}
+
 template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_plan &p, const F &f) {
   cudaError_t e;
   if (p.use_tiled) {
-    const size_t smem = sizeof(WarpSmem<D, F, STATS>) * TILED_WARPS;
-    auto kern = tiled_kernel<D, F, STATS>;
+    constexpr int SYMV = STATS ? 0 : symmetry<F>::value;
+    const bool sym = SYMV != 0 && p.symmetric && p.ytmp && p.row_bits;
+    const bool staged = p.variant == 1 && !sym;
+    const size_t smem = (staged ? sizeof(StagedSmem<D, F, STATS>) : sizeof(WarpSmem<D, F, STATS>)) * TILED_WARPS;
+    void (*kern)(const abr_matvec_plan, const F) = staged ? staged_kernel<D, F, STATS> : (sym ? tiled_kernel<D, F, STATS, SYMV> : tiled_kernel<D, F, STATS, 0>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
@@ -900,7 +1667,7 @@ template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_pl
     if (per_sm < 1) per_sm = 1;
     {
       // ask for no more shared memory than the resident CTAs need: what is left of the
-      // 256 KB array serves as L1 for the drain's gathers
+      // 256 KB array serves as L1
       int pct = (int)((100.0 * per_sm * (smem + 1024)) / (228.0 * 1024.0)) + 1;
       if (pct > 100) pct = 100;
       cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -910,6 +1677,7 @@ template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_pl
     if (grid > max_chunks) grid = max_chunks;
     if (grid < 1) grid = 1;
     kern<<<grid, TILED_THREADS, smem, p.stream>>>(p, f);
+    if (sym) k_sym_combine<<<p.sm_count * 8, 256, 0, p.stream>>>(p, F::BR);
     // rows handed over by the tiled kernel: exact per-row walk
     abr_matvec_plan p2 = p;
     p2.walk_only_list = 1;

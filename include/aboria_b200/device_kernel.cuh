@@ -86,6 +86,8 @@ struct ConstSumDiff {
 };
 // 1/(|dx| + eps)
 struct InvDist {
+  static constexpr int SYMMETRY = +1; // block(-dx, b, a) == +block(dx, a, b): eligible for the symmetric product
+  static constexpr bool USES_J = false; // the column index is not read: the staged kernel skips its reconstruction
   static constexpr int TILED_CTAS = 8;
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
@@ -97,6 +99,8 @@ struct InvDist {
 // the same for eps in [1e-100, 1e100] (|dx| + eps is then a normal number far from
 // overflow): branch-free sqrt and reciprocal
 struct InvDistFast {
+  static constexpr int SYMMETRY = +1; // block(-dx, b, a) == +block(dx, a, b): eligible for the symmetric product
+  static constexpr bool USES_J = false; // the column index is not read: the staged kernel skips its reconstruction
   static constexpr int TILED_CTAS = 8;
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
@@ -123,6 +127,8 @@ struct InvDistAA {
 //
 // tests/rbf_interpolation.h:310-313: pow(2 - r/h, 4) * (1 + 2 r/h)
 struct WendlandC2 {
+  static constexpr int SYMMETRY = +1; // block(-dx, b, a) == +block(dx, a, b): eligible for the symmetric product
+  static constexpr bool USES_J = false; // the column index is not read: the staged kernel skips its reconstruction
   static constexpr int TILED_CTAS = 8;
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
@@ -138,6 +144,8 @@ struct WendlandC2 {
 // SURVEY §8d c3 (tests/md.h:166-174 pattern): Lennard-Jones force, D x 1 block:
 // 24 eps (2 (s/r)^12 - (s/r)^6) / r^2 * dx needs 1/r^2 only — no square root
 template <int D> struct LJForce {
+  static constexpr int SYMMETRY = -1; // block(-dx, b, a) == -block(dx, a, b): eligible for the symmetric product
+  static constexpr bool USES_J = false; // the column index is not read: the staged kernel skips its reconstruction
   static constexpr int BR = D, BC = 1;
   double sigma2, eps24;
   static LJForce make(double sigma, double eps) { return LJForce{sigma * sigma, 24.0 * eps}; }
@@ -161,6 +169,8 @@ template <int D> struct LJForce {
 // tests/md.h:166-174: linear spring between overlapping discs/spheres, D x 1 block:
 // -k (diameter / r - 1) dx for r != 0
 template <int D> struct LinearSpring {
+  static constexpr int SYMMETRY = -1; // block(-dx, b, a) == -block(dx, a, b): eligible for the symmetric product
+  static constexpr bool USES_J = false; // the column index is not read: the staged kernel skips its reconstruction
   static constexpr int BR = D, BC = 1;
   double k, diameter;
   static LinearSpring make(double k, double diameter) { return LinearSpring{k, diameter}; }
@@ -174,6 +184,8 @@ template <int D> struct LinearSpring {
 };
 // tests/sph.h:154-165 W_fun (Wendland), times the particle mass
 template <int D> struct SphDensity {
+  static constexpr int SYMMETRY = +1; // block(-dx, b, a) == +block(dx, a, b): eligible for the symmetric product
+  static constexpr bool USES_J = false; // the column index is not read: the staged kernel skips its reconstruction
   static constexpr bool NEEDS_DX = false;
   static constexpr int BR = 1, BC = 1;
   double inv_h, pref; // pref = (1 / h^D) * wcon * mass

@@ -83,9 +83,14 @@ int abr_synchronize(abr_handle h);
  * a particle died or a bucket index overflowed (then the update must be redone
  * with n_alive_host != NULL). */
 int abr_check_async(abr_handle h);
-/* Tuning knobs (no effect on results): "two_level_min_n" — particle count from which
- * abr_update_positions uses the two-level (partition + bin-local sort) build;
- * "phased_gather" — 0/1. */
+/* Tuning knobs: "two_level_min_n" — particle count from which abr_update_positions uses
+ * the two-level (partition + bin-local sort) build; "phased_gather" — 0/1;
+ * "matvec_variant" — 0: cell-tiled kernel gathering candidates from L2, 1: candidates
+ * staged in shared memory with cp.async.bulk; "symmetric" — 1: products with rows ==
+ * columns whose functor declares SYMMETRY evaluate every unordered pair once (half
+ * stencil, src/Search.h:498-764) and add it to both rows with fp64 reductions; results
+ * then differ from the ordered kernel by summation order only (<= 1e-12 relative) and
+ * are no longer bit-reproducible from run to run.  None of them changes a pair set. */
 int abr_set_option(abr_handle h, const char *name, double value);
 const char *abr_last_error_string(abr_handle h);
 const char *abr_version(void);

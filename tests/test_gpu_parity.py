@@ -19,8 +19,8 @@ TOL = 1e-12
     (1, 14, 1, False), (1, 14, 1, True), (1, 1000, 10, True), (1, 1000, 100, False),
     (2, 1000, 10, True), (2, 1000, 10, False), (2, 1000, 1, True),
     (3, 1, 10, True), (3, 3, 10, False), (3, 1000, 100, True), (3, 1000, 10, False), (3, 1000, 1, True),
-    (3, 5000, 10, True), (3, 100000, 10, True), (2, 100000, 10, False)])
-@pytest.mark.parametrize("two_level", [False, True])
+    (3, 5000, 10, True), (3, 100000, 10, True), (2, 100000, 10, False), (3, 300000, 3, True), (3, 200000, 10, [True, False, True])])
+@pytest.mark.parametrize("two_level", [False, True, "counting"])
 def test_build_parity(D, N, nn, periodic, two_level):
     # both build strategies: LSD sort + random gather, and the two-level build
     # (records partitioned by the top key digit, bin-local passes, L2-local gather)
@@ -46,6 +46,26 @@ def test_build_dead_wrap_and_columns():
     assert_build_equal(o, out, p)
     assert 0 < out["n_alive"] < N
     # now with user columns: every column is gathered by the same order (two-level build)
+    # ... and with the counting-sort build (8-byte-word columns only: it must fall back for the others)
+    for strategy, vs in (("counting", {"a": torch.float64, "v": (torch.float64, (3,)), "rng": (torch.float64, (8,))}), ("counting", vars_)):
+        p3 = ab.Particles(3, N, variables=vs)
+        p3.set_option("counting_min_n", 0)
+        p3.set("position", torch.from_numpy(pos0.copy()))
+        p3.set("alive", torch.from_numpy(alive.copy()))
+        cols3 = {k: (rng.random((N,) + tuple(v[1])) if isinstance(v, tuple) and v[0] == torch.float64 else rng.random(N)) for k, v in vs.items() if (v[0] if isinstance(v, tuple) else v) == torch.float64}
+        for k, v in cols3.items():
+            p3.set(k, torch.from_numpy(v))
+        p3.init_neighbour_search(0.0, 1.0, periodic, 10.0)
+        assert p3.size() == out["n_alive"]
+        assert np.array_equal(p3.get_alive_indicies().cpu().numpy(), out["order"])
+        assert np.array_equal(p3.get("position").cpu().numpy().view(np.uint64), out["pos"].view(np.uint64))
+        assert np.array_equal(p3.get("id").cpu().numpy(), out["order"].astype(np.int64))
+        assert bool((p3.get("alive") == 1).all())
+        for k, v in cols3.items():
+            assert np.array_equal(p3.get(k).cpu().numpy(), v[out["order"]]), k
+        q3 = p3.get_query()
+        assert np.array_equal(q3.bucket_begin.cpu().numpy().view(np.uint32), out["bucket_begin"])
+        assert np.array_equal(q3.bucket_end.cpu().numpy().view(np.uint32), out["bucket_end"])
     p2 = ab.Particles(3, N, variables=vars_)
     p2.set_option("two_level_min_n", 0)
     p2.set("position", torch.from_numpy(pos0.copy()))
@@ -247,7 +267,7 @@ def test_matvec_rows_not_cols_and_row_radius():
     assert np.array_equal(hs.cpu().numpy().view(np.uint64), hs_o)
 
 
-@pytest.mark.parametrize("two_level", [False, True])
+@pytest.mark.parametrize("two_level", [False, True, "counting"])
 def test_clustered_cloud(two_level):
     # c4-style clustered cloud at reduced N: heavy buckets (very uneven first-level bins), periodic (1,1,0)
     N = 200000

@@ -16,7 +16,9 @@ def build_both(pos, low, high, periodic, n_leaf=10.0, alive=None, variables=None
     out = o.init_neighbour_search(pos, low, high, periodic, n_leaf, alive=al, sort_mode=orc.SORT_STABLE)
     p = ab.Particles(D, n, variables=variables)
     if two_level is not None:
-        p.set_option("two_level_min_n", 0 if two_level else 1e18)
+        # build strategy: False = LSD radix sort + gather, True = two-level radix build, "counting" = counting-sort build
+        p.set_option("two_level_min_n", 0 if two_level is True else 1e18)
+        p.set_option("counting_min_n", 0 if two_level == "counting" else 1e18)
     p.set("position", torch.from_numpy(pos.copy()))
     if alive is not None:
         p.set("alive", torch.from_numpy(np.ascontiguousarray(alive, dtype=np.uint8)))
