@@ -1,7 +1,9 @@
 // Host planner + built-in functor dispatch of the sparse kernel product.
 // Kernels live in include/aboria_b200/detail/matvec_kernels.cuh.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <string>
 
 #include "abr_internal.h"
 #include "aboria_b200/device_kernel.cuh"
@@ -273,6 +275,15 @@ int run_coeff(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, const ui
 
 int scan_exclusive_u32(Handle *h, uint32_t *data, uint64_t m); // abr_build.cu
 
+__global__ void k_zero_u64(unsigned long long *p) { *p = 0ull; }
+__global__ void __launch_bounds__(256) k_sum_u32_64(const uint32_t *__restrict__ v, uint64_t n, unsigned long long *__restrict__ out) {
+  unsigned long long acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint32_t *row_ptr, int32_t *col_idx, double *values,
                  size_t capacity, uint64_t *nnz_host) {
   if (!k || !row_ptr) return set_error(h, ABR_ERR_INVALID, "assemble: null pointer");
@@ -288,7 +299,18 @@ int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint3
     s.y = nullptr;
     int rc = run_pair_stats(h, s);
     if (rc) return rc;
-    // guard against 32-bit overflow of the running sum: total in 64 bits on the host side
+    // the row pointers are 32 bit: a total of 2^32 entries or more would wrap silently in the scan, so the
+    // counts are summed in 64 bits first
+    {
+      unsigned long long *tot = reinterpret_cast<unsigned long long *>(&h->d_scalars->pair_count);
+      k_zero_u64<<<1, 1, 0, h->stream>>>(tot);
+      k_sum_u32_64<<<(unsigned)std::min<uint64_t>((c.n_rows + 255) / 256, (uint64_t)h->sm_count * 8), 256, 0, h->stream>>>(row_ptr, c.n_rows, tot);
+      unsigned long long t64 = 0;
+      ABR_CUDA(h, cudaMemcpyAsync(&t64, tot, sizeof(t64), cudaMemcpyDeviceToHost, h->stream));
+      ABR_CUDA(h, cudaStreamSynchronize(h->stream));
+      h->launches += 2;
+      if (t64 >= 0xFFFFFFFFull) return set_error(h, ABR_ERR_UNSUPPORTED, "assemble: " + std::to_string(t64) + " entries do not fit 32-bit row pointers");
+    }
     rc = scan_exclusive_u32(h, row_ptr, c.n_rows + 1);
     if (rc) return rc;
     uint32_t last = 0;

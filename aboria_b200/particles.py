@@ -129,6 +129,11 @@ class Particles:
         if name != "position" and name in self.columns and t.shape[0] != self.size():
             raise ValueError("column length mismatch")
         self.columns[name] = t.contiguous()
+        if name == "position":
+            # the handle's query points at the tensor the last build reordered into: replacing the column
+            # leaves it without a search structure until the next update_positions (the reference would
+            # search a stale list; a raw pointer into freed device memory must not be searched at all)
+            self.searchable = False
 
     def resize_from_positions(self, pos):
         """Replace the whole set by n new particles at `pos` (host or device)."""
@@ -147,6 +152,7 @@ class Particles:
                 if name not in ("position", "id", "alive"):
                     self.columns[name].zero_()
             return
+        self.searchable = False
         self.columns["position"] = pos.to(self.device, non_blocking=True).contiguous().clone() if pos.device == self.device else pos.to(self.device, non_blocking=True).contiguous()
         self.columns["id"] = torch.arange(n, dtype=torch.int64, device=self.device)
         self.columns["alive"] = torch.ones(n, dtype=torch.uint8, device=self.device)
@@ -226,6 +232,7 @@ class Particles:
         self._order = order[:na]
         self._other = dict(zip(names, src))
         self.columns = {k: t[:na] for k, t in zip(names, dst)}
+        self._bound_position = self.columns["position"]  # keeps the tensor behind the handle's query alive until the next build
         self.n_buckets = self.grid()[2]
         if self._id_map:
             self._update_id_map()
@@ -273,15 +280,17 @@ class Particles:
     def get_query(self):
         return Query(self)
 
-    def _bucket_view(self, clone=True):
+    def _bucket_view(self, clone=True, sync=True):
         """(bucket_indices, bucket_begin, bucket_end) as int32 device tensors;
-        clone=False returns views borrowed from the handle (valid until the next build)"""
+        clone=False returns views borrowed from the handle (valid until the next build);
+        sync=False skips the stream synchronisation (stream-ordered consumers only)"""
         ki, bb, be = C.c_void_p(), C.c_void_p(), C.c_void_p()
         nb = C.c_uint64()
         check(self._h, self._lib.abr_celllist_get(self._h, C.byref(ki), C.byref(bb), C.byref(be), C.byref(nb)))
         n = self.size()
 
-        check(self._h, self._lib.abr_synchronize(self._h))
+        if sync:
+            check(self._h, self._lib.abr_synchronize(self._h))
 
         def view(ptr, count):
             if count == 0 or not ptr.value:

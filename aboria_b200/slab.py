@@ -36,6 +36,27 @@ def plan_layers(n_layers, world):
     return out
 
 
+def plan_layers_balanced(layer_counts, world):
+    """contiguous split of the bucket layers of dimension 0 by PARTICLE COUNT (prefix over
+    the per-layer histogram): rank g ends at the layer where the running count is nearest to
+    (g + 1) / world of the total; every rank keeps at least one layer"""
+    c = np.asarray(layer_counts, dtype=np.float64)
+    n_layers = len(c)
+    if n_layers < world:
+        raise ValueError("fewer bucket layers than ranks: replicas only (SURVEY §8e)")
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    total = cum[-1]
+    cuts = [0]
+    for g in range(1, world):
+        target = total * g / world
+        k = int(np.argmin(np.abs(cum - target)))
+        k = max(k, cuts[-1] + 1)
+        k = min(k, n_layers - (world - g))
+        cuts.append(k)
+    cuts.append(n_layers)
+    return [(cuts[g], cuts[g + 1]) for g in range(world)]
+
+
 def halo_width(radius, side0):
     """bucket layers a row can reach: ceil(r / side) with the same rounding
     guard as the tiled kernel (aboria_b200/csrc/abr_matvec.cu)"""
@@ -136,6 +157,43 @@ class SlabExchange:
         return (self.n_ghost_lo + self.n_ghost_hi) * row_bytes
 
 
+class _LocalLayout:
+    """where the owned and ghost ranges of a rank's local (ghost-padded) arrays are, and the halo
+    refresh of a per-particle vector (b before every product): contiguous slices, neighbours only"""
+
+    def __init__(self, rank, world, lower, upper, n_lo, n_own, n_hi, n_send_lo, n_send_hi, group):
+        self.rank, self.world, self.lower, self.upper, self.group = rank, world, lower, upper, group
+        self.n_ghost_lo, self.n_own, self.n_ghost_hi = n_lo, n_own, n_hi
+        self.own_begin, self.own_end = n_lo, n_lo + n_own
+        self.n_local = n_lo + n_own + n_hi
+        self.send_lo = (0, n_send_lo)
+        self.send_hi = (n_own - n_send_hi, n_own)
+
+    def fill_halo(self, local):
+        ob = self.own_begin
+        ops = []
+        if self.lower is not None and self.send_lo[1] > self.send_lo[0]:
+            ops.append(dist.P2POp(dist.isend, local[ob + self.send_lo[0]: ob + self.send_lo[1]], self.lower, self.group))
+        if self.upper is not None and self.send_hi[1] > self.send_hi[0]:
+            ops.append(dist.P2POp(dist.isend, local[ob + self.send_hi[0]: ob + self.send_hi[1]], self.upper, self.group))
+        if self.upper is not None and self.n_ghost_hi > 0:
+            ops.append(dist.P2POp(dist.irecv, local[self.own_end:], self.upper, self.group))
+        if self.lower is not None and self.n_ghost_lo > 0:
+            ops.append(dist.P2POp(dist.irecv, local[: self.n_ghost_lo], self.lower, self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return local
+
+    def assemble(self, owned_sorted):
+        out = torch.empty((self.n_local,) + tuple(owned_sorted.shape[1:]), dtype=owned_sorted.dtype, device=owned_sorted.device)
+        out[self.own_begin:self.own_end].copy_(owned_sorted)
+        return self.fill_halo(out)
+
+    def halo_bytes(self, row_bytes):
+        return (self.n_ghost_lo + self.n_ghost_hi) * row_bytes
+
+
 class SlabParticles:
     """One rank's share of a slab-decomposed particle set on its GPU."""
 
@@ -179,59 +237,231 @@ class SlabParticles:
         check(p._h, p._lib.abr_domain_force_grid(p._h, self.D, self.low.ctypes.data, self.high.ctypes.data, self.periodic.ctypes.data, self.size.ctypes.data))
         check(p._h, p._lib.abr_domain_set_window(p._h, win_lo, win_n, own_lo, own_n))
 
-    def build(self, pos_owned_unsorted, extra_columns=None):
-        """owned build (window = owned layers) -> halo exchange of the sorted
-        columns -> adopt the sorted local set (window = owned + 2w ghost layers)."""
+    def set_layers(self, layers):
+        """use another contiguous layer split (plan_layers_balanced) — same on every rank"""
+        self.layers = [tuple(map(int, x)) for x in layers]
+        self.lo_layer, self.hi_layer = self.layers[self.rank]
+        self.own_n = self.hi_layer - self.lo_layer
+        if self.own_n < self.w:
+            raise ValueError(f"rank {self.rank}: owns {self.own_n} bucket layers, fewer than the halo width {self.w}: replicas only (SURVEY §8e)")
+        if bool(self.periodic[0]) and self.own_n + 2 * self.w > int(self.size[0]):
+            raise ValueError("slab window would wrap onto itself: replicas only (SURVEY §8e)")
+        self._big = None
+
+    def layer_histogram(self, pos):
+        """global particle count per bucket layer of dimension 0 (one small all-reduce; set-up time only)"""
+        S0 = int(self.size[0])
+        x = pos[:, 0]
+        L = float(self.high[0] - self.low[0])
+        if bool(self.periodic[0]):
+            x = x - torch.floor((x - float(self.low[0])) / L) * L
+        layer = torch.floor((x - float(self.low[0])) * (1.0 / float(self.side[0]))).long().clamp_(0, S0 - 1)
+        h = torch.bincount(layer, minlength=S0).to(torch.float64)
+        dist.all_reduce(h, group=self.group)
+        return h.cpu().numpy()
+
+    def _neighbours(self):
+        per0 = bool(self.periodic[0])
+        lower = (self.rank - 1) % self.world if (per0 or self.rank > 0) else None
+        upper = (self.rank + 1) % self.world if (per0 or self.rank < self.world - 1) else None
+        return lower, upper
+
+    def build(self, pos_owned_unsorted, extra_columns=None, assume_all_alive=True):
+        """One build of this rank's share, ONE host synchronisation, ONE data exchange:
+          1. ordinary build of the owned particles in the ghost-padded window (own layers in the
+             middle; the reorder writes straight into the middle of ghost-padded column buffers);
+          2. the particle counts of my first / last w layers travel to the neighbours as device
+             tensors; the four counts (sent, received) come back to the host in one read;
+          3. one batch of P2P operations: the halo slices of every sorted column (contiguous: a
+             layer is a contiguous range of the sorted array) and of m_bucket_begin / m_bucket_end;
+          4. abr_celllist_patch_ghosts: ghost bucket ranges from the senders' ranges, owned ranges
+             shifted — no pass over the particles."""
         from ._lib import check
 
         p = self.p
-        p.resize_from_positions(pos_owned_unsorted)
-        for k, v in (extra_columns or {}).items():
-            p.columns[k] = v
-        p.low, p.high, p.periodic = self.low, self.high, self.periodic
-        # The owned build reorders every column straight into the middle of a buffer with room
-        # for the ghost ranges on both sides: no copy of the owned range when the local
-        # [ghost_lo | owned | ghost_hi] arrays are put together after the exchange.
+        dev = self.device
+        lower, upper = self._neighbours()
+        has_lo, has_hi = lower is not None, upper is not None
+        w, per_layer = self.w, self.per_layer
+        own_lo = w if has_lo else 0
+        win_lo = self.lo_layer - own_lo
+        win_n = self.own_n + own_lo + (w if has_hi else 0)
+        # the container's input columns: persistent buffers refilled in place (no allocation, no arange on the
+        # hot path); the caller's tensors stay untouched (the build wraps positions in place)
         n_in = pos_owned_unsorted.shape[0]
-        cap = n_in // 4 + 1024
+        extra = extra_columns or {}
+        stage = getattr(self, "_stage", None)
+        if stage is None or stage["position"].shape[0] != n_in or set(stage) != {"position", "id", "alive", *extra} or any(
+                stage[k].dtype != v.dtype or stage[k].shape[1:] != v.shape[1:] for k, v in extra.items()):
+            stage = {"position": torch.empty((n_in, self.D), dtype=torch.float64, device=dev), "id": torch.empty(n_in, dtype=torch.int64, device=dev),
+                     "alive": torch.empty(n_in, dtype=torch.uint8, device=dev)}
+            for k, v in extra.items():
+                stage[k] = torch.empty_like(v)
+            self._stage = stage
+            self._iota = torch.arange(n_in, dtype=torch.int64, device=dev)
+        stage["position"].copy_(torch.as_tensor(pos_owned_unsorted), non_blocking=True)
+        stage["id"].copy_(self._iota)
+        stage["alive"].fill_(1)
+        for k, v in extra.items():
+            stage[k].copy_(v)
+        p.columns = dict(stage)
+        p.low, p.high, p.periodic = self.low, self.high, self.periodic
+        cap = max(getattr(self, "_cap", 0), n_in // 8 + 4096)
         big = getattr(self, "_big", None)
-        if big is None or self._big_n != n_in or set(big) != set(p.columns) or any(
+        if big is None or self._big_n != n_in or self._cap != cap or set(big) != set(p.columns) or any(
                 big[k].dtype != v.dtype or big[k].shape[1:] != v.shape[1:] for k, v in p.columns.items()):
             big = {k: torch.empty((n_in + 2 * cap,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device) for k, v in p.columns.items()}
-            self._big, self._big_n = big, n_in
+            self._big, self._big_n, self._cap = big, n_in, cap
         p._other = {k: big[k][cap: cap + n_in] for k in p.columns}
-        # stage A: sort the owned particles into their (global-grid) buckets
-        self._force(self.lo_layer, self.own_n, 0, self.own_n)
-        n_own = p.update_positions()
-        if n_own != pos_owned_unsorted.shape[0]:
-            raise RuntimeError("slab build: particles died during the owned build")
-        bb = p._bucket_view(clone=False)[1]
-        layer_first = bb[:: self.per_layer].long().cpu()
-        layer_offsets = torch.cat([layer_first, torch.tensor([n_own], dtype=torch.int64)])
-        # stage B: halo layers of every sorted column
-        self.ex = SlabExchange(self.rank, self.world, bool(self.periodic[0]), self.w, layer_offsets, self.group)
-        ex = self.ex
+        # 1. owned build in the padded window
+        self._force(win_lo, win_n, own_lo, self.own_n)
+        n_own = p.update_positions(assume_all_alive=assume_all_alive)
         self.order_owned = p.get_alive_indicies()
-        in_place = ex.n_ghost_lo <= cap and ex.n_ghost_hi <= cap and all(
-            v.data_ptr() == big[k][cap:].data_ptr() for k, v in p.columns.items())
-        if in_place:
-            cols = {k: ex.fill_halo(big[k][cap - ex.n_ghost_lo: cap + n_own + ex.n_ghost_hi]) for k in p.columns}
-        else:  # halo larger than the reserve: put the local arrays together by copy
-            cols = {k: ex.assemble(v) for k, v in p.columns.items()}
+        _, bb, be = p._bucket_view(clone=False, sync=False)
+        c0 = own_lo * per_layer                       # first owned bucket
+        c1 = c0 + self.own_n * per_layer              # one past the last owned bucket
+        # 2. counts: [sent to lower, sent to upper] -> neighbours; everything to the host in ONE read
+        first = bb[c0]  # 0 unless a stray particle sits in a lower ghost layer (caught below)
+        mine = torch.stack([(bb[c0 + w * per_layer] if self.own_n > w else be[c1 - 1]) - first, be[c1 - 1] - bb[c1 - w * per_layer], be[c1 - 1] - first]).to(torch.int64)
+        got = torch.zeros(2, dtype=torch.int64, device=dev)
+        ops = []
+        if has_lo:
+            ops.append(dist.P2POp(dist.isend, mine[0:1], lower, self.group))
+        if has_hi:
+            ops.append(dist.P2POp(dist.isend, mine[1:2], upper, self.group))
+        if has_hi:
+            ops.append(dist.P2POp(dist.irecv, got[1:2], upper, self.group))
+        if has_lo:
+            ops.append(dist.P2POp(dist.irecv, got[0:1], lower, self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        n_send_lo, n_send_hi, n_own_dev, n_lo, n_hi = [int(v) for v in torch.cat([mine, got]).tolist()]  # the one host synchronisation
+        if n_own_dev != n_own:
+            raise RuntimeError(f"slab build: {n_own - n_own_dev} particle(s) died or left this rank's slab during the owned build")
+        p.check_async()
+        if not has_lo:
+            n_lo = 0
+        if not has_hi:
+            n_hi = 0
+        if n_lo > cap or n_hi > cap:  # halo larger than the reserve: grow it and redo (rare; first build of a clustered cloud)
+            self._cap = max(n_lo, n_hi) * 5 // 4 + 4096
+            self._big = None
+            return self.build(pos_owned_unsorted, extra_columns, assume_all_alive)
+        # 3. one batch: halo slices of every sorted column + bucket ranges of those layers
+        nb_w = w * per_layer
+        gh = getattr(self, "_ghost_ranges", None)
+        if gh is None or gh.shape[1] != nb_w:
+            gh = self._ghost_ranges = torch.empty((4, max(nb_w, 1)), dtype=torch.int32, device=dev)
+        ops = []
+        cols = {k: big[k][cap - n_lo: cap + n_own + n_hi] for k in p.columns}
+        for k in p.columns:
+            t = big[k]
+            if has_lo and n_send_lo > 0:
+                ops.append(dist.P2POp(dist.isend, t[cap: cap + n_send_lo], lower, self.group))
+            if has_hi and n_send_hi > 0:
+                ops.append(dist.P2POp(dist.isend, t[cap + n_own - n_send_hi: cap + n_own], upper, self.group))
+            if has_hi and n_hi > 0:
+                ops.append(dist.P2POp(dist.irecv, t[cap + n_own: cap + n_own + n_hi], upper, self.group))
+            if has_lo and n_lo > 0:
+                ops.append(dist.P2POp(dist.irecv, t[cap - n_lo: cap], lower, self.group))
+        for src, (to_lo, to_hi) in ((bb, (0, 2)), (be, (1, 3))):
+            if has_lo:
+                ops.append(dist.P2POp(dist.isend, src[c0: c0 + nb_w], lower, self.group))
+            if has_hi:
+                ops.append(dist.P2POp(dist.isend, src[c1 - nb_w: c1], upper, self.group))
+            if has_hi:
+                ops.append(dist.P2POp(dist.irecv, gh[to_hi][:nb_w], upper, self.group))
+            if has_lo:
+                ops.append(dist.P2POp(dist.irecv, gh[to_lo][:nb_w], lower, self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
         p.columns = cols
         p._other = {}  # the reorder buffers of the owned build are now the live columns
-        # stage C: bucket ranges of the sorted local set
-        has_lo = ex.lower is not None
-        has_hi = ex.upper is not None
-        win_lo = self.lo_layer - (self.w if has_lo else 0)
-        win_n = self.own_n + (self.w if has_lo else 0) + (self.w if has_hi else 0)
-        self._force(win_lo, win_n, self.w if has_lo else 0, self.own_n)
+        # 4. bucket ranges of the local set
         p._sync_stream()
         pos = p.columns["position"]
-        alive = p.columns["alive"]
-        check(p._h, p._lib.abr_celllist_adopt_sorted(p._h, C.c_void_p(pos.data_ptr()), C.c_void_p(alive.data_ptr()), pos.shape[0]))
+        check(p._h, p._lib.abr_celllist_patch_ghosts(p._h, C.c_void_p(pos.data_ptr()), n_lo, n_own, n_hi,
+                                                     C.c_void_p(gh[0].data_ptr()) if has_lo else None, C.c_void_p(gh[1].data_ptr()) if has_lo else None,
+                                                     C.c_void_p(gh[2].data_ptr()) if has_hi else None, C.c_void_p(gh[3].data_ptr()) if has_hi else None))
         p.searchable = True
-        return ex.n_local
+        self.ex = _LocalLayout(self.rank, self.world, lower, upper, n_lo, n_own, n_hi, n_send_lo, n_send_hi, self.group)
+        return self.ex.n_local
+
+    def migrate(self, pos, columns=None):
+        """Neighbour-only particle migration (the moving-particle loops of tests/md.h:318-326
+        on more than one GPU): particles whose bucket layer left this rank's slab go to the lower / upper
+        neighbour, arrivals are appended.  `pos` (n x D, unsorted, moved) and the other per-particle
+        columns are returned as new tensors (unchanged objects when nothing moves anywhere near this rank).
+        A particle that moved further than one slab is reported by the next build."""
+        from ._lib import check
+
+        p = self.p
+        dev = self.device
+        columns = dict(columns or {})
+        lower, upper = self._neighbours()
+        n = pos.shape[0]
+        self._force_global()
+        cls = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        counts = torch.zeros(3, dtype=torch.int32, device=dev)
+        p._sync_stream()
+        check(p._h, p._lib.abr_slab_classify(p._h, C.c_void_p(pos.data_ptr()), n, self.lo_layer, self.hi_layer, C.c_void_p(cls.data_ptr()), C.c_void_p(counts.data_ptr())))
+        mine = counts[1:3].to(torch.int64)
+        got = torch.zeros(2, dtype=torch.int64, device=dev)
+        ops = []
+        if lower is not None:
+            ops.append(dist.P2POp(dist.isend, mine[0:1], lower, self.group))
+        if upper is not None:
+            ops.append(dist.P2POp(dist.isend, mine[1:2], upper, self.group))
+        if upper is not None:
+            ops.append(dist.P2POp(dist.irecv, got[1:2], upper, self.group))
+        if lower is not None:
+            ops.append(dist.P2POp(dist.irecv, got[0:1], lower, self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        s_lo, s_hi, r_lo, r_hi = [int(v) for v in torch.cat([mine, got]).tolist()]
+        if lower is None and s_lo or upper is None and s_hi:
+            raise RuntimeError("slab migrate: a particle left a non-periodic domain towards a missing neighbour")
+        if s_lo + s_hi + r_lo + r_hi == 0:
+            return pos, columns
+        cls = cls[:n]
+        idx_lo = torch.nonzero(cls == 1).reshape(-1)
+        idx_hi = torch.nonzero(cls == 2).reshape(-1)
+        keep = torch.nonzero(cls == 0).reshape(-1)
+        allc = dict(columns)
+        allc["position"] = pos
+        out = {}
+        ops = []
+        recv = {}
+        for k, t in allc.items():
+            send_lo = t.index_select(0, idx_lo).contiguous()
+            send_hi = t.index_select(0, idx_hi).contiguous()
+            new = torch.empty((keep.shape[0] + r_lo + r_hi,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            new[: keep.shape[0]] = t.index_select(0, keep)
+            out[k] = new
+            recv[k] = (send_lo, send_hi)
+            nk = keep.shape[0]
+            if lower is not None and s_lo:
+                ops.append(dist.P2POp(dist.isend, send_lo, lower, self.group))
+            if upper is not None and s_hi:
+                ops.append(dist.P2POp(dist.isend, send_hi, upper, self.group))
+            if upper is not None and r_hi:
+                ops.append(dist.P2POp(dist.irecv, new[nk + r_lo: nk + r_lo + r_hi], upper, self.group))
+            if lower is not None and r_lo:
+                ops.append(dist.P2POp(dist.irecv, new[nk: nk + r_lo], lower, self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        new_pos = out.pop("position")
+        return new_pos, out
+
+    def _force_global(self):
+        from ._lib import check
+
+        p = self.p
+        check(p._h, p._lib.abr_domain_force_grid(p._h, self.D, self.low.ctypes.data, self.high.ctypes.data, self.periodic.ctypes.data, self.size.ctypes.data))
 
     def owned(self, local):
         return local[self.ex.own_begin: self.ex.own_end]
@@ -360,10 +590,20 @@ def run_bench(args, rank, world, dev, metric, unit, emit=None):
         return y
 
     step()
-    cnt, _ = sp.p.pair_stats(radius)
+    cnt, hs = sp.p.pair_stats(radius)
     pairs_t = sp.owned(cnt).long().sum()
     dist.all_reduce(pairs_t)
     pairs = int(pairs_t.item())
+    # parity guards before anything is timed: (1) the global pair count is the one a uniform cloud of this
+    # density must have (the single-GPU count of the same workload: tests/test_gpu_parity.py::test_c5_32m_sampled_oracle);
+    # (2) sampled owned rows: the cell-tiled kernel on the ghost-padded local set finds exactly the pair sets
+    # (count + hash) the exact per-row iterator walk finds on this rank
+    expect = n_total * (1.0 + 4.0 / 3.0 * np.pi * radius**3 * n_total)
+    assert abs(pairs - expect) / expect < 2e-3, f"global pair count {pairs} differs from the expectation {expect:.6g} of a uniform cloud"
+    sub = torch.arange(sp.ex.own_begin, sp.ex.own_end, 4001, device=dev)
+    cnt_w, hs_w = sp.p.pair_stats(radius, rows=sp.p.get("position")[sub].contiguous(), path=1)
+    assert bool((cnt[sub] == cnt_w).all()) and bool((hs[sub] == hs_w).all()), f"rank {rank}: tiled pair sets differ from the exact walk on sampled owned rows"
+    del hs, cnt_w, hs_w
     for _ in range(max(0, args.warmup - 1)):
         step()
     torch.cuda.synchronize()

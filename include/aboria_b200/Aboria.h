@@ -42,6 +42,7 @@
 #include <string>
 #include <tuple>
 #include <type_traits>
+#include <functional>
 #include <vector>
 
 #include "abr.h"
@@ -134,6 +135,11 @@ typename Var::value_type &get(particle_value<D, UserVars...> &p) {
   return std::get<detail::index_of<Var, typename particle_value<D, UserVars...>::variables>::value>(p.v);
 }
 
+template <typename Var, unsigned int D, typename... UserVars>
+const typename Var::value_type &get(const particle_value<D, UserVars...> &p) {
+  return std::get<detail::index_of<Var, typename particle_value<D, UserVars...>::variables>::value>(p.v);
+}
+
 // ---- Particles ---------------------------------------------------------------
 template <typename VAR = std::tuple<>, unsigned int DomainD = 3> class Particles;
 
@@ -172,13 +178,24 @@ public:
       std::get<2>(data_)[i] = uint8_t(true);
     }
   }
-  void push_back(const value_type &p) {
+  // src/Particles.h:264-297: with a neighbour search in place the ordered structure is rebuilt (the
+  // reference's update_positions(begin(), end()) for search.ordered()) unless the caller asks not to —
+  // then the container is no longer searchable until the next update_positions
+  void push_back(const value_type &p, bool update_neighbour_search = true) {
     push_all(p, std::make_index_sequence<n_columns>());
     std::get<1>(data_).back() = next_id_++;
     std::get<2>(data_).back() = uint8_t(true);
-    // the reference re-runs update_positions for an ordered structure on
-    // push_back; here the caller does that once after filling the container
-    searchable_ = false;
+    if (searchable_ && update_neighbour_search) {
+      update_positions();
+    } else {
+      searchable_ = false;
+    }
+  }
+  // the particle at position i, by value (the reference hands functors a const reference)
+  value_type operator[](size_t i) const {
+    value_type p;
+    get_all(p, i, std::make_index_sequence<n_columns>());
+    return p;
   }
 
   template <typename Var> std::vector<typename Var::value_type> &column() {
@@ -273,6 +290,18 @@ public:
   template <typename Var> const void *device_column() const { return dev_[detail::index_of<Var, variables>::value]; }
   const double *device_positions() const { return static_cast<const double *>(dev_[0]); }
   size_t device_size() const { return n_device_; }
+  // Ship every column of this set to the device as it is on the host NOW (no search structure needed).
+  // An operator whose row set is not its column set calls this before it binds row columns: the
+  // reference reads live host values of the row particles (src/Kernels.h:737-749), so a row set that never
+  // ran update_positions, or whose host columns were edited since, must not leave a null / stale pointer.
+  void sync_all_to_device() const {
+    if (n_device_ != size() || !dev_[0]) {
+      free_device();
+      alloc_device(size());
+      n_device_ = size();
+    }
+    upload_all(std::make_index_sequence<n_columns>());
+  }
   // copy a (possibly modified) host column to the device again
   template <typename Var> void sync_to_device() {
     const size_t c = detail::index_of<Var, variables>::value;
@@ -300,11 +329,15 @@ private:
     int dummy[] = {(std::get<I>(data_).resize(n), 0)...};
     (void)dummy;
   }
+  template <size_t... I> void get_all(value_type &p, size_t i, std::index_sequence<I...>) const {
+    int dummy[] = {(std::get<I>(p.v) = std::get<I>(data_)[i], 0)...};
+    (void)dummy;
+  }
   template <size_t... I> void push_all(const value_type &p, std::index_sequence<I...>) {
     int dummy[] = {(std::get<I>(data_).push_back(std::get<I>(p.v)), 0)...};
     (void)dummy;
   }
-  template <size_t... I> void upload_all(std::index_sequence<I...>) {
+  template <size_t... I> void upload_all(std::index_sequence<I...>) const {
     int dummy[] = {(detail::check_rc(h_, abr_memcpy_h2d(h_, dev_[I], std::get<I>(data_).data(), elem_bytes_[I] * size()), "upload"), 0)...};
     (void)dummy;
   }
@@ -312,13 +345,13 @@ private:
     int dummy[] = {(detail::check_rc(h_, abr_memcpy_d2h(h_, std::get<I>(data_).data(), dev_[I], elem_bytes_[I] * size()), "download"), 0)...};
     (void)dummy;
   }
-  void alloc_device(size_t n) {
+  void alloc_device(size_t n) const {
     for (size_t c = 0; c < n_columns; ++c) {
       detail::check_rc(h_, abr_malloc(h_, &dev_[c], elem_bytes_[c] * (n + 1)), "alloc");
       detail::check_rc(h_, abr_malloc(h_, &dev_other_[c], elem_bytes_[c] * (n + 1)), "alloc");
     }
   }
-  void free_device() {
+  void free_device() const {
     for (size_t c = 0; c < n_columns; ++c) {
       if (dev_[c]) abr_free(h_, dev_[c]);
       if (dev_other_[c]) abr_free(h_, dev_other_[c]);
@@ -331,9 +364,9 @@ private:
   bool searchable_;
   bool id_map_;
   abr_handle h_;
-  void *dev_[n_columns], *dev_other_[n_columns];
+  mutable void *dev_[n_columns], *dev_other_[n_columns]; // device copies: a cache of the host columns
   size_t elem_bytes_[n_columns];
-  size_t n_device_;
+  mutable size_t n_device_;
 };
 
 // get<variable>(particles)  (src/Get.h:1110-1150)
@@ -452,6 +485,41 @@ template <unsigned int D, typename P> struct sph_pressure : desc_base {
 };
 } // namespace kernels
 
+// ---- device-resident vector ---------------------------------------------------------
+// b and y of `K * b` kept on the GPU across the iterations of a solver (the reference's
+// Eigen::VectorXd lives on the host; shipping 2 x 256 MB over PCIe per product costs more than
+// the product itself).  Owns its memory through the C-ABI; movable, not copyable.
+class DeviceVector {
+public:
+  DeviceVector(abr_handle h, size_t n) : h_(h), n_(n), d_(nullptr) {
+    detail::check_rc(h_, abr_malloc(h_, (void **)&d_, sizeof(double) * (n + 1)), "DeviceVector");
+  }
+  template <typename HostVector> DeviceVector(abr_handle h, const HostVector &v) : DeviceVector(h, (size_t)v.size()) { upload(v); }
+  DeviceVector(DeviceVector &&o) noexcept : h_(o.h_), n_(o.n_), d_(o.d_) { o.d_ = nullptr; }
+  DeviceVector(const DeviceVector &) = delete;
+  DeviceVector &operator=(const DeviceVector &) = delete;
+  ~DeviceVector() {
+    if (d_) abr_free(h_, d_);
+  }
+  size_t size() const { return n_; }
+  double *data() { return d_; }
+  const double *data() const { return d_; }
+  void set_zero() { detail::check_rc(h_, abr_memset(h_, d_, 0, sizeof(double) * n_), "DeviceVector"); }
+  template <typename HostVector> void upload(const HostVector &v) {
+    ABR_CHECK((size_t)v.size() == n_, "DeviceVector: size mismatch");
+    detail::check_rc(h_, abr_memcpy_h2d(h_, d_, v.data(), sizeof(double) * n_), "DeviceVector");
+  }
+  template <typename HostVector> void download(HostVector &v) const {
+    ABR_CHECK((size_t)v.size() == n_, "DeviceVector: size mismatch");
+    detail::check_rc(h_, abr_memcpy_d2h(h_, v.data(), d_, sizeof(double) * n_), "DeviceVector");
+  }
+
+private:
+  abr_handle h_;
+  size_t n_;
+  double *d_;
+};
+
 // ---- sparse operator ------------------------------------------------------------
 // MatrixReplacement<1,1,tuple<KernelSparseConst>> (src/Operators.h:75-291);
 // stores REFERENCES to the particle sets like the reference (src/Kernels.h:133-134)
@@ -469,20 +537,43 @@ public:
     ABR_CHECK(cols_.searchable(), "column particles have no neighbour search");
     abr_handle h = cols_.handle();
     const bool same = (const void *)&rows_ == (const void *)&cols_;
-    // a row set without a search structure is shipped as bare positions
-    const double *row_pos = same ? cols_.device_positions() : upload_row_positions();
+    const double *row_pos = row_positions(same);
     KernelDesc k = k_;
     k.bind(rows_, cols_);
+    const double *rpr = upload_row_radii();
     double *b = nullptr, *y = nullptr;
     detail::check_rc(h, abr_malloc(h, (void **)&b, sizeof(double) * (cols() + 1)), "evaluate");
     detail::check_rc(h, abr_malloc(h, (void **)&y, sizeof(double) * (rows() + 1)), "evaluate");
     detail::check_rc(h, abr_memcpy_h2d(h, b, rhs.data(), sizeof(double) * cols()), "evaluate");
     detail::check_rc(h, abr_memcpy_h2d(h, y, lhs.data(), sizeof(double) * rows()), "evaluate");
-    detail::check_rc(h, abr_sparse_matvec(h, row_pos, rows_.size(), same ? 1 : 0, &k.d, radius_, nullptr, b, y, nullptr), "evaluate");
+    detail::check_rc(h, abr_sparse_matvec(h, row_pos, rows_.size(), same ? 1 : 0, &k.d, radius_, rpr, b, y, nullptr), "evaluate");
     detail::check_rc(h, abr_memcpy_d2h(h, lhs.data(), y, sizeof(double) * rows()), "evaluate");
     abr_free(h, b);
     abr_free(h, y);
-    if (!same) abr_free(h, const_cast<double *>(row_pos));
+    if (rpr) abr_free(h, const_cast<double *>(rpr));
+  }
+
+  // the same on device-resident vectors: nothing is allocated or copied — the form an iterative solver
+  // loop wants (two products per iteration on the same operator)
+  void evaluate(DeviceVector &lhs, const DeviceVector &rhs) const {
+    ABR_CHECK(lhs.size() == rows(), "lhs vector has incompatible size");
+    ABR_CHECK(rhs.size() == cols(), "rhs vector has incompatible size");
+    ABR_CHECK(cols_.searchable(), "column particles have no neighbour search");
+    abr_handle h = cols_.handle();
+    const bool same = (const void *)&rows_ == (const void *)&cols_;
+    const double *row_pos = row_positions(same);
+    KernelDesc k = k_;
+    k.bind(rows_, cols_);
+    const double *rpr = upload_row_radii();
+    detail::check_rc(h, abr_sparse_matvec(h, row_pos, rows_.size(), same ? 1 : 0, &k.d, radius_, rpr, rhs.data(), lhs.data(), nullptr), "evaluate");
+    if (rpr) abr_free(h, const_cast<double *>(rpr));
+  }
+  // y = K * b on the device
+  DeviceVector operator*(const DeviceVector &b) const {
+    DeviceVector y(cols_.handle(), rows());
+    y.set_zero();
+    evaluate(y, b);
+    return y;
   }
 
   // y = K * b   (Eigen zeroes the destination first, src/detail/Operators.h:219-232)
@@ -500,19 +591,20 @@ public:
     ABR_CHECK(j < cols(), "j greater than cols()");
     abr_handle h = cols_.handle();
     const bool same = (const void *)&rows_ == (const void *)&cols_;
-    const double *row_pos = same ? cols_.device_positions() : upload_row_positions();
+    const double *row_pos = row_positions(same);
     KernelDesc k = k_;
     k.bind(rows_, cols_);
+    const double *rpr = upload_row_radii();
     uint64_t *ij = nullptr;
     detail::check_rc(h, abr_malloc(h, (void **)&ij, 3 * sizeof(uint64_t)), "coeff");
     const uint64_t host_ij[2] = {i, j};
     detail::check_rc(h, abr_memcpy_h2d(h, ij, host_ij, sizeof(host_ij)), "coeff");
     detail::check_rc(h, abr_query_set_particles(h, cols_.device_positions(), cols_.device_size()), "coeff");
-    detail::check_rc(h, abr_sparse_coeff(h, row_pos, rows_.size(), &k.d, radius_, nullptr, ij, ij + 1, 1, reinterpret_cast<double *>(ij + 2)), "coeff");
+    detail::check_rc(h, abr_sparse_coeff(h, row_pos, rows_.size(), &k.d, radius_, rpr, ij, ij + 1, 1, reinterpret_cast<double *>(ij + 2)), "coeff");
     double out = 0;
     detail::check_rc(h, abr_memcpy_d2h(h, &out, ij + 2, sizeof(out)), "coeff");
     abr_free(h, ij);
-    if (!same) abr_free(h, const_cast<double *>(row_pos));
+    if (rpr) abr_free(h, const_cast<double *>(rpr));
     return out;
   }
 
@@ -524,19 +616,20 @@ public:
     ABR_CHECK(cols_.searchable(), "column particles have no neighbour search");
     abr_handle h = cols_.handle();
     const bool same = (const void *)&rows_ == (const void *)&cols_;
-    const double *row_pos = same ? cols_.device_positions() : upload_row_positions();
+    const double *row_pos = row_positions(same);
     KernelDesc k = k_;
     k.bind(rows_, cols_);
+    const double *rpr = upload_row_radii();
     const size_t nr = rows_.size(), BR = k.d.block_rows, BC = k.d.block_cols;
     uint32_t *row_ptr = nullptr;
     detail::check_rc(h, abr_malloc(h, (void **)&row_ptr, (nr + 1) * sizeof(uint32_t)), "assemble");
     uint64_t nnz = 0;
-    detail::check_rc(h, abr_sparse_assemble(h, row_pos, nr, same ? 1 : 0, &k.d, radius_, nullptr, row_ptr, nullptr, nullptr, 0, &nnz), "assemble");
+    detail::check_rc(h, abr_sparse_assemble(h, row_pos, nr, same ? 1 : 0, &k.d, radius_, rpr, row_ptr, nullptr, nullptr, 0, &nnz), "assemble");
     int32_t *col = nullptr;
     double *val = nullptr;
     detail::check_rc(h, abr_malloc(h, (void **)&col, (nnz + 1) * sizeof(int32_t)), "assemble");
     detail::check_rc(h, abr_malloc(h, (void **)&val, (nnz * BR * BC + 1) * sizeof(double)), "assemble");
-    detail::check_rc(h, abr_sparse_assemble(h, row_pos, nr, same ? 1 : 0, &k.d, radius_, nullptr, row_ptr, col, val, nnz, &nnz), "assemble");
+    detail::check_rc(h, abr_sparse_assemble(h, row_pos, nr, same ? 1 : 0, &k.d, radius_, rpr, row_ptr, col, val, nnz, &nnz), "assemble");
     std::vector<uint32_t> hp(nr + 1);
     std::vector<int32_t> hc(nnz);
     std::vector<double> hv(nnz * BR * BC);
@@ -553,22 +646,40 @@ public:
     abr_free(h, row_ptr);
     abr_free(h, col);
     abr_free(h, val);
-    if (!same) abr_free(h, const_cast<double *>(row_pos));
+    if (rpr) abr_free(h, const_cast<double *>(rpr));
+  }
+
+  // FRadius overload (src/Operators.h:478-489): radius_function(a) per row particle, evaluated on
+  // the host when the operator is applied (the reference evaluates it inside the row loop,
+  // src/Kernels.h:739) and shipped as radius_per_row
+  template <typename FRadius> void set_radius_function(const FRadius &f) {
+    radius_fn_ = [f](const typename RowParticles::value_type &a) { return (double)f(a); };
   }
 
 private:
-  const double *upload_row_positions() const {
+  // Device positions of the row set.  Rows that are not the column set need no search structure
+  // (tests/rbf_interpolation.h:326): every column of the row set is shipped as it is on the host now,
+  // so that the functor's row columns (bind) are neither null nor stale.
+  const double *row_positions(bool same) const {
+    if (same) return cols_.device_positions();
+    rows_.sync_all_to_device();
+    return rows_.device_positions();
+  }
+  const double *upload_row_radii() const {
+    if (!radius_fn_) return nullptr;
     abr_handle h = cols_.handle();
+    std::vector<double> r(rows_.size() + 1);
+    for (size_t i = 0; i < rows_.size(); ++i) r[i] = radius_fn_(rows_[i]);
     double *p = nullptr;
-    const auto &pos = rows_.template column<typename RowParticles::position>();
-    detail::check_rc(h, abr_malloc(h, (void **)&p, sizeof(typename RowParticles::double_d) * (pos.size() + 1)), "rows");
-    detail::check_rc(h, abr_memcpy_h2d(h, p, pos.data(), sizeof(typename RowParticles::double_d) * pos.size()), "rows");
+    detail::check_rc(h, abr_malloc(h, (void **)&p, sizeof(double) * r.size()), "radius");
+    detail::check_rc(h, abr_memcpy_h2d(h, p, r.data(), sizeof(double) * rows_.size()), "radius");
     return p;
   }
   const RowParticles &rows_;
   const ColParticles &cols_;
   double radius_;
   KernelDesc k_;
+  std::function<double(const typename RowParticles::value_type &)> radius_fn_;
 };
 
 // src/Operators.h:508-516
@@ -576,6 +687,15 @@ template <typename RowParticles, typename ColParticles, typename KernelDesc>
 SparseOperator<RowParticles, ColParticles, KernelDesc> create_sparse_operator(const RowParticles &rows, const ColParticles &cols,
                                                                              const double radius, const KernelDesc &k) {
   return SparseOperator<RowParticles, ColParticles, KernelDesc>(rows, cols, radius, k);
+}
+// src/Operators.h:478-489: the radius as a function of the row particle
+template <typename RowParticles, typename ColParticles, typename FRadius, typename KernelDesc,
+          typename = typename std::enable_if<!std::is_arithmetic<FRadius>::value>::type>
+SparseOperator<RowParticles, ColParticles, KernelDesc> create_sparse_operator(const RowParticles &rows, const ColParticles &cols,
+                                                                             const FRadius &radius_function, const KernelDesc &k) {
+  SparseOperator<RowParticles, ColParticles, KernelDesc> op(rows, cols, 0.0, k);
+  op.set_radius_function(radius_function);
+  return op;
 }
 
 // ---- zero and block operators -------------------------------------------------------

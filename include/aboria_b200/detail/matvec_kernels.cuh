@@ -207,18 +207,33 @@ __global__ void __launch_bounds__(128) coeff_kernel(const abr_matvec_plan p, con
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t pi = ii[q] / BR, pj = jj[q] / BC;
     const int ioff = (int)(ii[q] - pi * BR), joff = (int)(jj[q] - pj * BC);
+    if (pi >= p.n_rows || pj >= p.q.n) { // the reference ASSERTs (src/Kernels.h:103-104); through the C ABI: a zero entry, no wild read
+      out[q] = 0.0;
+      continue;
+    }
     double dx[D];
     double n2 = 0;
+    bool finite = true;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       double v = p.q.pos[pj * D + d] - p.row_pos[pi * D + d];
+      if (!isfinite(v)) { // a non-finite row point would never leave the wrap loops: a GPU kernel must not hang
+        finite = false;
+        v = 0.0;
+      }
       if (g.periodic[d]) {
         const double w = g.bmax[d] - g.bmin[d];
-        while (v > w / 2) v -= w;
-        while (v <= -w / 2) v += w;
+        int guard = 0;
+        while (v > w / 2 && ++guard < (1 << 20)) v -= w;
+        while (v <= -w / 2 && ++guard < (1 << 20)) v += w;
+        if (guard >= (1 << 20)) finite = false;
       }
       dx[d] = v;
       n2 += v * v;
+    }
+    if (!finite) {
+      out[q] = 0.0;
+      continue;
     }
     const double R = p.radius_per_row ? p.radius_per_row[pi] : p.radius;
     double val = 0.0;
@@ -1681,7 +1696,15 @@ template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_pl
     // rows handed over by the tiled kernel: exact per-row walk
     abr_matvec_plan p2 = p;
     p2.walk_only_list = 1;
-    walk_kernel<D, F, STATS><<<p.sm_count, 128, 0, p.stream>>>(p2, f);
+    // grid sized for the worst case (every row handed over: lattice inputs sit exactly on bucket faces);
+    // blocks beyond the list length leave at once
+    {
+      unsigned wgrid = (unsigned)((p.n_rows + 127) / 128);
+      const unsigned wmax = (unsigned)p.sm_count * 16u;
+      if (wgrid > wmax) wgrid = wmax;
+      if (wgrid < 1) wgrid = 1;
+      walk_kernel<D, F, STATS><<<wgrid, 128, 0, p.stream>>>(p2, f);
+    }
   } else {
     const unsigned grid = (unsigned)((p.n_rows + 127) / 128);
     if (grid > 0) walk_kernel<D, F, STATS><<<grid, 128, 0, p.stream>>>(p, f);

@@ -130,6 +130,25 @@ int abr_domain_set_window(abr_handle h, int win_lo, int win_n, int own_lo, int o
  * No permutation, no reorder. */
 int abr_celllist_adopt_sorted(abr_handle h, double *pos_sorted, uint8_t *alive, size_t n);
 
+/* Slabs, cheaper second step: after abr_update_positions in the ghost-padded window (own
+ * layers in the middle, the ghost layers still empty) and the halo exchange, adopt the local
+ * array [ghost_lo | owned | ghost_hi] WITHOUT a pass over the particles: owned bucket ranges
+ * shift by n_ghost_lo, ghost buckets take the sender's ranges — bb_lo/be_lo: the lower
+ * neighbour's m_bucket_begin/end of the layers it sent (own_lo * prod(size[1..]) entries, its own
+ * numbering, rebased here), bb_hi/be_hi likewise for the upper neighbour; device pointers, a side
+ * without ghost layers passes NULL.  Binds the query to pos_local.  m_bucket_indices (the sorted
+ * key array) is not kept on this path. */
+int abr_celllist_patch_ghosts(abr_handle h, const double *pos_local, size_t n_ghost_lo, size_t n_own, size_t n_ghost_hi,
+                              const uint32_t *bb_lo, const uint32_t *be_lo, const uint32_t *bb_hi, const uint32_t *be_hi);
+
+/* Slabs, particle migration: for every (unsorted, moved) particle of this rank decide from the
+ * GLOBAL grid (abr_domain_force_grid) whether its bucket layer in dimension 0 is still inside
+ * [lo_layer, hi_layer) — cls 0 — or now belongs to the lower (1) / upper (2) neighbour (the
+ * nearer slab face, periodic wrap applied as enforce_domain would); counts3[k] = particles of
+ * class k (device, 3 x u32).  Particles outside a non-periodic domain or non-finite stay (the
+ * build kills them). */
+int abr_slab_classify(abr_handle h, const double *pos, size_t n, int lo_layer, int hi_layer, uint8_t *cls, uint32_t *counts3);
+
 /* neighbour_search_base::update_positions (src/NeighbourSearchBase.h:350-495)
  * for the ordered case + CellListOrdered::update_positions_impl
  * (src/CellListOrdered.h:190-259):

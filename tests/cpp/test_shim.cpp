@@ -290,7 +290,90 @@ static void test_md_force_block_kernel() {
   TS_ASSERT(std::sqrt(err2 / nrm2) <= 1e-12);
 }
 
+// A row set WITHOUT a neighbour search whose functor reads a row column (the row
+// columns must be shipped, not null / stale), the FRadius overload
+// (/root/reference/src/Operators.h:478-489), push_back with update_neighbour_search
+// (src/Particles.h:264-297) and device-resident vectors for solver loops.
+static void test_rows_without_search_fradius_pushback_devicevector() {
+  ABORIA_VARIABLE(scalar1, double, "scalar1")
+  ABORIA_VARIABLE(scalar2, double, "scalar2")
+  typedef Particles<std::tuple<scalar1, scalar2>> ParticlesType;
+  typedef position_d<3> position;
+  ParticlesType cols, rows;
+  const double diameter = 0.1;
+  ParticlesType::value_type p;
+  for (int i = 0; i < 3; ++i) {
+    get<position>(p) = vdouble3(diameter * 0.9 * i, 0, 0);
+    get<scalar1>(p) = 1.0;
+    get<scalar2>(p) = 2.0 + i; // 2, 3, 4
+    cols.push_back(p);
+  }
+  cols.init_neighbour_search(vdouble3::Constant(-1), vdouble3::Constant(1), vbool3::Constant(false));
+  // two test points, never given a search structure; their scalar1 differs per row
+  get<position>(p) = vdouble3(0.01, 0, 0);
+  get<scalar1>(p) = 10.0;
+  rows.push_back(p);
+  get<position>(p) = vdouble3(0.17, 0, 0);
+  get<scalar1>(p) = 20.0;
+  rows.push_back(p);
+  auto G = create_sparse_operator(rows, cols, diameter, kernels::const_sum<scalar1, scalar2>());
+  vector_type v(3, 1.0);
+  vector_type y = G * v;
+  // row 0 (x=0.01) reaches columns at 0 and 0.09: (10+2) + (10+3) = 25; row 1 (x=0.17) reaches 0.09 and 0.18: (20+3) + (20+4) = 47
+  TS_ASSERT_EQUALS(y.size(), (size_t)2);
+  TS_ASSERT_EQUALS(y[0], 25.0);
+  TS_ASSERT_EQUALS(y[1], 47.0);
+  // the reference reads LIVE row values: edit the host column, apply again
+  get<scalar1>(rows)[0] = 100.0;
+  y = G * v;
+  TS_ASSERT_EQUALS(y[0], 205.0);
+  TS_ASSERT_EQUALS(G.coeff(1, 2), 24.0);
+  TS_ASSERT_EQUALS(G.coeff(1, 0), 0.0);
+
+  // FRadius: the radius is a function of the row particle
+  auto Gr = create_sparse_operator(rows, cols, [&](const ParticlesType::value_type &a) { return get<scalar1>(a) > 50.0 ? 0.05 : 0.2; },
+                                   kernels::const_sum<scalar1, scalar2>());
+  y = Gr * v;
+  TS_ASSERT_EQUALS(y[0], 102.0);                                   // radius 0.05: only the column at 0
+  TS_ASSERT_EQUALS(y[1], (20.0 + 2) + (20.0 + 3) + (20.0 + 4));    // radius 0.2: all three
+
+  // push_back on a searchable container refreshes the ordered structure (the default) ...
+  get<position>(p) = vdouble3(-0.05, 0, 0);
+  get<scalar1>(p) = 1.0;
+  get<scalar2>(p) = 7.0;
+  cols.push_back(p);
+  TS_ASSERT(cols.searchable());
+  TS_ASSERT_EQUALS(cols.size(), (size_t)4);
+  TS_ASSERT_EQUALS(get<position>(cols)[0][0], -0.05); // sorted by bucket: the new particle leads
+  vector_type v4(4, 1.0);
+  auto G4 = create_sparse_operator(rows, cols, diameter, kernels::const_sum<scalar1, scalar2>());
+  y = G4 * v4;
+  TS_ASSERT_EQUALS(y[0], 205.0 + 107.0);
+  // ... unless the caller defers it
+  cols.push_back(p, false);
+  TS_ASSERT(!cols.searchable());
+  cols.update_positions();
+  TS_ASSERT(cols.searchable());
+
+  // device-resident vectors: y = K b without host copies, twice on the same buffers
+  auto C = create_sparse_operator(cols, cols, diameter, kernels::const_sum<scalar1, scalar2>());
+  vector_type b5(cols.size(), 1.0), y_host = C * b5;
+  DeviceVector bd(cols.handle(), b5), yd(cols.handle(), cols.size());
+  yd.set_zero();
+  C.evaluate(yd, bd);
+  vector_type y_dev(cols.size());
+  yd.download(y_dev);
+  for (size_t i = 0; i < cols.size(); ++i) TS_ASSERT_EQUALS(y_dev[i], y_host[i]);
+  C.evaluate(yd, bd); // accumulates
+  yd.download(y_dev);
+  for (size_t i = 0; i < cols.size(); ++i) TS_ASSERT_EQUALS(y_dev[i], 2 * y_host[i]);
+  DeviceVector y2 = C * bd;
+  y2.download(y_dev);
+  for (size_t i = 0; i < cols.size(); ++i) TS_ASSERT_EQUALS(y_dev[i], y_host[i]);
+}
+
 int main() {
+  test_rows_without_search_fradius_pushback_devicevector();
   test_md_force_block_kernel();
   test_sparse_operator();
   test_block_operator();
