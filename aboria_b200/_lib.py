@@ -45,6 +45,7 @@ SIGNATURES = {
     "abr_celllist_adopt_sorted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "abr_celllist_patch_ghosts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "abr_slab_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "abr_slab_layers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "abr_celllist_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]),
     "abr_celllist_get": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "abr_gather_columns": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -84,6 +85,8 @@ def lib():
                 "(make -C aboria_b200/csrc).  aboria_b200 has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("ABR_LIB_PATH") and not hasattr(L, name):
+                continue  # an older build of the library in a tuning experiment: newer entry points are simply absent
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -113,6 +113,15 @@ int abr_destroy(abr_handle hh) {
   if (!h) return ABR_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->rows_h) { // internal handle of the rows != columns product
+    abr_destroy(reinterpret_cast<abr_handle>(h->rows_h));
+    h->rows_h = nullptr;
+  }
+  h->heavy_list.release();
+  h->cs_ko.release();
+  h->cs_scratch.release();
+  h->cs_scratch2.release();
+  h->cs_bins.release();
   for (int i = 0; i < 2; ++i) {
     h->keys[i].release();
     h->idx[i].release();
@@ -163,6 +172,8 @@ int abr_set_option(abr_handle hh, const char *name, double value) {
     h->counting_min_n = value < 0 ? 0 : (value > 1e18 ? (size_t)-1 : (size_t)value);
   } else if (k == "phased_gather") {
     h->phased_gather = value != 0;
+  } else if (k == "xrows_min_n") {
+    h->xrows_min_n = value < 0 ? 0 : (value > 1e18 ? (size_t)-1 : (size_t)value);
   } else if (k == "symmetric") {
     h->symmetric = value != 0;
   } else if (k == "matvec_variant") {
@@ -180,6 +191,7 @@ int abr_check_async(abr_handle hh) {
   if (h->async_pending_n == 0) return ABR_OK;
   const size_t n = h->async_pending_n;
   h->async_pending_n = 0;
+  h->max_bucket = h->h_scalars->max_bucket;
   if (h->h_scalars->n_alive != n)
     return abr::set_error(h, ABR_ERR_STATE, "asynchronous update_positions: particles died; results of this update are invalid, redo it synchronously");
   if (h->h_scalars->n_aliased != 0 || h->h_scalars->n_outside != 0)

@@ -472,6 +472,8 @@ k_boundaries(const uint32_t *__restrict__ keys, uint32_t n, uint32_t ncells, uin
   if (k != knext || p + 1 == n) {
     if (k < ncells) be[k] = p + 1;
   }
+  // bucket occupancy, sampled where a run of 65 equal keys ends: enough to tell the product that heavy buckets exist
+  if (p >= 64 && k < ncells && keys[p - 64] == k && (k != knext || p + 1 == n)) atomicMax(&sc->max_bucket, 65u);
 }
 
 // ---------------------------------------------------------------------------
@@ -1078,6 +1080,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     h->async_pending_n = 0;
     const size_t n_alive = h->h_scalars->n_alive;
     h->n_aliased = h->h_scalars->n_aliased;
+    h->max_bucket = h->h_scalars->max_bucket;
     if (h->h_scalars->n_outside != 0)
       return set_error(h, ABR_ERR_INVALID, "build: " + std::to_string(h->h_scalars->n_outside) +
                                                " particle(s) lie outside this rank's slab window");

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2)
 k_cs_binsort(const unsigned long long *__restrict__ ko, const unsigned long long *__restrict__ rec, unsigned long long *__restrict__ scratch,
              unsigned long long *__restrict__ scratch2, const uint32_t *__restrict__ bin_start, int shift, uint32_t ncells, uint32_t dead_key,
              const CsCols cols, uint32_t *__restrict__ bb, uint32_t *__restrict__ be, uint32_t *__restrict__ sorted_keys,
-             int32_t *__restrict__ order_out) {
+             int32_t *__restrict__ order_out, uint32_t *__restrict__ max_bucket) {
   extern __shared__ __align__(128) unsigned char cs_raw[];
   const uint32_t S = 1u << shift;
   uint32_t *off = reinterpret_cast<uint32_t *>(cs_raw); // [S + 1] exclusive offsets
@@ -301,6 +301,7 @@ k_cs_binsort(const unsigned long long *__restrict__ ko, const unsigned long long
           // == lower_bound / upper_bound of the bucket id in the sorted keys (src/CellListOrdered.h:229-239)
           bb[bucket] = bs + run;
           be[bucket] = bs + run + c;
+          if (c > 64) atomicMax(max_bucket, c);
         }
         run += c;
       }
@@ -511,7 +512,7 @@ int build_counting(Handle *h, double *pos, uint8_t *alive, uint32_t n, const Gri
     k_cs_scatter<NGV><<<G, CS_THREADS, 0, h->stream>>>(keys, n, chunk, shift, NB, cols, cursor, rec, ko);                               \
     ABR_CUDA(h, cudaFuncSetAttribute(k_cs_binsort<NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));                  \
     k_cs_binsort<NGV><<<NB, CS_THREADS, sort_smem, h->stream>>>(ko, rec, scr, scr2, bin_start, shift, g.ncells, g.key_bound, cols, bbp, bep, \
-                                                                 sorted_keys, order_out);                                              \
+                                                                 sorted_keys, order_out, &h->d_scalars->max_bucket);                   \
   }
   switch (NG) {
   case 1: ABR_CS_LAUNCH(1) break;

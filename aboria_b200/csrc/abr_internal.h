@@ -45,6 +45,9 @@ struct DevScalars {
   uint32_t n_unsorted;     // adopt_sorted: key inversions found
   uint32_t pad[1];
   unsigned long long pair_count;
+  unsigned long long heavy_state; // tiled product: heavy-bucket items << 40 | their row batches
+  uint32_t heavy_work;            // scheduler of the heavy launch
+  uint32_t max_bucket;            // largest bucket occupancy seen by the build (k_boundaries)
 };
 
 struct Handle {
@@ -79,6 +82,10 @@ struct Handle {
   DevBuf scan_tmp2, pair_i, pair_j, pair_q; // bucket-pair traversal (abr_pairs.cu)
   DevBuf idm_k[2], idm_i[2], idm_max, id_map_key, id_map_value; // id map (m_id_map_key / m_id_map_value) + sort scratch
   size_t id_map_n = 0;
+  Handle *rows_h = nullptr; // internal handle: row points of a rows != columns product bucketed into this grid (abr_matvec.cu)
+  size_t xrows_min_n = 1024;  // from this many rows on (abr_set_option("xrows_min_n")); fewer rows: one thread per row
+  uint32_t max_bucket = 0; // largest bucket occupancy of the last verified build (hint for the product's heavy-bucket split)
+  DevBuf heavy_list;     // tiled product: (bucket, first batch) of the buckets split into row batches
   DevBuf ytmp, row_bits; // symmetric product: accumulation scratch, exact-walk flags
   bool symmetric = false; // abr_set_option("symmetric"): evaluate each unordered pair once for functors that declare SYMMETRY
   DevBuf posb; // packed (x, y, z, b) records of the column particles for the tiled product

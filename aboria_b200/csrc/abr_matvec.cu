@@ -23,6 +23,8 @@ template <int D> __global__ void __launch_bounds__(256) k_pack_posb(const double
   if (j == 0) { // reset the tile scheduler and the exact-walk list of the product that follows (no memset node: see abr_build.cu)
     scal->work_counter = 0;
     scal->danger_count = 0;
+    scal->heavy_state = 0ull;
+    scal->heavy_work = 0;
   }
   if (j >= n) return;
   double r[4] = {0.0, 0.0, 0.0, 0.0};
@@ -31,6 +33,73 @@ template <int D> __global__ void __launch_bounds__(256) k_pack_posb(const double
   if (b) r[3] = b[j];
   double4 v = make_double4(r[0], r[1], r[2], r[3]);
   reinterpret_cast<double4 *>(posb)[j] = v;
+}
+
+// rows whose point the internal row build dropped (outside the domain, non-finite): to the exact walk
+__global__ void __launch_bounds__(256) k_rows_dropped(const uint8_t *__restrict__ alive, uint32_t n_rows, uint32_t *__restrict__ danger_count,
+                                                      uint32_t *__restrict__ danger_list, uint32_t capacity) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_rows && !alive[i]) {
+    const uint32_t slot = atomicAdd(danger_count, 1u);
+    if (slot < capacity) danger_list[slot] = i;
+  }
+}
+
+// Buckets the row points of a rows != columns product into the COLUMN grid: an ordinary build (keys, sort,
+// bucket ranges, reorder of the position column) on an internal handle that shares the column set's grid but
+// treats every dimension as non-periodic, so that row points outside the domain are dropped (they go to the
+// exact walk, which searches from outside through the images like the reference) instead of being wrapped.
+static int bucket_rows(Handle *h, const MatvecCall &c, abr_matvec_plan *p) {
+  if (!h->rows_h) {
+    h->rows_h = new Handle();
+    h->rows_h->device = h->device;
+    h->rows_h->sm_count = h->sm_count;
+    cudaError_t e = cudaMalloc(&h->rows_h->d_scalars, sizeof(DevScalars));
+    if (e == cudaSuccess) e = cudaMallocHost(&h->rows_h->h_scalars, 3 * sizeof(DevScalars));
+    if (e != cudaSuccess) return check_cuda(h, e, "row build: scalars");
+  }
+  Handle *r = h->rows_h;
+  r->stream = h->stream;
+  r->domain_set = true;
+  r->grid_forced = true;
+  r->D = h->D;
+  for (int d = 0; d < MAXD; ++d) {
+    r->bmin[d] = h->bmin[d];
+    r->bmax[d] = h->bmax[d];
+    r->periodic[d] = false;
+    r->size[d] = h->size[d];
+    r->side[d] = h->side[d];
+    r->inv_side[d] = h->inv_side[d];
+  }
+  r->n_leaf = h->n_leaf;
+  const size_t n = c.n_rows;
+  const size_t pos_bytes = n * (size_t)h->D * sizeof(double);
+  ABR_CUDA(h, r->posb.reserve(2 * pos_bytes + 64));            // [input copy | sorted]
+  ABR_CUDA(h, r->danger_list.reserve(n * sizeof(int32_t) + n)); // [order | alive]
+  double *pin = r->posb.as<double>();
+  double *psorted = reinterpret_cast<double *>(r->posb.as<char>() + ((pos_bytes + 63) / 64) * 64);
+  int32_t *order = r->danger_list.as<int32_t>();
+  uint8_t *alive = reinterpret_cast<uint8_t *>(order + n);
+  ABR_CUDA(h, cudaMemcpyAsync(pin, c.row_pos, pos_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  fill_u32(h, reinterpret_cast<uint32_t *>(alive), 0x01010101u, (n + 3) / 4);
+  const void *src[1] = {pin};
+  void *dst[1] = {psorted};
+  const size_t eb[1] = {(size_t)h->D * sizeof(double)};
+  ReorderSpec spec{1, src, dst, eb};
+  // asynchronous form: the alive count is never read on the host — the bucket ranges bound every access
+  int rc = build_celllist(r, pin, alive, n, order, nullptr, &spec);
+  if (rc) return set_error(h, rc, "row build: " + r->err);
+  h->launches += r->launches;
+  r->launches = 0;
+  ABR_CUDA(h, h->danger_list.reserve(n * sizeof(uint32_t)));
+  p->danger_list = h->danger_list.as<uint32_t>();
+  p->danger_capacity = (uint32_t)n;
+  p->xrow_pos = psorted;
+  p->xrow_bb = r->bucket_begin.as<uint32_t>();
+  p->xrow_be = r->bucket_end.as<uint32_t>();
+  p->xrow_index = order;
+  p->xrow_alive = alive;
+  return ABR_OK;
 }
 
 // Fills the plan: picks the tiled kernel when its preconditions hold, and the
@@ -113,6 +182,56 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
     if (!tiled && c.force_path == 0)
       return set_error(h, ABR_ERR_INVALID, "tiled path not applicable for this radius / grid");
   }
+  // Rows that are NOT the column set (RBF evaluation at test points, tests/rbf_interpolation.h:326) with a
+  // constant radius: bucket the row points into the column grid with an internal build and run the cell-tiled
+  // kernel on them instead of one thread per row.  Row points outside the domain (the reference searches from
+  // there too, through the images) and non-finite ones go to the exact walk.
+  bool xrows = false;
+  if (!tiled && c.force_path != 1 && !c.rows_are_cols && !c.radius_per_row && h->n_aliased == 0 && !h->windowed && c.radius > 0 &&
+      std::isfinite(c.radius) && h->n_sorted > 0 && h->n_sorted < (1ull << 28) && c.n_rows >= h->xrows_min_n) {
+    tiled = true;
+    xrows = true;
+  }
+  if (xrows) {
+    double xmax = 0;
+    for (int d = 0; d < D; ++d)
+      xmax = std::fmax(xmax, std::fmax(std::fabs(h->bmin[d]), std::fabs(h->bmax[d])) + (h->bmax[d] - h->bmin[d]));
+    xmax += c.radius;
+    const double delta = 256.0 * 2.220446049250313e-16 * xmax;
+    const double R = c.radius;
+    p->r2 = R * R;
+    p->r2lo = (R > 4 * delta) ? (R - 4 * delta) * (R - 4 * delta) : -1.0;
+    double stencil = 1;
+    for (int d = 0; d < D && tiled; ++d) {
+      const double wr = std::ceil(R * h->inv_side[d] - 1e-9);
+      if (!(wr < 1e6)) {
+        tiled = false;
+        break;
+      }
+      p->w[d] = std::max(1, (int)wr);
+      p->tolf[d] = std::fmax(4e-9, 8.0 * delta * h->inv_side[d]);
+      if (p->tolf[d] > 0.125) tiled = false;
+      stencil *= (2.0 * p->w[d] + 1.0);
+      if (p->w[d] >= 2) p->trim = 1;
+    }
+    if (stencil > 8192.0) tiled = false;
+    if (tiled) {
+      double M = 0;
+      for (int d = 0; d < D; ++d) M = std::fmax(M, (2.0 * p->w[d] + 2.0) * h->side[d]);
+      const double tol = 8.0 * (2.0 * D * std::ldexp(1.0, -22) * M / R + std::ldexp(1.0, -20));
+      double pr = p->r2 * (1.0 + tol);
+      float prf = (float)pr;
+      if ((double)prf < pr) prf = std::nextafterf(prf, INFINITY);
+      if (!(prf < 1.0e30f) || !(p->r2 > 1e-30)) tiled = false;
+      p->pre_r2 = prf;
+    }
+    if (tiled) {
+      const int rc = bucket_rows(h, c, p);
+      if (rc) return rc;
+    } else {
+      xrows = false;
+    }
+  }
   p->use_tiled = tiled ? 1 : 0;
   p->variant = h->matvec_variant;
   if (tiled && h->symmetric && c.b && c.y && !c.count && !c.hash) {
@@ -133,7 +252,7 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
     p->grab = (uint32_t)(gsz < 1 ? 1 : (gsz > TILED_GRAB ? TILED_GRAB : gsz));
   }
   if (tiled) {
-    ABR_CUDA(h, h->danger_list.reserve((size_t)c.n_rows * sizeof(uint32_t)));
+    if (!xrows) ABR_CUDA(h, h->danger_list.reserve((size_t)c.n_rows * sizeof(uint32_t)));
     p->danger_list = h->danger_list.as<uint32_t>();
     p->danger_capacity = (uint32_t)c.n_rows;
     // packed column records; b rides along when the block has one column
@@ -149,6 +268,21 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
     }
     h->launches += 1;
     p->posb = posb;
+    // buckets with many rows (clustered clouds) are split into row-batch work items; `max_bucket` is what the
+    // last VERIFIED build saw (an asynchronous build publishes it with abr_check_async) — a performance hint only
+    if (h->max_bucket > HEAVY_ROWS || xrows) {
+      const size_t cap = c.n_rows / HEAVY_ROWS + 2;
+      ABR_CUDA(h, h->heavy_list.reserve(cap * sizeof(uint2)));
+      p->heavy_list = h->heavy_list.as<uint2>();
+      p->heavy_capacity = (uint32_t)cap;
+      p->heavy_state = &h->d_scalars->heavy_state;
+      p->heavy_work = &h->d_scalars->heavy_work;
+    }
+    if (xrows) { // after k_pack_posb has reset the exact-walk list
+      k_rows_dropped<<<(unsigned)((c.n_rows + 255) / 256), 256, 0, h->stream>>>(p->xrow_alive, (uint32_t)c.n_rows, p->danger_count, p->danger_list,
+                                                                                p->danger_capacity);
+      h->launches += 1;
+    }
   }
   (void)BR;
   return ABR_OK;
@@ -159,7 +293,8 @@ static int launch_checked(Handle *h, const abr_matvec_plan &p, const F &f) {
   const int e = launch_plan<D, F, STATS>(p, f);
   if (e != 0) return check_cuda(h, (cudaError_t)e, "matvec launch");
   const bool sym = !STATS && symmetry<F>::value != 0 && p.symmetric && p.ytmp && p.row_bits;
-  h->counters[2] = p.use_tiled ? (sym ? 3 : 2) : 1;
+  const bool staged = p.variant == 1 && !sym && !p.xrow_pos;
+  h->counters[2] = p.use_tiled ? (sym ? 3 : 2) + ((!sym && !staged && p.heavy_list) ? 1 : 0) : 1;
   h->launches += h->counters[2];
   return ABR_OK;
 }
@@ -434,7 +569,7 @@ int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, cons
   if (rc) return rc;
   const int e = launch(&p, functor);
   if (e != 0) return check_cuda(h, (cudaError_t)e, "custom matvec launch");
-  h->counters[2] = p.use_tiled ? 2 : 1;
+  h->counters[2] = p.use_tiled ? 2 + ((p.heavy_list && !(p.variant == 1 && !p.xrow_pos)) ? 1 : 0) : 1;
   h->launches += h->counters[2];
   return ABR_OK;
 }

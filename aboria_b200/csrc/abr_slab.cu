@@ -42,9 +42,26 @@ k_patch_ghosts(uint32_t *__restrict__ bb, uint32_t *__restrict__ be, uint32_t n_
 // cls: 0 stays, 1 goes to the lower neighbour, 2 to the upper one; counts[cls] += 1
 __global__ void __launch_bounds__(256)
 k_slab_classify(const double *__restrict__ pos, uint32_t n, int D, double bmin0, double bmax0, double inv_side0, int S0, int periodic0, int lo_layer,
-                int hi_layer, uint8_t *__restrict__ cls, uint32_t *__restrict__ counts) {
+                int hi_layer, uint8_t *__restrict__ cls, uint32_t *__restrict__ counts, int32_t *__restrict__ layer_out) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t c = 0;
+  if (layer_out) { // layers only (abr_slab_layers)
+    if (p < n) {
+      double x = pos[(size_t)p * D];
+      int layer = -1;
+      if (isfinite(x)) {
+        if (periodic0) {
+          int guard = 0;
+          while (x < bmin0 && ++guard < (1 << 20)) x += (bmax0 - bmin0);
+          while (x >= bmax0 && ++guard < (1 << 20)) x -= (bmax0 - bmin0);
+        }
+        layer = (int)floor((x - bmin0) * inv_side0);
+        if (layer < 0 || layer >= S0) layer = -1;
+      }
+      layer_out[p] = layer;
+    }
+    return;
+  }
   if (p < n) {
     double x = pos[(size_t)p * D];
     if (isfinite(x)) {
@@ -119,7 +136,22 @@ int abr_slab_classify(abr_handle hh, const double *pos, size_t n, int lo_layer, 
   abr::fill_u32(h, counts3, 0u, 3);
   if (n == 0) return ABR_OK;
   abr::k_slab_classify<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(pos, (uint32_t)n, h->D, h->bmin[0], h->bmax[0], h->inv_side[0], (int)h->size[0],
-                                                                          h->periodic[0] ? 1 : 0, lo_layer, hi_layer, cls, counts3);
+                                                                          h->periodic[0] ? 1 : 0, lo_layer, hi_layer, cls, counts3, nullptr);
+  h->launches += 1;
+  ABR_CUDA(h, cudaGetLastError());
+  return ABR_OK;
+}
+
+int abr_slab_layers(abr_handle hh, const double *pos, size_t n, int32_t *layer_out) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return ABR_ERR_INVALID;
+  if (!h->domain_set) return abr::set_error(h, ABR_ERR_STATE, "slab_layers: domain has not been set");
+  if (n >= 0xFFFFFFF0ull) return abr::set_error(h, ABR_ERR_UNSUPPORTED, "slab_layers: too many particles");
+  if (n == 0) return ABR_OK;
+  if (!pos || !layer_out) return abr::set_error(h, ABR_ERR_INVALID, "slab_layers: null pointer");
+  ABR_CUDA(h, cudaSetDevice(h->device));
+  abr::k_slab_classify<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(pos, (uint32_t)n, h->D, h->bmin[0], h->bmax[0], h->inv_side[0], (int)h->size[0],
+                                                                          h->periodic[0] ? 1 : 0, 0, 0, nullptr, nullptr, layer_out);
   h->launches += 1;
   ABR_CUDA(h, cudaGetLastError());
   return ABR_OK;

@@ -248,17 +248,52 @@ class SlabParticles:
             raise ValueError("slab window would wrap onto itself: replicas only (SURVEY §8e)")
         self._big = None
 
+    def _layers_of(self, pos):
+        """bucket layer (dimension 0) of every particle, by the library's own key arithmetic; -1: the build would kill it"""
+        from ._lib import check
+
+        p = self.p
+        self._force_global()
+        p._sync_stream()
+        pos = pos.contiguous()
+        out = torch.empty(max(pos.shape[0], 1), dtype=torch.int32, device=self.device)
+        check(p._h, p._lib.abr_slab_layers(p._h, C.c_void_p(pos.data_ptr()), pos.shape[0], C.c_void_p(out.data_ptr())))
+        return out[: pos.shape[0]]
+
     def layer_histogram(self, pos):
         """global particle count per bucket layer of dimension 0 (one small all-reduce; set-up time only)"""
         S0 = int(self.size[0])
-        x = pos[:, 0]
-        L = float(self.high[0] - self.low[0])
-        if bool(self.periodic[0]):
-            x = x - torch.floor((x - float(self.low[0])) / L) * L
-        layer = torch.floor((x - float(self.low[0])) * (1.0 / float(self.side[0]))).long().clamp_(0, S0 - 1)
-        h = torch.bincount(layer, minlength=S0).to(torch.float64)
+        layer = self._layers_of(pos).long()
+        h = torch.bincount(layer[layer >= 0], minlength=S0).to(torch.float64)
         dist.all_reduce(h, group=self.group)
         return h.cpu().numpy()
+
+    def distribute(self, pos, columns=None):
+        """One-time distribution of a global cloud: every rank hands in ANY share of the particles
+        (e.g. a range of ids) and gets back the particles of its own slab (all-to-all by owner; set-up
+        time only — the per-step traffic of a moving cloud is the neighbour-only migrate()).  Particles
+        the build would kill (outside a non-periodic domain, non-finite) stay where they are."""
+        dev = self.device
+        columns = dict(columns or {})
+        layer = self._layers_of(pos).long()
+        his = torch.tensor([hi for _, hi in self.layers], dtype=torch.int64, device=dev)
+        owner = torch.bucketize(layer, his, right=True).clamp_(max=self.world - 1)
+        owner = torch.where(layer < 0, torch.full_like(owner, self.rank), owner)
+        order = torch.argsort(owner, stable=True)
+        send = torch.bincount(owner, minlength=self.world)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        send_l, recv_l = send.tolist(), recv.tolist()
+        allc = dict(columns)
+        allc["position"] = pos
+        out = {}
+        for k, t in allc.items():
+            src = t.index_select(0, order).contiguous()
+            dst = torch.empty((sum(recv_l),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_to_all_single(dst, src, recv_l, send_l, group=self.group)
+            out[k] = dst
+        new_pos = out.pop("position")
+        return new_pos, out
 
     def _neighbours(self):
         per0 = bool(self.periodic[0])
@@ -540,38 +575,49 @@ class SlabHostPipeline:
         torch.cuda.current_stream(self.dev).synchronize()
 
 
-def run_bench(args, rank, world, dev, metric, unit, emit=None):
-    """bench.py body for N > 1 (weak scaling: args.n_per_gpu particles per GPU
-    in the periodic unit cube, slabs along dimension 0)."""
+def run_bench(args, wl, rank, world, dev, metric, unit, emit=None):
+    """bench.py body for N > 1: slabs along dimension 0.  `wl` (bench.Workload) names the cloud: weak
+    scaling (n_per_gpu particles per GPU), strong scaling (n_total fixed) or the clustered cloud of
+    BASELINE config 4.  Every rank generates a RANGE OF IDS of the global cloud — particles anywhere in the
+    domain — and the owners are found by a one-time distribution (outside the timed region); the layer
+    split is balanced by the global per-layer particle histogram."""
     import json
     import os
     import sys
+    import time
 
     import aboria_b200 as ab
-    from aboria_b200 import kernels as K
     from aboria_b200 import synth
 
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from bench import EPS, N_LEAF, ClockSampler
+    from bench import N_LEAF, ClockSampler
 
     if emit is None:
         emit = lambda line: print(json.dumps(line))  # noqa: E731
 
-    n_total = args.n_per_gpu * world
-    box_side = (N_LEAF / float(n_total)) ** (1.0 / 3.0)
-    size = int(np.floor(1.0 / box_side))
-    side = 1.0 / size
-    radius = side
-    sp = SlabParticles(3, 0.0, 1.0, True, n_total, N_LEAF, radius, rank, world, dev)
-    # this rank's particles: uniform in its slab, share proportional to its layer count
-    shares = [int(round(n_total * (hi - lo) / size)) for lo, hi in sp.layers]
-    shares[-1] = n_total - sum(shares[:-1])
-    n_mine, first_id = shares[rank], sum(shares[:rank])
-    x_lo, x_hi = sp.slab_bounds()
-    pos_unsorted = synth.torch_uniform_positions(n_mine, 3, [x_lo, 0.0, 0.0], [x_hi, 1.0, 1.0], synth.SEED, first_id, dev)
-    # b is indexed by post-reorder position, as in the single-GPU bench (src/Kernels.h:745-748)
-    b_owned = torch.from_numpy(synth.vector(n_mine, first_id=first_id)).to(dev)
-    op = ab.create_sparse_operator(sp.p, sp.p, radius, K.inv_dist(EPS))
+    n_total = wl.n_total
+    radius = wl.radius
+    sp = SlabParticles(3, 0.0, 1.0, wl.periodic, n_total, N_LEAF, radius, rank, world, dev)
+    size = int(sp.size[0])
+    # this rank's share of the global cloud (a range of ids), then to the owners
+    first_id, n_share = wl.share(rank)
+    pos_any = wl.positions(rank, dev)
+    gid = torch.arange(first_id, first_id + n_share, dtype=torch.int64, device=dev)
+    hist = sp.layer_histogram(pos_any)
+    sp.set_layers(plan_layers_balanced(hist, world))
+    per_rank = [int(hist[lo:hi].sum()) for lo, hi in sp.layers]
+    pos_unsorted, cols = sp.distribute(pos_any, {"gid": gid})
+    del pos_any, gid
+    n_mine = pos_unsorted.shape[0]
+    assert n_mine == per_rank[rank], (n_mine, per_rank)
+    # b by GLOBAL particle id (compared across GPU counts by id); the product indexes it by post-reorder position
+    b_by_id_mine = torch.from_numpy(synth.vector(n_total)).to(dev)[cols["gid"]] if n_total <= 64_000_000 else None
+    if b_by_id_mine is None:  # large clouds: generate only this rank's values
+        ids_np = cols["gid"].cpu().numpy().astype(np.uint64)
+        b_by_id_mine = torch.from_numpy(synth.uniform01(synth.SEED + 1, ids_np)).to(dev)
+        del ids_np
+    del cols
+    op = ab.create_sparse_operator(sp.p, sp.p, radius, wl.kernel)
     state = {}
 
     def step(evs=None):
@@ -582,7 +628,11 @@ def run_bench(args, rank, world, dev, metric, unit, emit=None):
         b_local = state.get("b_local")
         if b_local is None or b_local.shape[0] != sp.ex.n_local:
             b_local = state["b_local"] = torch.zeros(sp.ex.n_local, dtype=torch.float64, device=dev)
-        b_local[sp.ex.own_begin: sp.ex.own_end].copy_(b_owned)  # owned entries; ghosts come from the neighbours
+        # b is indexed by post-reorder position (src/Kernels.h:745-748); the input is the same every step, so is
+        # the order: the owned entries of b are gathered once, the ghosts come from the neighbours every product
+        if "b_sorted" not in state:
+            state["b_sorted"] = b_by_id_mine[sp.order_owned.long()]
+        b_local[sp.ex.own_begin: sp.ex.own_end].copy_(state["b_sorted"])
         y = sp.matvec(op, b_local)
         if evs is not None:
             evs.append(torch.cuda.Event(enable_timing=True))
@@ -598,12 +648,14 @@ def run_bench(args, rank, world, dev, metric, unit, emit=None):
     # density must have (the single-GPU count of the same workload: tests/test_gpu_parity.py::test_c5_32m_sampled_oracle);
     # (2) sampled owned rows: the cell-tiled kernel on the ghost-padded local set finds exactly the pair sets
     # (count + hash) the exact per-row iterator walk finds on this rank
-    expect = n_total * (1.0 + 4.0 / 3.0 * np.pi * radius**3 * n_total)
-    assert abs(pairs - expect) / expect < 2e-3, f"global pair count {pairs} differs from the expectation {expect:.6g} of a uniform cloud"
+    expect = wl.expected_pairs()
+    if expect is not None:
+        assert abs(pairs - expect) / expect < 2e-3, f"global pair count {pairs} differs from the expectation {expect:.6g} of a uniform cloud"
     sub = torch.arange(sp.ex.own_begin, sp.ex.own_end, 4001, device=dev)
     cnt_w, hs_w = sp.p.pair_stats(radius, rows=sp.p.get("position")[sub].contiguous(), path=1)
     assert bool((cnt[sub] == cnt_w).all()) and bool((hs[sub] == hs_w).all()), f"rank {rank}: tiled pair sets differ from the exact walk on sampled owned rows"
-    del hs, cnt_w, hs_w
+    pairs_rank = int(sp.owned(cnt).long().sum().item())
+    del hs, cnt_w, hs_w, cnt
     for _ in range(max(0, args.warmup - 1)):
         step()
     torch.cuda.synchronize()
@@ -620,7 +672,8 @@ def run_bench(args, rank, world, dev, metric, unit, emit=None):
         step(evs)
     e1.record()
     torch.cuda.synchronize()
-    ms_mv = float(np.mean([evs[2 * k].elapsed_time(evs[2 * k + 1]) for k in range(args.steps)]))  # halo exchange of b + product, this rank
+    ms_mv = float(np.mean([evs[2 * k].elapsed_time(evs[2 * k + 1]) for k in range(args.steps)]))  # b gather + halo exchange of b + product, this rank
+    ms_build = float(np.mean([(evs[2 * k - 1] if k else e0).elapsed_time(evs[2 * k]) for k in range(args.steps)]))
     ms_local = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.barrier()
     dist.all_reduce(ms_local, op=dist.ReduceOp.MAX)  # max over ranks
@@ -628,15 +681,17 @@ def run_bench(args, rank, world, dev, metric, unit, emit=None):
     launches = sp.p.last_counters()["total_launches"] - launches0
     ms_per_step = float(ms_local.item()) / args.steps
     value = pairs / (ms_per_step * 1e-3)
+    per_rank_ms = torch.zeros(world, 3, dtype=torch.float64, device=dev)
+    per_rank_ms[rank, 0], per_rank_ms[rank, 1], per_rank_ms[rank, 2] = ms_build, ms_mv, float(n_mine)
+    dist.all_reduce(per_rank_ms)
 
     # end-to-end with host buffers: H2D of positions and b, D2H of y, every step
     pos_host = torch.empty((n_mine, 3), dtype=torch.float64, pin_memory=True)
     pos_host.copy_(pos_unsorted)
+    b_sorted = state["b_sorted"]
     b_host = torch.empty(n_mine, dtype=torch.float64, pin_memory=True)
-    b_host.copy_(b_owned)
+    b_host.copy_(b_sorted)
     y_host = torch.empty(n_mine, dtype=torch.float64, pin_memory=True)
-
-    import time
 
     pipe = SlabHostPipeline(sp, op, n_mine, dev)
     y_hosts = [y_host, torch.empty(n_mine, dtype=torch.float64, pin_memory=True)]
@@ -659,29 +714,35 @@ def run_bench(args, rank, world, dev, metric, unit, emit=None):
     for yh in y_hosts:
         rel = float(torch.linalg.norm(yh - y_ref) / torch.linalg.norm(y_ref))
         assert rel <= 1e-12, f"rank {rank}: pipelined e2e result differs (rel L2 {rel:.3e})"
+    # a checksum of the product by particle id: the same number at every GPU count (up to summation order)
+    chk = torch.stack([y_ref.sum().to(dev), (y_ref * y_ref).sum().to(dev)])
+    dist.all_reduce(chk)
     halo = torch.tensor([float(sp.ex.n_ghost_lo + sp.ex.n_ghost_hi)], dtype=torch.float64, device=dev)
     dist.all_reduce(halo)
+    n_all = torch.tensor([float(n_mine)], dtype=torch.float64, device=dev)
+    dist.all_reduce(n_all)
     if rank == 0:
         from bench import measured_peaks
 
         hbm_peak, peak_src = measured_peaks()
         n_loc, n_own = sp.ex.n_local, sp.ex.n_own
-        ncells_loc = int(sp.p.n_buckets)
+        ncells_loc = int(sp.per_layer) * (sp.own_n + 2 * sp.w)
         mv_bytes = n_own * (8 * 3 + 8) + n_loc * (8 * 3 + 8) + 8 * ncells_loc  # SURVEY §8d B_mv for this rank's rows / columns
-        pairs_rank = int(sp.owned(cnt).long().sum().item())
-        roofline = {"bound": "hbm", "kernel": "abr::tiled_kernel<3, InvDistFast> on rank 0 (sparse matvec incl. the halo exchange of b)",
+        roofline = {"bound": "hbm", "kernel": f"abr::tiled_kernel<3, {wl.kernel_name}> on rank 0 (sparse matvec incl. the halo exchange of b)",
                     "achieved": mv_bytes / (ms_mv * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": mv_bytes / (ms_mv * 1e-3) / 1e9 / hbm_peak,
                     "traffic": None, "algorithmic_bytes": mv_bytes, "peak_source": peak_src, "ms_matvec_rank0": ms_mv,
                     "pairs_per_s_matvec_only_rank0": pairs_rank / (ms_mv * 1e-3),
-                    "note": "the product is instruction-issue / fp64 bound, not HBM bound (DESIGN.md §4.2); same kernel as the 1-GPU line"}
+                    "note": "the product is instruction-issue / LSU bound, not HBM bound (DESIGN.md §4.2); same kernel as the 1-GPU line"}
+        prm = per_rank_ms.cpu().numpy()
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c5-weak: 3-D periodic unit cube, uniform random, n_leaf=10, r=bucket side, kernel 1/(|dx|+0.1), fp64; slabs along dim 0, NCCL halo exchange",
-                       "n_particles_per_gpu": args.n_per_gpu, "n_particles": n_total, "buckets": size ** 3, "radius": radius, "pairs_per_matvec": pairs,
-                       "halo_particles_total": int(halo.item()), "parallelism": f"slab{world}",
-                       "l2": "inputs exceed the 126 MB L2; no flush needed"},
-            "e2e": {"value": pairs / e2e_sec, "unit": unit, "h2d_bytes_per_step": int(n_mine * 32 * world), "d2h_bytes_per_step": int(n_mine * 8 * world),
+            "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name + "; slabs along dim 0 (layer split balanced by particle count), NCCL halo exchange",
+                       "n_particles_per_gpu": [int(v) for v in prm[:, 2]], "n_particles": int(n_all.item()), "buckets": int(np.prod(sp.size)), "radius": radius,
+                       "pairs_per_matvec": pairs, "halo_particles_total": int(halo.item()), "parallelism": f"slab{world}", "layers": [list(x) for x in sp.layers],
+                       "y_checksum": [float(chk[0]), float(chk[1])], "l2": "inputs exceed the 126 MB L2; no flush needed"},
+            "per_rank": {"ms_build": [float(v) for v in prm[:, 0]], "ms_matvec": [float(v) for v in prm[:, 1]]},
+            "e2e": {"value": pairs / e2e_sec, "unit": unit, "h2d_bytes_per_step": int(n_all.item()) * 32, "d2h_bytes_per_step": int(n_all.item()) * 8,
                     "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps,
                     "how": "SlabHostPipeline per rank: pinned host buffers; uploads of step k on a copy stream while step k-1 computes, download of y on a third stream; wall clock, max over ranks"},
             "gpu_launches": int(launches) * world, "clocks": clocks,

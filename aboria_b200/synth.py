@@ -36,10 +36,10 @@ def vector(n, seed=SEED + 1, first_id=0, width=1):
     return uniform01(seed, ids)
 
 
-def clustered_positions(n, D=3, n_blobs=64, sigma=0.03, background=0.1, seed=SEED, periodic_dims=(True, True, False)):
+def clustered_positions(n, D=3, n_blobs=64, sigma=0.03, background=0.1, seed=SEED, periodic_dims=(True, True, False), first_id=0):
     """Gaussian blobs + uniform background in [0,1)^D; coordinates
-    are wrapped in periodic dims and reflected in the others."""
-    ids = np.arange(n, dtype=np.uint64)
+    are wrapped in periodic dims and reflected in the others.  Particles first_id .. first_id+n-1."""
+    ids = np.arange(first_id, first_id + n, dtype=np.uint64)
     u = uniform01(seed + 7, ids)
     centres = uniform01(seed + 11, np.arange(n_blobs * D, dtype=np.uint64)).reshape(n_blobs, D)
     blob = (uniform01(seed + 13, ids) * n_blobs).astype(np.int64) % n_blobs
@@ -48,7 +48,7 @@ def clustered_positions(n, D=3, n_blobs=64, sigma=0.03, background=0.1, seed=SEE
     # Box-Muller
     g = np.sqrt(-2.0 * np.log(1.0 - uu[:, :D])) * np.cos(2.0 * np.pi * uu[:, D:])
     p = centres[blob] + sigma * g
-    bg = uniform_positions(n, D, seed=seed + 19)
+    bg = uniform_positions(n, D, seed=seed + 19, first_id=first_id)
     p = np.where((u < background)[:, None], bg, p)
     for d in range(D):
         if periodic_dims[d] if d < len(periodic_dims) else False:

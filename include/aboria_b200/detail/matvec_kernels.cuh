@@ -63,6 +63,18 @@ struct abr_matvec_plan {
   cudaStream_t stream;
   int sm_count;
   int walk_only_list; // walk kernel processes danger_list instead of all rows
+  // tiled path with a row set that is NOT the column set (create_sparse_operator(test, knots, ...),
+  // tests/rbf_interpolation.h:326): the row points bucketed into the column grid by an internal build
+  const double *xrow_pos;     // row positions sorted by column-grid bucket (null: rows are the columns)
+  const uint32_t *xrow_bb, *xrow_be; // per bucket: range of sorted rows
+  const int32_t *xrow_index;  // original index of sorted row k (y, row columns and the exact-walk list use it)
+  const uint8_t *xrow_alive;  // 0: the row point was dropped by the row build (outside the domain): exact walk
+  // heavy buckets (clustered clouds): (bucket, first batch number) items appended by the first launch, consumed by the second
+  uint2 *heavy_list;
+  uint32_t heavy_capacity;
+  unsigned long long *heavy_state; // items << 40 | row batches
+  uint32_t *heavy_work;
+  int heavy_phase;    // 1: the second launch (consumes the heavy list)
   int symmetric;      // tiled path: half stencil + y[j] scatter for functors that declare SYMMETRY (see tiled_kernel)
   double *ytmp;       //   zeroed scratch the symmetric kernel accumulates into (n_rows * BR)
   uint32_t *row_bits; //   one bit per row: result comes from the exact walk, not from ytmp
@@ -286,6 +298,7 @@ constexpr int ROW_BITS = 4;
 #define ABR_WQ 256
 #endif
 constexpr int WQ = ABR_WQ;            // pairs compacted per drain pass
+constexpr uint32_t HEAVY_ROWS = 64;   // a bucket with more rows than this is split into row-batch work items (second launch)
 constexpr int PCOL = 16;              // columns of the partial-sum table (lanes l and l+16 share one)
 
 // resident CTAs per SM the tiled kernel is compiled for: 7 (72 registers) by default; a
@@ -341,6 +354,7 @@ template <int D, class F, bool STATS> struct WarpSmem {
   uint32_t danger;
   uint32_t danger_pre;                    // rows flagged before the candidates are seen (symmetric kernel: their partners are flagged too)
   uint32_t pad_[2];
+  uint32_t rowid[RB];                     // index of the batch's rows in the caller's numbering (y, row columns)
   double rowsb[F::BC][RB];                // b of the rows (symmetric kernel only: y[j] += K(j,i) b[i])
   SymCtx sym;
 };
@@ -410,7 +424,7 @@ __device__ __forceinline__ void flag_row(const SymCtx &p, uint32_t j) {
 // lane utilisation instead of on the ~15 % of lanes that pass the cut-off test.
 // dx and |dx|^2 are recomputed here in fp64 with the reference's operations in
 // the reference's order.
-template <int D, class F, bool STATS, int SYM, class SM>
+template <int D, class F, bool STATS, int SYM, bool GEN, class SM>
 __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, int lane, uint32_t cnt, uint32_t r0,
                                           const double (*rowp)[SM::RB], uint32_t image_id) {
   constexpr int BR = F::BR, BC = F::BC;
@@ -495,7 +509,7 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
         // F is evaluated unconditionally (it is pure; j, i are valid indices even for
         // a pair that fails the test); only the accumulation is predicated
         double blk[BR * BC];
-        f(dx, d2, r0 + i, j, blk);
+        f(dx, d2, GEN ? sm.rowid[i] : r0 + i, j, blk);
         double s[BR];
   #pragma unroll
         for (int a2 = 0; a2 < BR; ++a2) {
@@ -568,7 +582,7 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 // pointer bump; the exact un-fused fp64 predicate is applied to them in
 // drain_queues.  (6.45 candidates are tested per accepted pair, so this loop is
 // kept off the fp64 pipe altogether.)
-template <int D, class F, bool STATS, int SYM, class SM>
+template <int D, class F, bool STATS, int SYM, bool GEN, class SM>
 __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_r2, const F &f, int lane,
                                           const float *pA, const float *pB, uint32_t jA, uint32_t jB, bool vA, bool vB,
                                           int nr, const double (*rowp)[SM::RB], uint32_t image_id, uint32_t r0,
@@ -609,7 +623,7 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
     eA += 2u;
     eB += 2u;
     if (__any_sync(0xFFFFFFFFu, qa >= q0 + QDRAIN * 128u)) {
-      drain_queues<D, F, STATS, SYM>(sm, dc, f, lane, (qa - q0) >> 7, r0, rowp, image_id);
+      drain_queues<D, F, STATS, SYM, GEN>(sm, dc, f, lane, (qa - q0) >> 7, r0, rowp, image_id);
       qa = q0;
     }
   }
@@ -630,7 +644,10 @@ __device__ __forceinline__ void test_rows(SM &sm, const DrainCtx &dc, float pre_
 #ifndef ABR_SYM_CTAS_LESS
 #define ABR_SYM_CTAS_LESS 1 // the symmetric form keeps a little more state: one resident CTA less per SM
 #endif
-template <int D, class F, bool STATS, int SYM = 0>
+// GEN: the general form — rows from another particle set bucketed into this grid (plan.xrow_*) and heavy
+// buckets split into row-batch work items (plan.heavy_*).  GEN = false compiles both away: the common
+// rows == columns product on a cloud without heavy buckets pays nothing for them (measured: 1.8 %).
+template <int D, class F, bool STATS, int SYM = 0, bool GEN = false>
 __global__ void __launch_bounds__(TILED_THREADS, (TiledCfg<D, F, STATS>::CTAS - (SYM != 0 && TiledCfg<D, F, STATS>::CTAS > 5 ? ABR_SYM_CTAS_LESS : 0)))
 tiled_kernel(const abr_matvec_plan p, const F f) {
   constexpr int BR = F::BR;
@@ -698,51 +715,27 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
   od_first[0] = 0;
   decode_run(lane, od_first, wz_first);
 
-  while (true) {
-    // warp-level dynamic scheduler: no block barrier anywhere in this kernel
-    uint32_t grab = 0;
-    if (lane == 0) grab = atomicAdd(p.work_counter, p.grab);
-    grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
-    if (grab >= tcount) break;
-    const uint32_t grab_end = min(grab + p.grab, tcount);
-
-    // bucket coordinates of the first bucket of the grab (inverse of collapse_index);
-    // the following ones are reached by counting up, last dimension fastest
-    int tc[D];
-    {
-      const uint32_t cell = tfirst + grab;
-      uint32_t rem = cell;
+  // everything a target bucket needs; `batch` (heavy launch only): which row batch of the bucket
+  int tc[D];
 #pragma unroll
-      for (int d = D - 1; d >= 0; --d) {
-        tc[d] = (int)(rem % (uint32_t)g.size[d]);
-        rem /= (uint32_t)g.size[d];
-      }
-      if (D > 1) { // local layer -> global layer (slab window; identity on a single GPU)
-        int gl = g.win_lo + (int)(cell / per_layer);
-        if (gl < 0) gl += g.size[0];
-        if (gl >= g.size[0]) gl -= g.size[0];
-        tc[0] = gl;
-      }
-    }
-    --tc[L]; // the loop advances before it works
-
-    for (uint32_t cell = tfirst + grab; cell < tfirst + grab_end; ++cell) {
-      // advance the bucket coordinates to `cell`
-      if (++tc[L] == S) {
-        if (D > 1) {
-          tc[L] = 0;
-          if (D > 2) {
-            if (++tc[D > 2 ? 1 : 0] == g.size[D > 2 ? 1 : 0]) {
-              tc[D > 2 ? 1 : 0] = 0;
-              if (++tc[0] >= g.size[0]) tc[0] -= g.size[0]; // next (global) layer of the window
-            }
-          } else {
-            if (++tc[0] >= g.size[0]) tc[0] -= g.size[0];
-          }
+  for (int d = 0; d < D; ++d) tc[d] = 0;
+  const bool HEAVY = GEN && p.heavy_phase != 0;
+  auto do_cell = [&](const uint32_t cell, const uint32_t batch) {
+      const bool xrows = GEN && SYM == 0 && p.xrow_pos != nullptr; // rows from another particle set, bucketed into this grid
+      const uint32_t rb = xrows ? p.xrow_bb[cell] : bbeg[cell], re = xrows ? p.xrow_be[cell] : bend[cell];
+      if (rb == re) return;
+      if (GEN && !HEAVY && p.heavy_list && re - rb > HEAVY_ROWS) {
+        // a heavy bucket (clustered clouds): its row batches become independent work items of the second launch
+        if (lane == 0) {
+          const uint32_t nbatch = (re - rb + RB - 1) / RB;
+          const unsigned long long old = atomicAdd(p.heavy_state, (1ull << 40) + nbatch);
+          const uint32_t slot = (uint32_t)(old >> 40);
+          if (slot < p.heavy_capacity) p.heavy_list[slot] = make_uint2(cell, (uint32_t)(old & ((1ull << 40) - 1ull)));
         }
+        return;
       }
-      const uint32_t rb = bbeg[cell], re = bend[cell];
-      if (rb == re) continue;
+      const uint32_t r_lo = HEAVY ? rb + batch * RB : rb, r_hi = HEAVY ? min(re, r_lo + RB) : re;
+      const double *__restrict__ rpos = xrows ? p.xrow_pos : pos;
       const bool owned_target = SYM == 0 || first_cell == 0u || cell >= first_cell; // else: a lower ghost layer (symmetric kernel on a slab rank)
       const int zlo = tc[L] - p.w[L], zhi = tc[L] + p.w[L];
       // does any neighbour of this bucket lie across a periodic boundary / outside?
@@ -755,7 +748,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
 #pragma unroll
       for (int d = 0; d < D; ++d) origin[d] = g.bmin[d] + (double)(tc[d] - p.w[d]) * g.side[d];
 
-      for (uint32_t r0 = rb; r0 < re; r0 += RB) {
+      for (uint32_t r0 = r_lo; r0 < r_hi; r0 += RB) {
         const int nr = (int)min((uint32_t)RB, re - r0);
         // ---- load the rows of this batch, flag rounding-sensitive ones ----
         bool my_danger = false;
@@ -763,7 +756,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
         if (lane < nr) {
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            const double r = pos[(size_t)(r0 + lane) * D + d];
+            const double r = rpos[(size_t)(r0 + lane) * D + d];
             sm.rows0[d][lane] = r;
             const double fl = (r - g.bmin[d]) * g.inv_side[d];
             const double fr = fl - floor(fl);
@@ -772,6 +765,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
           }
         }
         if (lane == 0) sm.danger = 0;
+        if (GEN && lane < nr) sm.rowid[lane] = xrows ? (uint32_t)p.xrow_index[r0 + lane] : r0 + lane;
         if (SYM != 0) {
           if (lane < nr) {
 #pragma unroll
@@ -877,13 +871,13 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
 #pragma unroll
               for (int d = 0; d < D; ++d) pj[h][d] = (float)(rec[d] - origin[d]);
             }
-            test_rows<D, F, STATS, SYM>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
+            test_rows<D, F, STATS, SYM, GEN>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rows0,
                                         image_id0, r0, qa);
           }
         }
         // pairs queued so far belong to the primary image
         if (__any_sync(0xFFFFFFFFu, qa != q0)) {
-          drain_queues<D, F, STATS, SYM>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rows0, image_id0);
+          drain_queues<D, F, STATS, SYM, GEN>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rows0, image_id0);
           qa = q0;
         }
         if (boundary && owned_target) {
@@ -948,12 +942,12 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) pj[h][d] = (float)((rec[d] - (double)img[d] * g.L[d]) - origin[d]);
                   }
-                  test_rows<D, F, STATS, SYM>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
+                  test_rows<D, F, STATS, SYM, GEN>(sm, dc, pre_r2, f, lane, pj[0], pj[1], jj[0], jj[1], vv[0], vv[1], nr, sm.rowsS,
                                               image_id, r0, qa);
                 }
                 // leave no pair of this image in the queues (rowsS is reused)
                 if (__any_sync(0xFFFFFFFFu, qa != q0)) {
-                  drain_queues<D, F, STATS, SYM>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rowsS, image_id);
+                  drain_queues<D, F, STATS, SYM, GEN>(sm, dc, f, lane, (qa - q0) >> 7, r0, sm.rowsS, image_id);
                   qa = q0;
                 }
               }
@@ -983,7 +977,7 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
               flag_row(sm.sym, r0 + lane); // a partner's drain may have flagged it already
             } else {
               const uint32_t slot = atomicAdd(p.danger_count, 1u);
-              if (slot < p.danger_capacity) p.danger_list[slot] = r0 + lane;
+              if (slot < p.danger_capacity) p.danger_list[slot] = GEN ? sm.rowid[lane] : r0 + lane;
             }
           } else if (STATS) {
             unsigned long long c = 0, hsum = 0;
@@ -992,8 +986,9 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
               c += sm.part[0][lane][(k + lane) & (PCOL - 1)];
               hsum += sm.part[1][lane][(k + lane) & (PCOL - 1)];
             }
-            if (p.stat_count) p.stat_count[r0 + lane] = (uint32_t)c;
-            if (p.stat_hash) p.stat_hash[r0 + lane] = hsum;
+            const uint32_t orow = GEN ? sm.rowid[lane] : r0 + lane;
+            if (p.stat_count) p.stat_count[orow] = (uint32_t)c;
+            if (p.stat_hash) p.stat_hash[orow] = hsum;
           } else {
 #pragma unroll
             for (int a2 = 0; a2 < NACC; ++a2) {
@@ -1003,16 +998,95 @@ tiled_kernel(const abr_matvec_plan p, const F f) {
               if (SYM != 0)
                 atomicAdd(&p.ytmp[(size_t)(r0 + lane) * BR + a2], s); // partners add to the same entry concurrently
               else
-                p.y[(size_t)(r0 + lane) * BR + a2] += s;
+                p.y[(size_t)(GEN ? sm.rowid[lane] : r0 + lane) * BR + a2] += s;
             }
           }
         }
         __syncwarp();
       }
+  };
+
+  if (HEAVY) {
+    // second launch: (heavy bucket, row batch) items handed out one at a time
+    const unsigned long long st = *p.heavy_state;
+    const uint32_t n_items = min((uint32_t)(st >> 40), p.heavy_capacity);
+    const uint32_t n_batches = (uint32_t)(st & ((1ull << 40) - 1ull));
+    while (true) {
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(p.heavy_work, 1u);
+      t = __shfl_sync(0xFFFFFFFFu, t, 0);
+      if (t >= n_batches) break;
+      // the item whose batches contain t (the list is ordered by its base)
+      uint32_t lo = 0, hi = n_items;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.heavy_list[mid].y <= t) lo = mid; else hi = mid;
+      }
+      const uint2 item = p.heavy_list[lo];
+      const uint32_t cell = item.x;
+      uint32_t rem = cell;
+#pragma unroll
+      for (int d = D - 1; d >= 0; --d) {
+        tc[d] = (int)(rem % (uint32_t)g.size[d]);
+        rem /= (uint32_t)g.size[d];
+      }
+      if (D > 1) {
+        int gl = g.win_lo + (int)(cell / per_layer);
+        if (gl < 0) gl += g.size[0];
+        if (gl >= g.size[0]) gl -= g.size[0];
+        tc[0] = gl;
+      }
+      do_cell(cell, t - item.y);
+    }
+    return;
+  }
+
+  while (true) {
+    // warp-level dynamic scheduler: no block barrier anywhere in this kernel
+    uint32_t grab = 0;
+    if (lane == 0) grab = atomicAdd(p.work_counter, p.grab);
+    grab = __shfl_sync(0xFFFFFFFFu, grab, 0);
+    if (grab >= tcount) break;
+    const uint32_t grab_end = min(grab + p.grab, tcount);
+
+    // bucket coordinates of the first bucket of the grab (inverse of collapse_index);
+    // the following ones are reached by counting up, last dimension fastest
+    {
+      const uint32_t cell = tfirst + grab;
+      uint32_t rem = cell;
+#pragma unroll
+      for (int d = D - 1; d >= 0; --d) {
+        tc[d] = (int)(rem % (uint32_t)g.size[d]);
+        rem /= (uint32_t)g.size[d];
+      }
+      if (D > 1) { // local layer -> global layer (slab window; identity on a single GPU)
+        int gl = g.win_lo + (int)(cell / per_layer);
+        if (gl < 0) gl += g.size[0];
+        if (gl >= g.size[0]) gl -= g.size[0];
+        tc[0] = gl;
+      }
+    }
+    --tc[L]; // the loop advances before it works
+
+    for (uint32_t cell = tfirst + grab; cell < tfirst + grab_end; ++cell) {
+      // advance the bucket coordinates to `cell`
+      if (++tc[L] == S) {
+        if (D > 1) {
+          tc[L] = 0;
+          if (D > 2) {
+            if (++tc[D > 2 ? 1 : 0] == g.size[D > 2 ? 1 : 0]) {
+              tc[D > 2 ? 1 : 0] = 0;
+              if (++tc[0] >= g.size[0]) tc[0] -= g.size[0]; // next (global) layer of the window
+            }
+          } else {
+            if (++tc[0] >= g.size[0]) tc[0] -= g.size[0];
+          }
+        }
+      }
+      do_cell(cell, 0u);
     }
   }
 }
-
 // ---------------------------------------------------------------------------
 // staged_kernel — the cell-tiled product with the candidate records staged in
 // shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, SASS UBLKCP /
@@ -1671,9 +1745,12 @@ template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_pl
   if (p.use_tiled) {
     constexpr int SYMV = STATS ? 0 : symmetry<F>::value;
     const bool sym = SYMV != 0 && p.symmetric && p.ytmp && p.row_bits;
-    const bool staged = p.variant == 1 && !sym;
+    const bool staged = p.variant == 1 && !sym && !p.xrow_pos;
     const size_t smem = (staged ? sizeof(StagedSmem<D, F, STATS>) : sizeof(WarpSmem<D, F, STATS>)) * TILED_WARPS;
-    void (*kern)(const abr_matvec_plan, const F) = staged ? staged_kernel<D, F, STATS> : (sym ? tiled_kernel<D, F, STATS, SYMV> : tiled_kernel<D, F, STATS, 0>);
+    const bool gen = !sym && !staged && (p.xrow_pos || p.heavy_list);
+    void (*kern)(const abr_matvec_plan, const F) = staged ? staged_kernel<D, F, STATS>
+                                                    : (sym ? tiled_kernel<D, F, STATS, SYMV, false>
+                                                           : (gen ? tiled_kernel<D, F, STATS, 0, true> : tiled_kernel<D, F, STATS, 0, false>));
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
@@ -1692,6 +1769,12 @@ template <int D, class F, bool STATS> inline int launch_plan(const abr_matvec_pl
     if (grid > max_chunks) grid = max_chunks;
     if (grid < 1) grid = 1;
     kern<<<grid, TILED_THREADS, smem, p.stream>>>(p, f);
+    if (gen && p.heavy_list) {
+      // heavy buckets of the first launch, one (bucket, row batch) per warp at a time; returns at once when there are none
+      abr_matvec_plan ph = p;
+      ph.heavy_phase = 1;
+      kern<<<grid, TILED_THREADS, smem, p.stream>>>(ph, f);
+    }
     if (sym) k_sym_combine<<<p.sm_count * 8, 256, 0, p.stream>>>(p, F::BR);
     // rows handed over by the tiled kernel: exact per-row walk
     abr_matvec_plan p2 = p;

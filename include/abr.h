@@ -148,6 +148,10 @@ int abr_celllist_patch_ghosts(abr_handle h, const double *pos_local, size_t n_gh
  * class k (device, 3 x u32).  Particles outside a non-periodic domain or non-finite stay (the
  * build kills them). */
 int abr_slab_classify(abr_handle h, const double *pos, size_t n, int lo_layer, int hi_layer, uint8_t *cls, uint32_t *counts3);
+/* The bucket layer of dimension 0 of every particle (the same arithmetic as the build's key; -1 for a
+ * particle the build would kill): what an initial distribution of a global cloud over the slab owners,
+ * or a per-layer histogram for a balanced split, needs. */
+int abr_slab_layers(abr_handle h, const double *pos, size_t n, int32_t *layer_out);
 
 /* neighbour_search_base::update_positions (src/NeighbourSearchBase.h:350-495)
  * for the ordered case + CellListOrdered::update_positions_impl

@@ -70,7 +70,7 @@ def test_custom_functor_rows_are_cols(N, r, periodic):
     check(p._h, L.custom_weighted_inv_dist(p._h, pt.data_ptr(), N, 1, wt.data_ptr(), wt.data_ptr(), 0.1, r, bt.data_ptr(), y.data_ptr(), C.byref(npairs)))
     torch.cuda.synchronize()
     assert npairs.value == npairs_o
-    assert p.last_counters()["launches"] == 2  # the cell-tiled kernel (+ its exact-walk pass), not the per-row walk
+    assert p.last_counters()["launches"] >= 2  # the cell-tiled kernel + its exact-walk pass (+ a heavy-bucket launch), not the per-row walk (1)
     assert rel_l2(y.cpu().numpy(), y_o) <= TOL
 
     # 2 x 1 block functor

@@ -203,7 +203,7 @@ def test_matvec_c1_inverse_distance():
     # evaluate accumulates (y += K b): applying twice doubles
     op.evaluate(y2, bt)
     assert rel_l2(y2.cpu().numpy(), 2 * y_o) <= TOL
-    assert p.last_counters()["launches"] == 2  # tiled kernel + exact-walk kernel
+    assert p.last_counters()["launches"] >= 2  # tiled kernel + exact-walk kernel (+ heavy-bucket launch), not the per-row walk (1)
 
 
 def test_matvec_all_kernels_small():

@@ -1,0 +1,17 @@
+mkdir -p gpurun_out
+for rep in 1 2; do
+for v in C A; do
+  if [ $v = C ]; then export ABR_LIB_PATH=$PWD/aboria_b200/libC/libabr.so; else unset ABR_LIB_PATH; fi
+  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/r2k_bench_$v$rep.json 2> gpurun_out/r2k_bench_$v$rep.err
+done; done
+unset ABR_LIB_PATH
+python - <<PY
+import json
+for v in ("C1","A1","C2","A2"):
+    try:
+        d=json.loads(open(f"gpurun_out/r2k_bench_{v}.json").read().strip().splitlines()[-1])
+        print(v, d["ms_per_step"], d["ms_build"], d["ms_matvec"], d["value"], d["e2e"]["ms_per_step"], d["clocks"])
+    except Exception as e:
+        print(v, "fail", e, open(f"gpurun_out/r2k_bench_{v}.err").read()[-1500:])
+PY
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8) > gpurun_out/r2k_tests.log; tail -8 gpurun_out/r2k_tests.log
