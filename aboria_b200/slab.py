@@ -268,6 +268,18 @@ class SlabParticles:
         dist.all_reduce(h, group=self.group)
         return h.cpu().numpy()
 
+    def cost_histogram(self, pos, cost):
+        """global sum of a per-particle cost (e.g. accepted pairs per row from pair_stats) per bucket layer of
+        dimension 0: the histogram to balance by when the work per particle is far from uniform (clustered
+        clouds: pairs ~ density^2)"""
+        S0 = int(self.size[0])
+        layer = self._layers_of(pos).long()
+        ok = layer >= 0
+        h = torch.zeros(S0, dtype=torch.float64, device=self.device)
+        h.index_add_(0, layer[ok], cost.to(torch.float64)[ok])
+        dist.all_reduce(h, group=self.group)
+        return h.cpu().numpy()
+
     def distribute(self, pos, columns=None):
         """One-time distribution of a global cloud: every rank hands in ANY share of the particles
         (e.g. a range of ids) and gets back the particles of its own slab (all-to-all by owner; set-up
@@ -342,6 +354,8 @@ class SlabParticles:
         p.columns = dict(stage)
         p.low, p.high, p.periodic = self.low, self.high, self.periodic
         cap = max(getattr(self, "_cap", 0), n_in // 8 + 4096)
+        if hasattr(self, "_test_cap"):  # tests: a rank-dependent reserve, so that only some ranks outgrow it
+            cap = self._test_cap(n_in)
         big = getattr(self, "_big", None)
         if big is None or self._big_n != n_in or self._cap != cap or set(big) != set(p.columns) or any(
                 big[k].dtype != v.dtype or big[k].shape[1:] != v.shape[1:] for k, v in p.columns.items()):
@@ -379,10 +393,15 @@ class SlabParticles:
             n_lo = 0
         if not has_hi:
             n_hi = 0
-        if n_lo > cap or n_hi > cap:  # halo larger than the reserve: grow it and redo (rare; first build of a clustered cloud)
-            self._cap = max(n_lo, n_hi) * 5 // 4 + 4096
-            self._big = None
-            return self.build(pos_owned_unsorted, extra_columns, assume_all_alive)
+        if n_lo > cap or n_hi > cap:
+            # halo larger than the reserve on THIS rank (other ranks may be fine: nothing collective may be repeated):
+            # move the sorted owned columns into larger ghost-padded buffers — a local copy — and go on
+            new_cap = max(n_lo, n_hi) * 5 // 4 + 4096
+            big2 = {k: torch.empty((n_in + 2 * new_cap,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device) for k, v in big.items()}
+            for k in big:
+                big2[k][new_cap: new_cap + n_own].copy_(big[k][cap: cap + n_own])
+            big = self._big = big2
+            cap = self._cap = new_cap
         # 3. one batch: halo slices of every sorted column + bucket ranges of those layers
         nb_w = w * per_layer
         gh = getattr(self, "_ghost_ranges", None)
@@ -575,6 +594,36 @@ class SlabHostPipeline:
         torch.cuda.current_stream(self.dev).synchronize()
 
 
+def bind_to_gpu_numa_node(dev):
+    """Run this process on the cores of the NUMA node its GPU hangs off, so that the pinned host buffers it
+    allocates next live in that node's memory (first touch).  With eight ranks staging 1 GB per step each from
+    ONE node the host side of the box, not PCIe, bounds the end-to-end step (round 1: 0.32 weak-scaling
+    efficiency end to end at 8 GPUs).  Returns (node, n_cpus) or None when the topology cannot be read."""
+    import os
+
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except Exception:
+        return None
+
+
 def run_bench(args, wl, rank, world, dev, metric, unit, emit=None):
     """bench.py body for N > 1: slabs along dimension 0.  `wl` (bench.Workload) names the cloud: weak
     scaling (n_per_gpu particles per GPU), strong scaling (n_total fixed) or the clustered cloud of
@@ -619,6 +668,24 @@ def run_bench(args, wl, rank, world, dev, metric, unit, emit=None):
     del cols
     op = ab.create_sparse_operator(sp.p, sp.p, radius, wl.kernel)
     state = {}
+    balance = "particle count per layer"
+    if wl.cloud == "clustered":
+        # work per particle is far from uniform on a clustered cloud (pairs ~ density^2): re-split the layers by
+        # the accepted-pair count per layer (one build + stats pass, set-up time only) and redistribute
+        sp.build(pos_unsorted)
+        cnt0, _ = sp.p.pair_stats(radius)
+        cost_in = torch.zeros(n_mine, dtype=torch.float64, device=dev)
+        cost_in[sp.order_owned.long()] = sp.owned(cnt0).to(torch.float64)
+        cost_hist = sp.cost_histogram(pos_unsorted, cost_in)
+        del cnt0
+        new_layers = plan_layers_balanced(cost_hist, world)
+        if [tuple(x) for x in new_layers] != [tuple(x) for x in sp.layers]:
+            sp.set_layers(new_layers)
+            pos_unsorted, cols2 = sp.distribute(pos_unsorted, {"b": b_by_id_mine})
+            b_by_id_mine = cols2["b"]
+            n_mine = pos_unsorted.shape[0]
+        balance = "accepted pairs per layer (stats pass at set-up)"
+        del cost_in
 
     def step(evs=None):
         sp.build(pos_unsorted)  # copied into the container (the bench input itself stays unsorted)
@@ -686,6 +753,7 @@ def run_bench(args, wl, rank, world, dev, metric, unit, emit=None):
     dist.all_reduce(per_rank_ms)
 
     # end-to-end with host buffers: H2D of positions and b, D2H of y, every step
+    numa = bind_to_gpu_numa_node(dev)  # pinned buffers in the memory of the GPU's own NUMA node
     pos_host = torch.empty((n_mine, 3), dtype=torch.float64, pin_memory=True)
     pos_host.copy_(pos_unsorted)
     b_sorted = state["b_sorted"]
@@ -737,14 +805,15 @@ def run_bench(args, wl, rank, world, dev, metric, unit, emit=None):
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name + "; slabs along dim 0 (layer split balanced by particle count), NCCL halo exchange",
+            "config": {"workload": wl.name + f"; slabs along dim 0 (layer split balanced by {balance}), NCCL halo exchange",
                        "n_particles_per_gpu": [int(v) for v in prm[:, 2]], "n_particles": int(n_all.item()), "buckets": int(np.prod(sp.size)), "radius": radius,
                        "pairs_per_matvec": pairs, "halo_particles_total": int(halo.item()), "parallelism": f"slab{world}", "layers": [list(x) for x in sp.layers],
                        "y_checksum": [float(chk[0]), float(chk[1])], "l2": "inputs exceed the 126 MB L2; no flush needed"},
             "per_rank": {"ms_build": [float(v) for v in prm[:, 0]], "ms_matvec": [float(v) for v in prm[:, 1]]},
             "e2e": {"value": pairs / e2e_sec, "unit": unit, "h2d_bytes_per_step": int(n_all.item()) * 32, "d2h_bytes_per_step": int(n_all.item()) * 8,
                     "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps,
-                    "how": "SlabHostPipeline per rank: pinned host buffers; uploads of step k on a copy stream while step k-1 computes, download of y on a third stream; wall clock, max over ranks"},
+                    "how": "SlabHostPipeline per rank: pinned host buffers (allocated on the GPU's own NUMA node); uploads of step k on a copy stream while step k-1 computes, "
+                           "download of y on a third stream; wall clock, max over ranks", "numa_node_rank0": numa[0] if numa else None},
             "gpu_launches": int(launches) * world, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": None,
         }

@@ -358,7 +358,10 @@ def run_ours(args):
 
         from aboria_b200 import slab
 
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a rank that fails must not leave the others waiting for the default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("ABR_NCCL_TIMEOUT_S", 180))))
         return slab.run_bench(args, wl, rank, world, dev, METRIC, UNIT, emit)
 
     n = wl.n_total

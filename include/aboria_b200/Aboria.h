@@ -698,6 +698,74 @@ SparseOperator<RowParticles, ColParticles, KernelDesc> create_sparse_operator(co
   return op;
 }
 
+
+// ---- Level 3: the neighbour sum of the symbolic layer ------------------------------------
+// Symbol / Label / create_dx / AccumulateWithinDistance with the reference's names and call shape
+// (src/Symbolic.h:269-444):
+//     Symbol<rho> r;  Label<0, P> a(particles);  Label<1, P> b(particles);
+//     AccumulateWithinDistance<std::plus<double>> sum(2 * h);
+//     r[a] = sum(b, summand);            // rho_a = sum over b within 2h of a of summand(dx, a, b)
+// evaluated as sparse_sum_impl does (src/detail/Contexts.h:247-289: init, then `sum = sum + expr`
+// over distance_search<2>(b-set, r_a, max_distance)) — on the GPU, through the same cell-tiled product
+// (b == 1, y preset to init).  The one restriction: the summand is not a Boost.Proto expression but a
+// kernel function of the device (a descriptor of namespace kernels, e.g. kernels::sph_density), scalar or
+// D x 1 vector valued.
+template <typename Var> struct Symbol;
+template <unsigned int I, typename P> struct Label {
+  explicit Label(P &p) : particles(p) {}
+  P &get_particles() const { return particles; }
+  P &particles;
+};
+// dx = r_b - r_a of a pair of labels (src/Symbolic.h:372-388): a marker here — the device functors receive dx
+template <typename LA, typename LB> struct Dx {};
+template <unsigned int I, unsigned int J, typename P> Dx<Label<I, P>, Label<J, P>> create_dx(const Label<I, P> &, const Label<J, P> &) { return {}; }
+
+namespace detail {
+template <typename ColParticles, typename KernelDesc> struct within_distance_sum {
+  const ColParticles &cols;
+  double max_distance;
+  KernelDesc summand;
+  double init;
+};
+inline void store_sum(double &dst, const double *y, size_t) { dst = y[0]; }
+template <unsigned int N> inline void store_sum(Vector<double, N> &dst, const double *y, size_t br) {
+  for (size_t k = 0; k < br && k < N; ++k) dst[k] = y[k];
+}
+template <typename Var, typename P> struct symbol_ref {
+  P &rows;
+  // s[a] = sum(b, summand)
+  template <typename ColParticles, typename KernelDesc> symbol_ref &operator=(const within_distance_sum<ColParticles, KernelDesc> &e) {
+    const size_t br = e.summand.d.block_rows;
+    ABR_CHECK(e.summand.d.block_cols == 1, "AccumulateWithinDistance: the summand must be scalar or D x 1");
+    SparseOperator<P, ColParticles, KernelDesc> op(rows, e.cols, e.max_distance, e.summand);
+    std::vector<double> y(rows.size() * br, e.init), ones(e.cols.size(), 1.0);
+    op.evaluate(y, ones);
+    auto &col = rows.template column<Var>();
+    for (size_t i = 0; i < rows.size(); ++i) store_sum(col[i], y.data() + i * br, br);
+    return *this;
+  }
+};
+} // namespace detail
+
+template <typename Var> struct Symbol {
+  template <unsigned int I, typename P> detail::symbol_ref<Var, P> operator[](const Label<I, P> &a) const { return detail::symbol_ref<Var, P>{a.get_particles()}; }
+};
+
+// AccumulateWithinDistance<std::plus<T>> (src/Symbolic.h:420-444); other functors are not offered on the device
+template <typename T> class AccumulateWithinDistance;
+template <typename T> class AccumulateWithinDistance<std::plus<T>> {
+public:
+  explicit AccumulateWithinDistance(const double max_distance = 1.0) : max_distance_(max_distance), init_(0.0) {}
+  void set_max_distance(const double max_distance) { max_distance_ = max_distance; }
+  void set_init(const double init) { init_ = init; }
+  template <unsigned int I, typename P, typename KernelDesc> detail::within_distance_sum<P, KernelDesc> operator()(const Label<I, P> &b, const KernelDesc &summand) const {
+    return detail::within_distance_sum<P, KernelDesc>{b.get_particles(), max_distance_, summand, init_};
+  }
+
+private:
+  double max_distance_, init_;
+};
+
 // ---- zero and block operators -------------------------------------------------------
 // create_zero_operator (src/Operators.h:531-537, KernelZero)
 template <typename RowParticles, typename ColParticles> class ZeroOperator {

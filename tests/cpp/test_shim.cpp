@@ -376,7 +376,42 @@ static void test_rows_without_search_fradius_pushback_devicevector() {
   for (size_t i = 0; i < cols.size(); ++i) TS_ASSERT_EQUALS(y_dev[i], y_host[i]);
 }
 
+// Level 3 names (src/Symbolic.h:269-444): r[a] = sum(b, summand) with AccumulateWithinDistance<std::plus<double>>
+static void test_accumulate_within_distance() {
+  ABORIA_VARIABLE(scalar1, double, "scalar1")
+  ABORIA_VARIABLE(scalar2, double, "scalar2")
+  ABORIA_VARIABLE(total, double, "total")
+  typedef Particles<std::tuple<scalar1, scalar2, total>> ParticlesType;
+  typedef position_d<3> position;
+  ParticlesType particles;
+  const double diameter = 0.1;
+  ParticlesType::value_type p;
+  for (int i = 0; i < 3; ++i) {
+    get<position>(p) = vdouble3(diameter * 0.9 * i, 0, 0);
+    get<scalar1>(p) = 1.0;
+    get<scalar2>(p) = 2.0;
+    get<total>(p) = -1.0;
+    particles.push_back(p);
+  }
+  particles.init_neighbour_search(vdouble3::Constant(-1), vdouble3::Constant(1), vbool3::Constant(false));
+  Symbol<total> t;
+  Label<0, ParticlesType> a(particles);
+  Label<1, ParticlesType> b(particles);
+  auto dx = create_dx(a, b);
+  (void)dx;
+  AccumulateWithinDistance<std::plus<double>> sum(diameter);
+  t[a] = sum(b, kernels::const_sum<scalar1, scalar2>()); // sum over neighbours of (scalar1_a + scalar2_b): rows of C = [3 3 0; 3 3 3; 0 3 3]
+  TS_ASSERT_EQUALS(get<total>(particles)[0], 6.0);
+  TS_ASSERT_EQUALS(get<total>(particles)[1], 9.0);
+  TS_ASSERT_EQUALS(get<total>(particles)[2], 6.0);
+  sum.set_init(0.5);
+  sum.set_max_distance(2 * diameter);
+  t[a] = sum(b, kernels::const_sum<scalar1, scalar2>());
+  TS_ASSERT_EQUALS(get<total>(particles)[0], 9.5);
+}
+
 int main() {
+  test_accumulate_within_distance();
   test_rows_without_search_fradius_pushback_devicevector();
   test_md_force_block_kernel();
   test_sparse_operator();

@@ -74,7 +74,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+    if os.environ.get("ABR_SLAB_TEST_CAP"):
+        # force the "halo larger than the reserve" path on some ranks only (rank-dependent reserve)
+        slab.SlabParticles._test_cap = lambda self, n_in: (64 if self.rank % 2 == 0 else n_in // 2 + 4096)
     ok_all = True
     cases = [("uniform", 200_000, True, 1.0), ("uniform", 200_000, False, 1.0), ("uniform", 60_000 * max(1, world // 2), True, 1.7),
              ("clustered", 400_000, [True, True, False], 1.0)]

@@ -18,7 +18,13 @@ def test_slab_matches_single_gpu():
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "slab_gpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    assert r.returncode == 0
+    # once more with a rank-dependent halo reserve: some ranks outgrow it, the others do not
+    env = dict(os.environ, ABR_SLAB_TEST_CAP="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0
