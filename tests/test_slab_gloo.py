@@ -88,3 +88,51 @@ def test_plan_layers_and_halo_width():
     assert slab.halo_width(1.09 / 294, 1.0 / 294) == 2
     with pytest.raises(ValueError):
         slab.SlabExchange(0, 1, False, 3, torch.tensor([0, 5, 9]))
+
+
+def test_plan_layers_balanced():
+    # uniform histogram: the even split; a clustered one: near-equal particle counts, contiguous, every rank >= 1 layer
+    assert slab.plan_layers_balanced(np.ones(294), 8) == slab.plan_layers(294, 8) or \
+        [hi - lo for lo, hi in slab.plan_layers_balanced(np.ones(294), 8)].count(37) == 6
+    rng = np.random.default_rng(3)
+    h = rng.integers(1, 50, 117).astype(np.float64)
+    h[40:48] += 4000.0  # a blob
+    for world in (2, 4, 8):
+        plan = slab.plan_layers_balanced(h, world)
+        assert plan[0][0] == 0 and plan[-1][1] == 117
+        assert all(plan[g][1] == plan[g + 1][0] for g in range(world - 1)) and all(hi > lo for lo, hi in plan)
+        counts = [h[lo:hi].sum() for lo, hi in plan]
+        even = [h[lo:hi].sum() for lo, hi in slab.plan_layers(117, world)]
+        assert max(counts) <= max(even)  # never worse than the split by layer count
+    with pytest.raises(ValueError):
+        slab.plan_layers_balanced(np.ones(3), 4)
+
+
+def _layout_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank r owns values 100 r + k; it sends its first 2 / last 3 owned entries, receives 3 from below and 2 from above
+        n_own = 10
+        lower, upper = (rank - 1) % world, (rank + 1) % world
+        lay = slab._LocalLayout(rank, world, lower, upper, 3, n_own, 2, 2, 3, None)
+        local = torch.zeros(lay.n_local, dtype=torch.float64)
+        local[lay.own_begin:lay.own_end] = torch.arange(n_own, dtype=torch.float64) + 100.0 * rank
+        lay.fill_halo(local)
+        want_lo = torch.arange(n_own - 3, n_own, dtype=torch.float64) + 100.0 * lower   # the lower neighbour's last 3
+        want_hi = torch.arange(0, 2, dtype=torch.float64) + 100.0 * upper              # the upper neighbour's first 2
+        ok = torch.equal(local[:3], want_lo) and torch.equal(local[lay.own_end:], want_hi)
+        out = lay.assemble(torch.arange(n_own, dtype=torch.float64) + 100.0 * rank)
+        ok = ok and torch.equal(out, local) and lay.halo_bytes(8) == 40
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_local_layout_halo_world2():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_layout_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}
