@@ -12,7 +12,42 @@
 #define ABR_FAST_INVDIST 1
 #endif
 
+// This file is compiled once per dimension (Makefile: -DABR_MATVEC_D=1|2|3; the kernels are templates
+// on D and on the functor, ~70 instantiations per dimension): the D = 3 object also carries the planner
+// and the host entry points, the others only their `matvec_entry_d<k>` (the single-TU build without the
+// macro still works).
+#ifndef ABR_MATVEC_D
+#define ABR_MATVEC_D 0 // everything in one translation unit
+#endif
+#define ABR_D_HERE(d) (ABR_MATVEC_D == 0 || ABR_MATVEC_D == (d))
+#define ABR_MATVEC_MAIN (ABR_MATVEC_D == 0 || ABR_MATVEC_D == 3)
+
 namespace abr {
+
+// one entry point per dimension (defined at the end of this file, each in its own object)
+struct MvArgs {
+  const uint32_t *row_ptr;
+  int32_t *col_idx;
+  double *values;
+  const uint64_t *ii, *jj;
+  uint64_t m;
+  double *out;
+  int lnorm, transform_kind;
+  const double *t_host;
+};
+enum { MV_BUILTIN = 0, MV_ASSEMBLE, MV_COEFF, MV_STATS, MV_NORM };
+int matvec_entry_d1(Handle *h, int op, const abr_matvec_plan &p, const abr_kernel_desc *k, const MvArgs &a);
+int matvec_entry_d2(Handle *h, int op, const abr_matvec_plan &p, const abr_kernel_desc *k, const MvArgs &a);
+int matvec_entry_d3(Handle *h, int op, const abr_matvec_plan &p, const abr_kernel_desc *k, const MvArgs &a);
+__attribute__((unused)) static inline int matvec_entry(Handle *h, int op, const abr_matvec_plan &p, const abr_kernel_desc *k, const MvArgs &a) {
+  switch (h->D) {
+  case 1: return matvec_entry_d1(h, op, p, k, a);
+  case 2: return matvec_entry_d2(h, op, p, k, a);
+  default: return matvec_entry_d3(h, op, p, k, a);
+  }
+}
+
+#if ABR_MATVEC_MAIN
 
 // (x, y, z, b) records for the tiled kernel: the drain gathers position and b of a
 // column particle with ONE 256-bit load instead of four scattered 8-byte loads
@@ -288,6 +323,8 @@ static int make_plan(Handle *h, const MatvecCall &c, int BR, abr_matvec_plan *p,
   return ABR_OK;
 }
 
+#endif // ABR_MATVEC_MAIN (planner)
+
 template <int D, class F, bool STATS>
 static int launch_checked(Handle *h, const abr_matvec_plan &p, const F &f) {
   const int e = launch_plan<D, F, STATS>(p, f);
@@ -385,6 +422,7 @@ template <int D> static int dispatch_coeff(Handle *h, const abr_matvec_plan &p, 
   return ABR_OK;
 }
 
+#if ABR_MATVEC_MAIN
 int run_coeff(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, const uint64_t *ii, const uint64_t *jj, size_t m, double *out) {
   if (!k) return set_error(h, ABR_ERR_INVALID, "coeff: null kernel descriptor");
   if (m == 0) return ABR_OK;
@@ -401,11 +439,12 @@ int run_coeff(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, const ui
   p.radius = c.radius;
   p.radius_per_row = c.radius_per_row;
   p.stream = h->stream;
-  switch (h->D) {
-  case 1: return dispatch_coeff<1>(h, p, k, ii, jj, m, out);
-  case 2: return dispatch_coeff<2>(h, p, k, ii, jj, m, out);
-  default: return dispatch_coeff<3>(h, p, k, ii, jj, m, out);
-  }
+  MvArgs a{};
+  a.ii = ii;
+  a.jj = jj;
+  a.m = m;
+  a.out = out;
+  return matvec_entry(h, MV_COEFF, p, k, a);
 }
 
 int scan_exclusive_u32(Handle *h, uint32_t *data, uint64_t m); // abr_build.cu
@@ -462,11 +501,11 @@ int run_assemble(Handle *h, const MatvecCall &c, const abr_kernel_desc *k, uint3
   w.count = nullptr;
   int rc = make_plan(h, w, k->block_rows, &p);
   if (rc) return rc;
-  switch (h->D) {
-  case 1: return dispatch_assemble<1>(h, p, k, row_ptr, col_idx, values);
-  case 2: return dispatch_assemble<2>(h, p, k, row_ptr, col_idx, values);
-  default: return dispatch_assemble<3>(h, p, k, row_ptr, col_idx, values);
-  }
+  MvArgs a{};
+  a.row_ptr = row_ptr;
+  a.col_idx = col_idx;
+  a.values = values;
+  return matvec_entry(h, MV_ASSEMBLE, p, k, a);
 }
 
 int run_builtin_matvec(Handle *h, const MatvecCall &c, const abr_kernel_desc *k) {
@@ -476,11 +515,7 @@ int run_builtin_matvec(Handle *h, const MatvecCall &c, const abr_kernel_desc *k)
   abr_matvec_plan p;
   int rc = make_plan(h, c, k->block_rows, &p, k->block_cols);
   if (rc) return rc;
-  switch (h->D) {
-  case 1: return dispatch_builtin<1>(h, p, k);
-  case 2: return dispatch_builtin<2>(h, p, k);
-  default: return dispatch_builtin<3>(h, p, k);
-  }
+  return matvec_entry(h, MV_BUILTIN, p, k, MvArgs{});
 }
 
 int run_pair_stats(Handle *h, const MatvecCall &c) {
@@ -489,13 +524,9 @@ int run_pair_stats(Handle *h, const MatvecCall &c) {
   abr_matvec_plan p;
   int rc = make_plan(h, c, 1, &p);
   if (rc) return rc;
-  StatsFunctor f;
-  switch (h->D) {
-  case 1: return launch_checked<1, StatsFunctor, true>(h, p, f);
-  case 2: return launch_checked<2, StatsFunctor, true>(h, p, f);
-  default: return launch_checked<3, StatsFunctor, true>(h, p, f);
-  }
+  return matvec_entry(h, MV_STATS, p, nullptr, MvArgs{});
 }
+#endif // ABR_MATVEC_MAIN (coeff / assemble / product / stats entry points)
 
 template <int D, int TK> static int launch_norm_stats_t(Handle *h, const abr_matvec_plan &p, int lnorm, const Xform &xf) {
   const unsigned grid = (unsigned)((p.n_rows + 127) / 128);
@@ -543,6 +574,7 @@ template <int D> static int launch_norm_stats(Handle *h, const abr_matvec_plan &
   return launch_norm_stats_t<D, 0>(h, p, lnorm, xf);
 }
 
+#if ABR_MATVEC_MAIN
 int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm, int transform_kind, const double *t_host) {
   if (transform_kind != 0 && !t_host) return set_error(h, ABR_ERR_INVALID, "distance_search: null transform");
   if (c.n_rows == 0) return ABR_OK;
@@ -552,11 +584,11 @@ int run_norm_stats(Handle *h, const MatvecCall &c, int lnorm, int transform_kind
   w.force_path = 1;
   int rc = make_plan(h, w, 1, &p);
   if (rc) return rc;
-  switch (h->D) {
-  case 1: return launch_norm_stats<1>(h, p, lnorm, transform_kind, t_host);
-  case 2: return launch_norm_stats<2>(h, p, lnorm, transform_kind, t_host);
-  default: return launch_norm_stats<3>(h, p, lnorm, transform_kind, t_host);
-  }
+  MvArgs a{};
+  a.lnorm = lnorm;
+  a.transform_kind = transform_kind;
+  a.t_host = t_host;
+  return matvec_entry(h, MV_NORM, p, nullptr, a);
 }
 
 int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, const void *functor,
@@ -573,5 +605,26 @@ int run_custom_matvec(Handle *h, const MatvecCall &c, abr_launch_fn launch, cons
   h->launches += h->counters[2];
   return ABR_OK;
 }
+
+#endif // ABR_MATVEC_MAIN (norm stats / custom entry points)
+
+template <int D> static int matvec_entry_t(Handle *h, int op, const abr_matvec_plan &p, const abr_kernel_desc *k, const MvArgs &a) {
+  switch (op) {
+  case MV_BUILTIN: return dispatch_builtin<D>(h, p, k);
+  case MV_ASSEMBLE: return dispatch_assemble<D>(h, p, k, a.row_ptr, a.col_idx, a.values);
+  case MV_COEFF: return dispatch_coeff<D>(h, p, k, a.ii, a.jj, a.m, a.out);
+  case MV_STATS: return launch_checked<D, StatsFunctor, true>(h, p, StatsFunctor());
+  default: return launch_norm_stats<D>(h, p, a.lnorm, a.transform_kind, a.t_host);
+  }
+}
+#if ABR_D_HERE(1)
+int matvec_entry_d1(Handle *h, int op, const abr_matvec_plan &p, const abr_kernel_desc *k, const MvArgs &a) { return matvec_entry_t<1>(h, op, p, k, a); }
+#endif
+#if ABR_D_HERE(2)
+int matvec_entry_d2(Handle *h, int op, const abr_matvec_plan &p, const abr_kernel_desc *k, const MvArgs &a) { return matvec_entry_t<2>(h, op, p, k, a); }
+#endif
+#if ABR_D_HERE(3)
+int matvec_entry_d3(Handle *h, int op, const abr_matvec_plan &p, const abr_kernel_desc *k, const MvArgs &a) { return matvec_entry_t<3>(h, op, p, k, a); }
+#endif
 
 } // namespace abr

@@ -1722,7 +1722,7 @@ staged_kernel(const abr_matvec_plan p, const F f) {
 // ---------------------------------------------------------------------------
 // symmetric kernel, second step: y += ytmp for the owned rows that keep their tiled result
 // (flagged rows are recomputed from y by the exact walk that follows)
-__global__ void __launch_bounds__(256) k_sym_combine(const abr_matvec_plan p, int BR) {
+static __global__ void __launch_bounds__(256) k_sym_combine(const abr_matvec_plan p, int BR) {
   const Grid &g = p.q.g;
   uint32_t per_layer = 1;
   for (int d = 1; d < g.D; ++d) per_layer *= (uint32_t)g.size[d];
