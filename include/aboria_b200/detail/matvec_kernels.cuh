@@ -299,7 +299,15 @@ constexpr int ROW_BITS = 4;
 #endif
 constexpr int WQ = ABR_WQ;            // pairs compacted per drain pass
 constexpr uint32_t HEAVY_ROWS = 64;   // a bucket with more rows than this is split into row-batch work items (second launch)
-constexpr int PCOL = 16;              // columns of the partial-sum table (lanes l and l+16 share one)
+// partial-sum table update in the drain (profiles/r2w_acc_modes.txt):
+//   0  16 columns, the two half-warps update one after the other (default)
+//   1  16 columns, one pass: lanes l and l+16 share a column; when they also hold the same row the lower
+//      lane adds both terms (two shuffles), otherwise the two addresses differ
+//   2  32 columns, one pass (2 KB more shared memory per warp: one or two resident CTAs fewer per SM)
+#ifndef ABR_ACC_MODE
+#define ABR_ACC_MODE 0
+#endif
+constexpr int PCOL = ABR_ACC_MODE == 2 ? 32 : 16; // columns of the partial-sum table
 
 // resident CTAs per SM the tiled kernel is compiled for: 7 (72 registers) by default; a
 // functor whose math is light enough for 64 registers declares
@@ -529,9 +537,8 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
             }
           }
         }
-  #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (ok && (lane >> 4) == half) {
+        if (ABR_ACC_MODE == 2) {
+          if (ok) {
   #pragma unroll
             for (int a2 = 0; a2 < BR; ++a2) {
               double *slot = reinterpret_cast<double *>(&sm.part[a2][i][col]);
@@ -539,6 +546,36 @@ __device__ __noinline__ void drain_queues(SM &sm, const DrainCtx p, const F f, i
             }
           }
           __syncwarp();
+        } else if (ABR_ACC_MODE == 1) {
+          // the partner lane (l ^ 16) uses the same column: same row too -> the lower lane carries both terms
+          const uint32_t mine = ok ? i : 0xFFFFu;
+          const uint32_t theirs = __shfl_xor_sync(0xFFFFFFFFu, mine, 16);
+          const bool merge = ok && mine == theirs;
+  #pragma unroll
+          for (int a2 = 0; a2 < BR; ++a2) {
+            const double t = __shfl_xor_sync(0xFFFFFFFFu, s[a2], 16);
+            if (merge) s[a2] += t;
+          }
+          if (ok && !(merge && lane >= 16)) {
+  #pragma unroll
+            for (int a2 = 0; a2 < BR; ++a2) {
+              double *slot = reinterpret_cast<double *>(&sm.part[a2][i][col]);
+              *slot += s[a2];
+            }
+          }
+          __syncwarp();
+        } else {
+  #pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (ok && (lane >> 4) == half) {
+  #pragma unroll
+              for (int a2 = 0; a2 < BR; ++a2) {
+                double *slot = reinterpret_cast<double *>(&sm.part[a2][i][col]);
+                *slot += s[a2];
+              }
+            }
+            __syncwarp();
+          }
         }
       }
     }
