@@ -95,6 +95,10 @@ int abr_create(abr_handle *out, int device, void *stream) {
   if (const char *e = getenv("ABR_PHASED_GATHER")) h->phased_gather = (e[0] != '0');
   if (const char *e = getenv("ABR_MATVEC_VARIANT")) h->matvec_variant = atoi(e);
   if (const char *e = getenv("ABR_SYMMETRIC")) h->symmetric = (e[0] != '0');
+  if (const char *e = getenv("ABR_STAGE_RECORDS")) h->stage_records = (e[0] != '0');
+  if (const char *e = getenv("ABR_GATHER_SLOTS")) h->gather_slots = (e[0] != '0');
+  if (const char *e = getenv("ABR_RECORD_AOS")) h->record_aos = (e[0] != '0');
+  if (const char *e = getenv("ABR_STAGE_THREADS")) h->stage_threads = atoi(e) == 512 ? 512 : 1024;
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
   for (int d = 0; d < abr::MAXD; ++d) {
@@ -166,6 +170,18 @@ int abr_set_option(abr_handle hh, const char *name, double value) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !name) return ABR_ERR_INVALID;
   const std::string k(name);
+  if (k == "stage_records") {
+    h->stage_records = value != 0;
+    return ABR_OK;
+  }
+  if (k == "record_aos") {
+    h->record_aos = value != 0;
+    return ABR_OK;
+  }
+  if (k == "gather_slots") {
+    h->gather_slots = value != 0;
+    return ABR_OK;
+  }
   if (k == "two_level_min_n") {
     h->two_level_min_n = value < 0 ? 0 : (size_t)value;
   } else if (k == "counting_min_n") {

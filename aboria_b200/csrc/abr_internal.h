@@ -77,6 +77,10 @@ struct Handle {
   size_t counting_min_n = (size_t)-1;             // counting-sort build (abr_build2.cu) from this many particles; off by default: measured slower
                                                   // than the two-level radix build on B200 (3.4 vs 2.7 ms at 32 M, profiles/r2f_counting_build.txt)
   size_t two_level_min_n = (size_t)1 << 20;  // use the two-level build from this many particles (abr_set_option)
+  bool gather_slots = true;                  // two-level build: final reorder with the loads of every column in flight at once
+  int stage_threads = 512;                   // threads per CTA of the staged record move (512 or 1024)
+  bool record_aos = false;                   // staged record move writes one record per particle (RecLayout); measured slower, off
+  bool stage_records = true;                 // two-level build: bulk-copy staged record move when the tile windows fit in shared memory
   DevBuf bucket_begin, bucket_end;
   DevBuf danger_list;
   DevBuf scan_tmp2, pair_i, pair_j, pair_q; // bucket-pair traversal (abr_pairs.cu)

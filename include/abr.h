@@ -84,7 +84,9 @@ int abr_synchronize(abr_handle h);
  * with n_alive_host != NULL). */
 int abr_check_async(abr_handle h);
 /* Tuning knobs: "two_level_min_n" — particle count from which abr_update_positions uses
- * the two-level (partition + bin-local sort) build; "phased_gather" — 0/1;
+ * the two-level (partition + bin-local sort) build; "stage_records" — 1 (default): its
+ * record partition stages each tile's column windows in shared memory with
+ * cp.async.bulk when they fit, 0: records read directly from L2; "phased_gather" — 0/1;
  * "matvec_variant" — 0: cell-tiled kernel gathering candidates from L2, 1: candidates
  * staged in shared memory with cp.async.bulk; "symmetric" — 1: products with rows ==
  * columns whose functor declares SYMMETRY evaluate every unordered pair once (half

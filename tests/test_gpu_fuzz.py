@@ -63,6 +63,8 @@ def make_case(case):
         if k > 1:
             pos[idx[1], rng.integers(0, D)] = np.inf
     strategy = [False, True, "counting"][int(rng.integers(0, 3))]
+    if strategy is True:
+        strategy = [True, "records", "direct"][case % 3]
     return dict(rng=rng, D=D, N=N, low=low, high=high, periodic=periodic, n_leaf=n_leaf, shape=str(shape), pos=pos, alive=alive,
                 strategy=strategy)
 

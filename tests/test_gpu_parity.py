@@ -20,7 +20,7 @@ TOL = 1e-12
     (2, 1000, 10, True), (2, 1000, 10, False), (2, 1000, 1, True),
     (3, 1, 10, True), (3, 3, 10, False), (3, 1000, 100, True), (3, 1000, 10, False), (3, 1000, 1, True),
     (3, 5000, 10, True), (3, 100000, 10, True), (2, 100000, 10, False), (3, 300000, 3, True), (3, 200000, 10, [True, False, True])])
-@pytest.mark.parametrize("two_level", [False, True, "counting"])
+@pytest.mark.parametrize("two_level", [False, True, "counting", "records", "direct"])
 def test_build_parity(D, N, nn, periodic, two_level):
     # both build strategies: LSD sort + random gather, and the two-level build
     # (records partitioned by the top key digit, bin-local passes, L2-local gather)
@@ -66,6 +66,29 @@ def test_build_dead_wrap_and_columns():
         q3 = p3.get_query()
         assert np.array_equal(q3.bucket_begin.cpu().numpy().view(np.uint32), out["bucket_begin"])
         assert np.array_equal(q3.bucket_end.cpu().numpy().view(np.uint32), out["bucket_end"])
+    # two-level build with columns that fit its staged record move / register-slot gather / record layout
+    # (8-byte-word columns plus at most four bytes of 1/2/4-byte ones), in all three variants
+    for strategy in (True, "records", "direct"):
+        for vs in ({"a": torch.float64, "flag": torch.uint8}, {"k": torch.int32}, {"h": torch.int16}, {"h": torch.int16, "flag": torch.uint8}):
+            p4 = ab.Particles(3, N, variables=vs)
+            p4.set_option("two_level_min_n", 0)
+            p4.set_option("record_aos", 1 if strategy == "records" else 0)
+            p4.set_option("stage_records", 0 if strategy == "direct" else 1)
+            p4.set_option("gather_slots", 0 if strategy == "direct" else 1)
+            p4.set("position", torch.from_numpy(pos0.copy()))
+            p4.set("alive", torch.from_numpy(alive.copy()))
+            cols4 = {}
+            for k, v in vs.items():
+                cols4[k] = rng.random(N) if v == torch.float64 else rng.integers(0, 120, N).astype({torch.uint8: np.uint8, torch.int32: np.int32, torch.int16: np.int16}[v])
+                p4.set(k, torch.from_numpy(cols4[k]))
+            p4.init_neighbour_search(0.0, 1.0, periodic, 10.0)
+            assert p4.size() == out["n_alive"]
+            assert np.array_equal(p4.get_alive_indicies().cpu().numpy(), out["order"]), (strategy, vs)
+            assert np.array_equal(p4.get("position").cpu().numpy().view(np.uint64), out["pos"].view(np.uint64)), (strategy, vs)
+            assert np.array_equal(p4.get("id").cpu().numpy(), out["order"].astype(np.int64)), (strategy, vs)
+            assert bool((p4.get("alive") == 1).all())
+            for k, v in cols4.items():
+                assert np.array_equal(p4.get(k).cpu().numpy(), v[out["order"]]), (strategy, k)
     p2 = ab.Particles(3, N, variables=vars_)
     p2.set_option("two_level_min_n", 0)
     p2.set("position", torch.from_numpy(pos0.copy()))
@@ -267,7 +290,7 @@ def test_matvec_rows_not_cols_and_row_radius():
     assert np.array_equal(hs.cpu().numpy().view(np.uint64), hs_o)
 
 
-@pytest.mark.parametrize("two_level", [False, True, "counting"])
+@pytest.mark.parametrize("two_level", [False, True, "counting", "records", "direct"])
 def test_clustered_cloud(two_level):
     # c4-style clustered cloud at reduced N: heavy buckets (very uneven first-level bins), periodic (1,1,0)
     N = 200000

@@ -17,8 +17,13 @@ def build_both(pos, low, high, periodic, n_leaf=10.0, alive=None, variables=None
     p = ab.Particles(D, n, variables=variables)
     if two_level is not None:
         # build strategy: False = LSD radix sort + gather, True = two-level radix build, "counting" = counting-sort build
-        p.set_option("two_level_min_n", 0 if two_level is True else 1e18)
+        # "records": two-level with the binned copy as one record per particle; "direct": two-level without the
+        # bulk-copy staged record move and with the column-by-column final gather (the round-1 kernels)
+        p.set_option("two_level_min_n", 0 if two_level in (True, "records", "direct") else 1e18)
         p.set_option("counting_min_n", 0 if two_level == "counting" else 1e18)
+        p.set_option("record_aos", 1 if two_level == "records" else 0)
+        p.set_option("stage_records", 0 if two_level == "direct" else 1)
+        p.set_option("gather_slots", 0 if two_level == "direct" else 1)
     p.set("position", torch.from_numpy(pos.copy()))
     if alive is not None:
         p.set("alive", torch.from_numpy(np.ascontiguousarray(alive, dtype=np.uint8)))

@@ -1,0 +1,13 @@
+#!/bin/bash
+# build: one-record-per-particle binned copy (k_radix_scatter<3> + k_gather_records): parity, then A/B
+cd "$GRAFT_REPO_ROOT" || exit 1
+out=gpurun_out/r2y_stage_records.txt
+timeout 600 python -m pytest tests/test_gpu_fuzz.py tests/test_gpu_parity.py tests/test_gpu_apps.py tests/test_golden_fixtures.py -m gpu -q -x 2>&1 | tail -8 | tee -a $out
+run() {
+  r=$(env "$@" timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['ms_build'], d['ms_matvec'], d['config']['pairs_per_matvec'])")
+  echo "$*: step/build/product ms, pairs: $r" | tee -a $out
+}
+run ABR_RECORD_AOS=1
+run ABR_RECORD_AOS=0
+run ABR_RECORD_AOS=1
+run ABR_RECORD_AOS=0 ABR_GATHER_SLOTS=0 ABR_STAGE_RECORDS=0
