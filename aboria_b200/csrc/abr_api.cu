@@ -98,6 +98,7 @@ int abr_create(abr_handle *out, int device, void *stream) {
   if (const char *e = getenv("ABR_STAGE_RECORDS")) h->stage_records = (e[0] != '0');
   if (const char *e = getenv("ABR_GATHER_SLOTS")) h->gather_slots = (e[0] != '0');
   if (const char *e = getenv("ABR_RECORD_AOS")) h->record_aos = (e[0] != '0');
+  if (const char *e = getenv("ABR_SKIP_ALIVE_MOVE")) h->skip_alive_move = (e[0] != '0');
   if (const char *e = getenv("ABR_STAGE_THREADS")) h->stage_threads = atoi(e) == 512 ? 512 : 1024;
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;

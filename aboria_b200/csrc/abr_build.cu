@@ -1175,6 +1175,16 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *p, uint32_t v, uint6
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
+// the alive column after a reorder: ones for the n_alive survivors (n_dev: device-side count)
+__global__ void __launch_bounds__(256) k_fill_ones_bounded(uint8_t *p, uint32_t n, const uint32_t *__restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
+  const uint32_t i = (blockIdx.x * 256 + threadIdx.x) * 16;
+  if (i + 16 <= n && (((uintptr_t)p) & 15u) == 0) {
+    *reinterpret_cast<uint4 *>(p + i) = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  } else {
+    for (uint32_t k = i; k < min(n, i + 16); ++k) p[k] = 1;
+  }
+}
 void fill_u32(Handle *h, uint32_t *p, uint32_t v, uint64_t n) {
   if (n == 0) return;
   const uint64_t blocks = (n + 255) / 256;
@@ -1266,6 +1276,7 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     tmp_cols.ncols = 0;
     RecLayout rec{};                     // two-level: the binned copy as one record per particle (rec_aos)
     bool rec_aos = false;
+    uint8_t *alive_dst = nullptr;        // two-level: the reordered alive column is filled, not moved
     if (counting) {
       const int rc = build_counting(h, pos, alive, n32, g, bits, reorder, order_out);
       if (rc) return rc;
@@ -1309,18 +1320,26 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
       ABR_CUDA(h, h->tile_tab.reserve((size_t)(4 * t_bound + RADIX + 8) * sizeof(uint32_t)));
       ABR_CUDA(h, h->seg_hist.reserve((size_t)RADIX * t_bound * sizeof(uint32_t)));
       GatherCols src_cols;
-      src_cols.ncols = tmp_cols.ncols = reorder->ncols;
       {
         uint8_t *base = h->tmp_cols.as<uint8_t>();
+        int m = 0;
         for (int c = 0; c < reorder->ncols; ++c) {
-          src_cols.src[c] = static_cast<const uint8_t *>(reorder->src[c]);
-          src_cols.dst[c] = base;
-          src_cols.eb[c] = (uint32_t)reorder->elem_bytes[c];
-          tmp_cols.src[c] = base;
-          tmp_cols.dst[c] = static_cast<uint8_t *>(reorder->dst[c]);
-          tmp_cols.eb[c] = (uint32_t)reorder->elem_bytes[c];
+          // the alive column does not travel: every particle that survives the reorder is alive (the dead
+          // ones sort behind n_alive), so its reordered copy is a run of ones (k_fill_ones_bounded below)
+          if (alive && reorder->src[c] == static_cast<const void *>(alive) && reorder->elem_bytes[c] == 1 && h->skip_alive_move) {
+            alive_dst = static_cast<uint8_t *>(reorder->dst[c]);
+            continue;
+          }
+          src_cols.src[m] = static_cast<const uint8_t *>(reorder->src[c]);
+          src_cols.dst[m] = base;
+          src_cols.eb[m] = (uint32_t)reorder->elem_bytes[c];
+          tmp_cols.src[m] = base;
+          tmp_cols.dst[m] = static_cast<uint8_t *>(reorder->dst[c]);
+          tmp_cols.eb[m] = (uint32_t)reorder->elem_bytes[c];
           base += ((reorder->elem_bytes[c] * n + 255) / 256) * 256;
+          ++m;
         }
+        src_cols.ncols = tmp_cols.ncols = m;
       }
       uint32_t *keys1 = h->keys[1].as<uint32_t>();
       uint32_t *orig = h->idx[1].as<uint32_t>();
@@ -1444,6 +1463,10 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
           k_gather_slots<<<gb, 256, 0, h->stream>>>(fc, gs, perm, n32, &h->d_scalars->n_alive);
         else
           k_gather_fused<<<gb, 256, 0, h->stream>>>(fc, perm, n32, &h->d_scalars->n_alive);
+        if (alive_dst) {
+          k_fill_ones_bounded<<<grid_for((n + 15) / 16, 256), 256, 0, h->stream>>>(alive_dst, n32, &h->d_scalars->n_alive);
+          h->launches += 1;
+        }
         h->launches += 1;
         rc = ABR_OK;
       } else {

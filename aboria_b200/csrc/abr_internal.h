@@ -80,6 +80,7 @@ struct Handle {
   bool gather_slots = true;                  // two-level build: final reorder with the loads of every column in flight at once
   int stage_threads = 512;                   // threads per CTA of the staged record move (512 or 1024)
   bool record_aos = false;                   // staged record move writes one record per particle (RecLayout); measured slower, off
+  bool skip_alive_move = true;               // two-level build: the reordered alive column is a run of ones, not a gather
   bool stage_records = true;                 // two-level build: bulk-copy staged record move when the tile windows fit in shared memory
   DevBuf bucket_begin, bucket_end;
   DevBuf danger_list;
