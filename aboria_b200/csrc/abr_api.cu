@@ -99,6 +99,7 @@ int abr_create(abr_handle *out, int device, void *stream) {
   if (const char *e = getenv("ABR_GATHER_SLOTS")) h->gather_slots = (e[0] != '0');
   if (const char *e = getenv("ABR_RECORD_AOS")) h->record_aos = (e[0] != '0');
   if (const char *e = getenv("ABR_SKIP_ALIVE_MOVE")) h->skip_alive_move = (e[0] != '0');
+  if (const char *e = getenv("ABR_BOUNDS_ONE_SWEEP")) h->bounds_one_sweep = (e[0] != '0');
   if (const char *e = getenv("ABR_STAGE_THREADS")) h->stage_threads = atoi(e) == 512 ? 512 : 1024;
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
@@ -133,6 +134,7 @@ int abr_destroy(abr_handle hh) {
   }
   h->tile_hist.release();
   h->scan_tmp.release();
+  h->gap_list.release();
   h->idx2.release();
   h->tmp_cols.release();
   h->tile_tab.release();
@@ -173,6 +175,14 @@ int abr_set_option(abr_handle hh, const char *name, double value) {
   const std::string k(name);
   if (k == "stage_records") {
     h->stage_records = value != 0;
+    return ABR_OK;
+  }
+  if (k == "bounds_one_sweep") {
+    h->bounds_one_sweep = value != 0;
+    return ABR_OK;
+  }
+  if (k == "skip_alive_move") {
+    h->skip_alive_move = value != 0;
     return ABR_OK;
   }
   if (k == "record_aos") {

@@ -646,6 +646,106 @@ k_boundaries(const uint32_t *__restrict__ keys, uint32_t n, uint32_t ncells, uin
   if (p >= 64 && k < ncells && keys[p - 64] == k && (k != knext || p + 1 == n)) atomicMax(&sc->max_bucket, 65u);
 }
 
+// The same bucket ranges in ONE sweep over the sorted keys, every bucket written exactly once — no
+// 0xFFFFFFFF fills of both arrays, no suffix-min scan over the buckets afterwards.  The thread at a run
+// boundary p (keys[p-1] < keys[p]; p == n closes the array) writes bucket_end of the run that ends,
+// bucket_begin of the run that starts, and begin = end = p for the EMPTY buckets between the two, which
+// is what lower_bound / upper_bound give them (src/CellListOrdered.h:229-239).  Gaps are filled by the
+// whole warp (coalesced); a gap longer than GAP_LONG goes to a list that k_fill_gaps sweeps with the
+// whole grid, so a cloud that leaves most of the grid empty costs no more than a fill.
+constexpr uint32_t GAP_LONG = 4096;
+struct GapList {
+  uint32_t *count;  // entries appended
+  uint32_t *lo, *hi, *val; // buckets [lo, hi) get begin = end = val
+  uint32_t capacity;
+};
+__global__ void __launch_bounds__(256)
+k_boundaries_fill(const uint32_t *__restrict__ keys, uint32_t n, uint32_t ncells, uint32_t dead_key,
+                  uint32_t *__restrict__ bb, uint32_t *__restrict__ be, DevScalars *sc, const GapList gl) {
+  // four consecutive boundaries per thread: one 16-byte load, the neighbours by shuffle
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p0 = t * 4u; // boundaries p0 .. p0+3 (boundary p sits in front of element p; p == n closes the array)
+  const int lane = threadIdx.x & 31;
+  uint32_t k[4];
+  if (p0 + 3 < n) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(keys + p0);
+    k[0] = v.x, k[1] = v.y, k[2] = v.z, k[3] = v.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) k[e] = p0 + e < n ? keys[p0 + e] : 0xFFFFFFFFu;
+  }
+  uint32_t kprev = __shfl_up_sync(0xFFFFFFFFu, k[3], 1);
+  if (lane == 0) kprev = (p0 > 0 && p0 <= n) ? keys[p0 - 1] : 0xFFFFFFFFu;
+  uint32_t knext4 = __shfl_down_sync(0xFFFFFFFFu, k[0], 1);
+  if (lane == 31) knext4 = p0 + 4 < n ? keys[p0 + 4] : 0xFFFFFFFFu;
+  uint32_t glo[4], ghi[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const uint32_t p = p0 + e;
+    const uint32_t kk = k[e];
+    const uint32_t kp = e == 0 ? kprev : k[e - 1];
+    const uint32_t kn = e == 3 ? knext4 : k[e + 1];
+    glo[e] = ghi[e] = 0;
+    if (p <= n) {
+      const uint32_t kc = kk < ncells ? kk : ncells;                   // keys beyond the grid (dead, outside) close it
+      const uint32_t kp1 = p > 0 ? (kp < ncells ? kp + 1u : ncells) : 0u; // first bucket after the previous run
+      if (p < n) {
+        if (p > 0 && kk < kp) atomicAdd(&sc->n_unsorted, 1u);
+        if (p == 0 || kk != kp) {
+          if (kk >= ncells && (p == 0 || kp < ncells)) sc->n_incell = p;
+          if (kk == dead_key) sc->n_alive = p;
+        }
+        // bucket occupancy, sampled where a run of 65 equal keys ends: tells the product that heavy buckets exist
+        if ((kk != kn || p + 1 == n) && p >= 64 && kk < ncells && keys[p - 64] == kk) atomicMax(&sc->max_bucket, 65u);
+      }
+      if (p == 0 || p == n || kk != kp) {
+        if (p > 0 && kp < ncells) be[kp] = p;
+        if (kc < ncells) bb[kc] = p;
+        if (kp1 < kc) {
+          glo[e] = kp1;
+          ghi[e] = kc;
+        }
+      }
+    }
+  }
+  // empty buckets, warp-cooperatively
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    uint32_t pending = __ballot_sync(0xFFFFFFFFu, ghi[e] > glo[e]);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const uint32_t lo = __shfl_sync(0xFFFFFFFFu, glo[e], src), hi = __shfl_sync(0xFFFFFFFFu, ghi[e], src);
+      const uint32_t val = __shfl_sync(0xFFFFFFFFu, p0, src) + e;
+      if (hi - lo > GAP_LONG) {
+        if (lane == 0) {
+          const uint32_t slot = atomicAdd(gl.count, 1u);
+          if (slot < gl.capacity) {
+            gl.lo[slot] = lo;
+            gl.hi[slot] = hi;
+            gl.val[slot] = val;
+          }
+        }
+      } else {
+        for (uint32_t j = lo + lane; j < hi; j += 32) {
+          bb[j] = val;
+          be[j] = val;
+        }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_fill_gaps(const GapList gl, uint32_t *__restrict__ bb, uint32_t *__restrict__ be) {
+  const uint32_t m = min(*gl.count, gl.capacity);
+  for (uint32_t g = 0; g < m; ++g) {
+    const uint32_t lo = gl.lo[g], hi = gl.hi[g], val = gl.val[g];
+    for (uint32_t j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
+      bb[j] = val;
+      be[j] = val;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // k4: gather.  8-byte-word columns: one thread per output word, so the stores
 // of a warp are one contiguous 256-byte span; the loads of one element are
@@ -1433,12 +1533,25 @@ int build_celllist(Handle *h, double *pos, uint8_t *alive, size_t n, int32_t *or
     // bucket ranges
     uint32_t *bb = h->bucket_begin.as<uint32_t>();
     uint32_t *be = h->bucket_end.as<uint32_t>();
-    fill_u32(h, bb, 0xFFFFFFFFu, prod);
-    fill_u32(h, be, 0xFFFFFFFFu, prod);
-    k_boundaries<<<gb, 256, 0, h->stream>>>(h->sorted_keys, n32, (uint32_t)prod, g.key_bound, bb, be, h->d_scalars);
-    h->launches += 1;
-    cudaError_t e = device_scan<OpMin, true, 1>(h, bb, prod, bb, be);
-    if (e != cudaSuccess) return check_cuda(h, e, "bucket fill");
+    if (h->bounds_one_sweep) {
+      // one sweep: every bucket written once (k_boundaries_fill); long runs of empty buckets through a list
+      const uint32_t cap = (uint32_t)(prod / GAP_LONG + 2);
+      ABR_CUDA(h, h->gap_list.reserve((size_t)(3 * cap + 4) * sizeof(uint32_t)));
+      uint32_t *gp = h->gap_list.as<uint32_t>();
+      const GapList gl{gp, gp + 4, gp + 4 + cap, gp + 4 + 2 * cap, cap};
+      fill_u32(h, gp, 0u, 1);
+      k_boundaries_fill<<<grid_for(((uint64_t)n + 4) / 4, 256), 256, 0, h->stream>>>(h->sorted_keys, n32, (uint32_t)prod, g.key_bound, bb, be,
+                                                                               h->d_scalars, gl);
+      k_fill_gaps<<<h->sm_count * 4, 256, 0, h->stream>>>(gl, bb, be);
+      h->launches += 2;
+    } else {
+      fill_u32(h, bb, 0xFFFFFFFFu, prod);
+      fill_u32(h, be, 0xFFFFFFFFu, prod);
+      k_boundaries<<<gb, 256, 0, h->stream>>>(h->sorted_keys, n32, (uint32_t)prod, g.key_bound, bb, be, h->d_scalars);
+      h->launches += 1;
+      cudaError_t e = device_scan<OpMin, true, 1>(h, bb, prod, bb, be);
+      if (e != cudaSuccess) return check_cuda(h, e, "bucket fill");
+    }
 
     } // radix builds
 

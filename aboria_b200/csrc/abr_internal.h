@@ -71,7 +71,7 @@ struct Handle {
   int win_lo = 0, win_n = 0, own_lo = 0, own_n = 0;
 
   // --- device state ---------------------------------------------------------
-  DevBuf keys[2], idx[2], tile_hist, scan_tmp;
+  DevBuf keys[2], idx[2], tile_hist, scan_tmp, gap_list;
   DevBuf idx2, tmp_cols, tile_tab, seg_hist; // two-level build
   DevBuf cs_ko, cs_scratch, cs_scratch2, cs_bins; // counting-sort build (abr_build2.cu)
   size_t counting_min_n = (size_t)-1;             // counting-sort build (abr_build2.cu) from this many particles; off by default: measured slower
@@ -80,6 +80,7 @@ struct Handle {
   bool gather_slots = true;                  // two-level build: final reorder with the loads of every column in flight at once
   int stage_threads = 512;                   // threads per CTA of the staged record move (512 or 1024)
   bool record_aos = false;                   // staged record move writes one record per particle (RecLayout); measured slower, off
+  bool bounds_one_sweep = true;              // bucket ranges in one sweep over the sorted keys (k_boundaries_fill) instead of fills + boundaries + suffix-min scan
   bool skip_alive_move = true;               // two-level build: the reordered alive column is a run of ones, not a gather
   bool stage_records = true;                 // two-level build: bulk-copy staged record move when the tile windows fit in shared memory
   DevBuf bucket_begin, bucket_end;

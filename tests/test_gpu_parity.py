@@ -75,6 +75,8 @@ def test_build_dead_wrap_and_columns():
             p4.set_option("record_aos", 1 if strategy == "records" else 0)
             p4.set_option("stage_records", 0 if strategy == "direct" else 1)
             p4.set_option("gather_slots", 0 if strategy == "direct" else 1)
+            p4.set_option("skip_alive_move", 0 if strategy == "direct" else 1)
+            p4.set_option("bounds_one_sweep", 0 if strategy == "direct" else 1)
             p4.set("position", torch.from_numpy(pos0.copy()))
             p4.set("alive", torch.from_numpy(alive.copy()))
             cols4 = {}

@@ -24,6 +24,8 @@ def build_both(pos, low, high, periodic, n_leaf=10.0, alive=None, variables=None
         p.set_option("record_aos", 1 if two_level == "records" else 0)
         p.set_option("stage_records", 0 if two_level == "direct" else 1)
         p.set_option("gather_slots", 0 if two_level == "direct" else 1)
+        p.set_option("skip_alive_move", 0 if two_level == "direct" else 1)
+        p.set_option("bounds_one_sweep", 0 if two_level == "direct" else 1)
     p.set("position", torch.from_numpy(pos.copy()))
     if alive is not None:
         p.set("alive", torch.from_numpy(np.ascontiguousarray(alive, dtype=np.uint8)))

@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+out=gpurun_out/r2y_stage_records.txt
+echo "== bucket ranges in one sweep (k_boundaries_fill)" | tee -a $out
+timeout 700 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | tee -a $out
+run() {
+  r=$(env "$@" timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['ms_build'], d['ms_matvec'], d['config']['pairs_per_matvec'])")
+  echo "$*: step/build/product ms, pairs: $r" | tee -a $out
+}
+run ABR_BOUNDS_ONE_SWEEP=1
+run ABR_BOUNDS_ONE_SWEEP=0
