@@ -17,6 +17,13 @@ __device__ __forceinline__ uint32_t enforce_one(double *__restrict__ pos, uint8_
   for (int d = 0; d < D; ++d) r0[d] = r[d] = pos[(size_t)p * D + d];
   const uint8_t a0 = alive[p];
   uint8_t a = a0;
+  // the common case first: a particle already inside [bmin, bmax) in every dimension (NaN and infinities
+  // fail the comparisons) is neither wrapped nor killed nor written back — 2 D comparisons instead of the
+  // general path's finite test, wrap loops and write-back checks
+  bool inside = true;
+#pragma unroll
+  for (int d = 0; d < D; ++d) inside = inside && (r[d] >= g.bmin[d]) && (r[d] < g.bmax[d]);
+  if (!inside) {
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     if (!isfinite(r[d])) {
@@ -40,6 +47,7 @@ __device__ __forceinline__ uint32_t enforce_one(double *__restrict__ pos, uint8_
   for (int d = 0; d < D; ++d)
     if (__double_as_longlong(r[d]) != __double_as_longlong(r0[d])) pos[(size_t)p * D + d] = r[d];
   if (a != a0) alive[p] = a;
+  }
   uint32_t key = g.key_bound;
   if (a) {
     int v[D];
