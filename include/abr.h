@@ -86,7 +86,14 @@ int abr_check_async(abr_handle h);
 /* Tuning knobs: "two_level_min_n" — particle count from which abr_update_positions uses
  * the two-level (partition + bin-local sort) build; "stage_records" — 1 (default): its
  * record partition stages each tile's column windows in shared memory with
- * cp.async.bulk when they fit, 0: records read directly from L2; "phased_gather" — 0/1;
+ * cp.async.bulk when they fit, 0: records read directly from L2; "gather_slots" — 1
+ * (default): its final reorder keeps the loads of every column in flight at once;
+ * "skip_alive_move" — 1 (default): the reordered alive column is written as a run of
+ * ones (every particle that survives the reorder is alive) instead of being moved — a
+ * caller that stores other non-zero values in `alive` gets them normalised to 1;
+ * "bounds_one_sweep" — 1 (default): bucket_begin/end from one sweep over the sorted keys;
+ * "record_aos" — 1: binned copy as one record per particle (measured slower, default 0);
+ * "phased_gather" — 0/1;
  * "matvec_variant" — 0: cell-tiled kernel gathering candidates from L2, 1: candidates
  * staged in shared memory with cp.async.bulk; "symmetric" — 1: products with rows ==
  * columns whose functor declares SYMMETRY evaluate every unordered pair once (half
