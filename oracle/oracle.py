@@ -115,7 +115,7 @@ class Oracle:
         self.order = None
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and callable(lib):  # (module globals are gone at interpreter shutdown)
             lib().orc_destroy(self.h)
             self.h = None
 

@@ -8,6 +8,8 @@ Bit-exact for the build and the pair sets, rel. L2 <= 1e-12 for the product vect
 The reference tests the same space case by case (tests/neighbours.h:1252-1327 case lists,
 tests/operators.h:810-933, tests/rbf_interpolation.h:326); this walks through it at random with
 fixed seeds so that a failure reproduces from its case number."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -20,11 +22,12 @@ from util import assert_build_equal, build_both, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
-N_CASES = 240
+N_CASES = int(os.environ.get("ABR_FUZZ_CASES", "240"))      # a longer hunt: ABR_FUZZ_CASES=1000 ABR_FUZZ_SEED=50000 pytest tests/test_gpu_fuzz.py
+SEED0 = int(os.environ.get("ABR_FUZZ_SEED", "9000"))
 
 
 def make_case(case):
-    rng = np.random.default_rng(9000 + case)
+    rng = np.random.default_rng(SEED0 + case)
     D = int(rng.choice([1, 2, 3], p=[0.15, 0.35, 0.5]))
     nmax = {1: 3000, 2: 20000, 3: 30000}[D]
     N = int(np.exp(rng.uniform(0.0, np.log(nmax)))) if rng.random() < 0.5 else int(rng.integers(nmax // 20, nmax))
@@ -85,6 +88,24 @@ def pick_kernel(rng, D, r):
     return K.inv_dist(1e-3 * r), orc.K_INV_DIST, [1e-3 * r], 1
 
 
+def product_agrees(y, y_o, o, rows, okid, params, r, b, BR, npairs, radius_per_row=None):
+    """rel. L2 <= TOL against the oracle.  A sum whose terms cancel (a particle between its own periodic
+    images, a perfect lattice under a force kernel: the exact result is 0) leaves only rounding noise in both
+    vectors; there the error is measured against the size of the terms, sum_j |K_ij b_j|, taken from the
+    oracle's assembled matrix."""
+    if rel_l2(y, y_o) <= TOL:
+        return True
+    if npairs > 5e6:
+        return False
+    row_ptr, col, vals = o.assemble(rows, okid, params, r, BR=BR, radius_per_row=radius_per_row)
+    n_rows = rows.shape[0]
+    vals = np.asarray(vals).reshape(len(col), BR)
+    terms = np.abs(vals * b[col][:, None])
+    mag = np.zeros((n_rows, BR))
+    np.add.at(mag, np.repeat(np.arange(n_rows), np.diff(np.append(row_ptr[:n_rows], len(col)).astype(np.int64))), terms)
+    return np.linalg.norm(y - y_o) <= TOL * np.linalg.norm(mag)
+
+
 @pytest.mark.parametrize("case", range(N_CASES))
 def test_random_configuration(case):
     c = make_case(case)
@@ -130,7 +151,7 @@ def test_random_configuration(case):
     y = (op * bt).cpu().numpy()
     p.set_option("symmetric", 0)
     p.set_option("matvec_variant", 0)
-    assert rel_l2(y, y_o) <= TOL, (tag, form, okid, rel_l2(y, y_o))
+    assert product_agrees(y, y_o, o, out["pos"], okid, params, r, b, BR, npairs), (tag, form, okid, rel_l2(y, y_o))
 
     # a separate row set (no search structure of its own, partly outside the domain)
     if rng.random() < 0.5:
@@ -143,7 +164,7 @@ def test_random_configuration(case):
         test.set("position", torch.from_numpy(rows.copy()))
         G = ab.create_sparse_operator(test, p, r, kern)
         yr = (G * bt).cpu().numpy()
-        assert rel_l2(yr, y_or) <= TOL, (tag, "rows != cols", M, okid, rel_l2(yr, y_or))
+        assert product_agrees(yr, y_or, o, rows, okid, params, r, b, BR, npairs), (tag, "rows != cols", M, okid, rel_l2(yr, y_or))
         # per-row radii (the FRadius overload, src/Operators.h:478-489), zero and beyond-the-box radii included
         if rng.random() < 0.5:
             rpr = rng.uniform(0.0, 1.5 * r, size=M)
@@ -151,4 +172,4 @@ def test_random_configuration(case):
             y_o2, _ = o.sparse_matvec(rows, okid, params, 0.0, b, BR=BR, BC=1, radius_per_row=rpr)
             G2 = ab.create_sparse_operator(test, p, rpr, kern)
             y2 = (G2 * bt).cpu().numpy()
-            assert rel_l2(y2, y_o2) <= TOL, (tag, "per-row radius", M, okid, rel_l2(y2, y_o2))
+            assert product_agrees(y2, y_o2, o, rows, okid, params, 0.0, b, BR, npairs, radius_per_row=rpr), (tag, "per-row radius", M, okid, rel_l2(y2, y_o2))
