@@ -497,10 +497,10 @@ def run_ours(args):
     share = ms_mv / ms_per_step
     roofline = {"bound": "hbm", "kernel": f"abr::tiled_kernel<3, {wl.kernel_name}> (sparse matvec, dominant kernel of the step: {100 * share:.0f} % of it)",
                 "achieved": mv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": mv_gbs / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=32M (profiles/r1y_ncu_tiled_kernel_v9_summary.txt)
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=32M (profiles/r2z_ncu_tiled_kernel_summary.txt)
                 "traffic": 2.345e9 if (n == 32_000_000 and wl.cloud == "uniform") else None, "algorithmic_bytes": mv_bytes, "peak_source": peak_src,
                 "note": "the product is instruction-issue / LSU bound, not HBM bound (arithmetic intensity >> 6 flop/B, SURVEY §8d; DESIGN.md §4.2): "
-                        "see roofline_fp64 and profiles/r1y_ncu_tiled_kernel_v9_summary.txt (11.5 G warp instructions per launch, issue slots 73 % busy, "
+                        "see roofline_fp64 and profiles/r2z_ncu_tiled_kernel_summary.txt (11.5 G warp instructions per launch, issue slots 73 % busy, "
                         "LSU data pipe 74 %). algorithmic bytes = N(8D+8BR)+N(8D+8BC)+8C; achieved uses the product time incl. the 0.3 ms record-packing pass"}
     roofline_fp64 = {"bound": "fp64", "achieved": mv_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": mv_tflops / fp64_peak,
                      "peak_source": "measured here (abr_probe_fp64_peak, DFMA loop)", "flops_per_pair": wl.flops_per_pair,
